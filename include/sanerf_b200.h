@@ -1,0 +1,180 @@
+/*
+ * sanerf_b200.h — C ABI of libsanerf_b200.so, the sm_100a (B200) implementation of the
+ * Segment-Anything-NeRF render hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (passed as
+ * `void*`, i.e. a `cudaStream_t`; NULL = legacy default stream) and returns an `int`
+ * status (SANERF_OK == 0).  Nothing here allocates, frees or synchronises: the caller
+ * owns every buffer (same ownership contract as the reference's pybind functions, which
+ * write into caller-allocated tensors — SURVEY §8 b3).  All kernels are enqueued on the
+ * given stream and are safe to capture into a CUDA graph.
+ *
+ * Each function cites the reference interface it replaces (paths relative to the
+ * reference checkout).  The Python shims `_gridencoder`, `_shencoder`, `_freqencoder`
+ * in `segment-anything-nerf_b200/` re-export the reference's 8 pybind names on top of
+ * these symbols; INTEGRATION.md shows the binding.
+ */
+#ifndef SANERF_B200_H_
+#define SANERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SANERF_ABI_VERSION 3
+
+#if defined(__GNUC__)
+#define SANERF_API __attribute__((visibility("default")))
+#else
+#define SANERF_API
+#endif
+
+/* status codes */
+enum {
+    SANERF_OK = 0,
+    SANERF_ERR_INVALID_ARG = 1,  /* unsupported D / C / dtype / layout (reference: std::runtime_error, gridencoder.cu:392,409) */
+    SANERF_ERR_NULL_POINTER = 2, /* a required pointer is NULL (reference: TORCH_CHECK, gridencoder.cu:468-484) */
+    SANERF_ERR_CUDA = 3,         /* kernel launch failed; see sanerf_last_error() */
+    SANERF_ERR_MISALIGNED = 4    /* a buffer violates the documented alignment */
+};
+
+/* element types of tables / encoder outputs */
+enum { SANERF_F32 = 0, SANERF_F16 = 1 };
+
+/* layouts of the per-level feature tensor */
+enum {
+    SANERF_LAYOUT_LBC = 0, /* [L, B, C]  — what the reference kernel writes (gridencoder.cu:103) */
+    SANERF_LAYOUT_BLC = 1  /* [B, L*C]   — what GridEncoder.forward returns after its permute copy (grid.py:63) */
+};
+
+SANERF_API int sanerf_abi_version(void);
+/* Thread-local description of the last non-OK status returned on this thread. */
+SANERF_API const char* sanerf_last_error(void);
+SANERF_API const char* sanerf_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------
+ * Multiresolution hash / tiled grid encoder.
+ * Replaces: grid_encode_forward / grid_encode_backward / grad_total_variation /
+ * grad_weight_decay (gridencoder/src/gridencoder.h:12-16, gridencoder.cu:467-713).
+ *
+ *  inputs      f32 [B, D]           coordinates already mapped to [0,1]
+ *  embeddings  T   [rows, C]        T = f32 or f16 (dtype)
+ *  offsets     i32 [L+1]            level row offsets (grid.py:124-134)
+ *  outputs     T   [L,B,C] or [B,L*C] (out_layout)
+ *  dy_dx       T   [B, L*D*C] or NULL
+ *  S = log2(per_level_scale), H = base resolution, gridtype 0 hash / 1 tiled,
+ *  interp 0 linear / 1 smoothstep.  D in {2,3,4,5}, C in {1,2,4,8,16,32}.
+ *  Levels >= max_level are left untouched unless zero_tail != 0 (then written as 0).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                               void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                               uint32_t max_level, float S, uint32_t H, void* dy_dx,
+                               uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                               int out_layout, int zero_tail, void* stream);
+
+/*  grad             T [L,B,C] or [B,L*C] (grad_layout)
+ *  grad_embeddings  T [rows, C]  accumulated into (caller zero-fills; grid.py:83)
+ *  dy_dx / grad_inputs  both NULL, or T [B, L*D*C] / T [B, D] (grad_inputs is overwritten)
+ */
+SANERF_API int sanerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                const int32_t* offsets, void* grad_embeddings, uint32_t B,
+                                uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S,
+                                uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype,
+                                int align_corners, uint32_t interp, int dtype, int grad_layout,
+                                void* stream);
+
+/* In-place total-variation gradient on `grad` (gridencoder.cu:525-668). inputs T [B, D] in [0,1]. */
+SANERF_API int sanerf_grad_total_variation(const void* inputs, const void* embeddings, void* grad,
+                                const int32_t* offsets, float weight, uint32_t B, uint32_t D,
+                                uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                int align_corners, int dtype, void* stream);
+
+/* In-place level-mean weight decay: grad += 2*w*param/level_rows (gridencoder.cu:670-713). B = rows. */
+SANERF_API int sanerf_grad_weight_decay(const void* embeddings, void* grad, const int32_t* offsets,
+                             float weight, uint32_t B, uint32_t C, uint32_t L, int dtype,
+                             void* stream);
+
+/* Debug / parity entry point (no reference equivalent — SURVEY §8 c7): for every sample,
+ * level < L and corner < 2^D write the table row (relative to the level's offset) the
+ * forward kernel would read, plus the level geometry computed on the device.
+ *  rows      u32 [B, L, 2^D]
+ *  geometry  u32 [L, 4] = {resolution, level_rows, uses_hash, covered_dims} (may be NULL)
+ */
+SANERF_API int sanerf_grid_dump_indices(const float* inputs, const int32_t* offsets, uint32_t* rows,
+                             uint32_t* geometry, uint32_t B, uint32_t D, uint32_t L, float S,
+                             uint32_t H, uint32_t gridtype, int align_corners, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spherical-harmonics encoder, degree 1..8 (shencoder/src/shencoder.h:9-10, shencoder.cu:27-439).
+ *  inputs f32 [B,3] (unit vectors), outputs f32 [B, deg*deg], dy_dx f32 [B, 3*deg*deg] or NULL.
+ * `ray_stride` > 0 broadcasts: sample b uses inputs[b / ray_stride] (one direction per ray;
+ * the reference re-evaluates the same direction T times, network.py:237). 0/1 = plain.
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D,
+                             uint32_t degree, float* dy_dx, uint32_t ray_stride, void* stream);
+/* grad_inputs[b,d] += sum_ch grad[b,ch]*dy_dx[b,d,ch]  (accumulates, like shencoder.cu:378) */
+SANERF_API int sanerf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D,
+                              uint32_t degree, const float* dy_dx, float* grad_inputs,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Frequency (positional) encoder (freqencoder/src/freqencoder.h:7,10, freqencoder.cu:30-129).
+ *  inputs f32 [B,D], outputs f32 [B,C], C = D + 2*D*deg, column order [x, sin 2^0 x, cos 2^0 x, ...]
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg,
+                               uint32_t C, float* outputs, void* stream);
+SANERF_API int sanerf_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D,
+                                uint32_t deg, uint32_t C, float* grad_inputs, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * trunc_exp activation (activation.py:5-18): y = exp(x); dx = g * exp(clamp(x,-15,15)).
+ * `stride`/`offset` let it read column `offset` of a [n, stride] matrix (network.py:226 takes
+ * channel 0 of the 16-wide grid_mlp output) — pass stride=1, offset=0 for a flat vector.
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_trunc_exp_forward(const float* x, float* y, uint64_t n, uint32_t stride,
+                             uint32_t offset, void* stream);
+SANERF_API int sanerf_trunc_exp_backward(const float* g, const float* x, float* dx, uint64_t n,
+                              uint32_t stride, uint32_t offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-ray front-to-back compositing (nerf/renderer.py:309-338, :377-383, :453).
+ *
+ * Samples are PACKED: ray r owns samples [ray_offsets[r], ray_offsets[r+1]).  The reference's
+ * dense [N,T] block is the special case ray_offsets == NULL with uniform count T.
+ *
+ *  sigmas, deltas, ts   f32 [M]        density, interval length, mid-point distance
+ *  feats                f32 [M, C]     per-sample channels (colour feature, SAM feature, ...); C may be 0
+ *  last_sample_opaque   != 0: the last sample of each ray gets delta*sigma := +inf (renderer.py:314-316)
+ *  t_thresh             early ray termination: samples whose incoming transmittance < t_thresh
+ *                       get weight 0 (0 disables; the reference never terminates — SURVEY §8 c5)
+ * outputs:
+ *  weights      f32 [M]      alpha_i * T_i with NaN -> 0 (renderer.py:318-326)
+ *  weights_sum  f32 [N]      sum_i w_i
+ *  depth        f32 [N]      sum_i w_i t_i
+ *  out          f32 [N, C]   sum_i w_i feats_i
+ *  n_alive      i32 [N]      number of samples with T_i >= t_thresh (may be NULL)
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_composite_forward(const float* sigmas, const float* deltas, const float* ts,
+                             const float* feats, const int32_t* ray_offsets, uint32_t N,
+                             uint32_t T, uint32_t C, int last_sample_opaque, float t_thresh,
+                             float* weights, float* weights_sum, float* depth, float* out,
+                             int32_t* n_alive, void* stream);
+
+/* Backward of the above.  Incoming gradients (any may be NULL = zero):
+ *  g_weights [M], g_weights_sum [N], g_depth [N], g_out [N,C]
+ * Produces grad_sigmas [M] and grad_feats [M,C] (grad_feats may be NULL).  deltas / ts carry no
+ * gradient (bins are detached, renderer.py:275).
+ */
+SANERF_API int sanerf_composite_backward(const float* sigmas, const float* deltas, const float* ts,
+                              const float* feats, const int32_t* ray_offsets, uint32_t N,
+                              uint32_t T, uint32_t C, int last_sample_opaque, float t_thresh,
+                              const float* weights, const float* g_weights,
+                              const float* g_weights_sum, const float* g_depth, const float* g_out,
+                              float* grad_sigmas, float* grad_feats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SANERF_B200_H_ */

@@ -1,0 +1,82 @@
+// Shared helpers for libsanerf_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "sanerf_b200.h"
+
+namespace sanerf {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+template <typename T>
+__host__ __device__ constexpr T div_up(T a, T b) { return (a + b - 1) / b; }
+
+// thread-local error text returned by sanerf_last_error()
+char* error_buffer();
+int fail(int status, const char* fmt, ...);
+
+// Every launcher ends with this: surfaces launch-configuration errors (never syncs).
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SANERF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    return SANERF_OK;
+}
+
+#define SANERF_REQUIRE_PTR(p)                                                        \
+    do {                                                                             \
+        if ((p) == nullptr) return ::sanerf::fail(SANERF_ERR_NULL_POINTER, #p " is NULL"); \
+    } while (0)
+
+// ---- vector reductions into global memory (sm_90+: red.global.add.v2/v4.f32) -------------
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v2_f32(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b),
+                 "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f16x2(__half* addr, __half2 v) {
+    uint32_t u = *reinterpret_cast<uint32_t*>(&v);
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(u) : "memory");
+}
+__device__ __forceinline__ void red_add_v2_f16x2(__half* addr, __half2 a, __half2 b) {
+    uint32_t ua = *reinterpret_cast<uint32_t*>(&a), ub = *reinterpret_cast<uint32_t*>(&b);
+    asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(ua), "r"(ub)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f16x2(__half* addr, __half2 a, __half2 b, __half2 c,
+                                                 __half2 d) {
+    uint32_t ua = *reinterpret_cast<uint32_t*>(&a), ub = *reinterpret_cast<uint32_t*>(&b);
+    uint32_t uc = *reinterpret_cast<uint32_t*>(&c), ud = *reinterpret_cast<uint32_t*>(&d);
+    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(ua),
+                 "r"(ub), "r"(uc), "r"(ud)
+                 : "memory");
+}
+
+// read-only 128-bit / 64-bit loads through the non-coherent path
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg_f2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// streaming (evict-first) stores for write-once outputs
+__device__ __forceinline__ void st_cs_f4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace sanerf
