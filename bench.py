@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the Segment-Anything-NeRF render hot path on B200 (contract: see the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload rgb|sam|frame]
+
+One "step" of the default workload (BASELINE.json configs[1]) is one stage-1 RGB training step:
+8192 synthetic rays per GPU, 128/64/32 proposal/final samples (2^18 final samples), random-init tables of
+the reference's shapes, forward + backward + gradient all-reduce (N>1) + Adam.  `value` is whole-job
+rays/s with the rays already resident in HBM; `e2e` is the same step driven from pinned HOST buffers
+through the public API (H2D copy of rays + targets and D2H read of the loss inside the timed region).
+
+`--impl reference` times the reference's own algorithm for this path restated in pure torch
+(oracle/render_torch.py — the "pure-torch reference path" of BASELINE.json) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "segment-anything-nerf_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train rays/s (RGB fwd+bwd+Adam step)"
+N_RAYS = 8192                     # steady-state rays per step: 2^18 points / 32 final samples
+NUM_STEPS = (128, 64, 32)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def synthetic_rays(n, device, seed):
+    """origins U(-0.5,0.5)^3, unit directions, U(0,1) RGB targets."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    o = torch.rand(n, 3, generator=g) - 0.5
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    rgb = torch.rand(n, 3, generator=g)
+    return o.to(device), d.to(device), rgb.to(device)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the pure-torch restatement of the reference path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import render_torch as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    n_rays = args.ref_rays
+    model = R.NeRFNetworkRef().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, eps=1e-15)
+    o, d, rgb = synthetic_rays(n_rays, "cpu", 1234)
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss, _ = model.rgb_loss(o, d, rgb, update_proposal=True, perturb=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n_rays * args.steps / dt
+    sample = f"{n_rays} rays/step x {args.steps} steps of the same RGB training step (128/64/32 samples, same tables)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "configs[1]: stage-1 RGB training step, 8192 rays x (128,64,32) samples, L16 T2^19 F2 "
+                               "main grid + 2 proposal grids, fwd+bwd+Adam", "rays_per_step": n_rays,
+                   "device": "cpu", "threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(budget_s=20.0):
+    """Bounded sample of the same workload through the oracle port on the host cores (rank 0, N=1 only)."""
+    from oracle import render_torch as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    n_rays = 512
+    model = R.NeRFNetworkRef().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, eps=1e-15)
+    o, d, rgb = synthetic_rays(n_rays, "cpu", 1234)
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss, _ = model.rgb_loss(o, d, rgb, update_proposal=True, perturb=True)
+        loss.backward()
+        opt.step()
+
+    step()  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while n < 2 or (time.perf_counter() - t0 < budget_s and n < 50):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n_rays * n / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps x {n_rays} rays of the same RGB training step (oracle/render_torch.py, fp32, "
+                      f"{dt:.1f} s of CPU work)"}
+
+
+# ----------------------------------------------------------------------------------------------
+def algorithmic_bytes_encode(B, L, C, D=3, table_bytes=4, out_bytes=4):
+    """per sample 4*D + L*2^D*C*s_p + L*C*s_o."""
+    return B * (4 * D + L * (1 << D) * C * table_bytes + L * C * out_bytes)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from nerf.network import NeRFNetwork
+    from sanerf_b200 import _lib
+    from sanerf_b200.train import RGBTrainer, default_opt
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    torch.manual_seed(0)                      # identical replicas on every rank
+    model = NeRFNetwork(default_opt()).to(dev)
+    trainer = RGBTrainer(model, lr=1e-2, iters=20000, world_size=world)
+
+    n_sets = 4                                 # rotate over a few synthetic ray batches
+    dev_sets = [synthetic_rays(N_RAYS, dev, 1234 + rank * 100 + i) for i in range(n_sets)]
+    host_sets = [tuple(t.cpu().pin_memory() for t in s) for s in dev_sets]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, n_steps, watch=None, pred=None):
+        evs = []
+        _lib.stats.reset(watch, pred)
+        barrier()
+        for i in range(n_steps):
+            flush.fill_(float(i))                                  # evict L2 between timed iterations
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step_fn(i)
+            e.record()
+            evs.append((s, e))
+        barrier()
+        total_ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.stats.count
+
+    def step_device(i):
+        o, d, rgb = dev_sets[i % n_sets]
+        trainer.step(o, d, rgb)
+
+    last_loss = [0.0]
+
+    def step_e2e(i):
+        ho, hd, hrgb = host_sets[i % n_sets]
+        o, d, rgb = (t.to(dev, non_blocking=True) for t in (ho, hd, hrgb))
+        last_loss[0] = trainer.step(o, d, rgb).item()              # D2H read of the step's result
+
+    for i in range(args.warmup):
+        step_device(i)
+    # dominant kernel: proposal-level-0 grid encode (1,048,576 samples x L5) -- picked from the ncu launch list
+    pred = lambda info: info.get("L") == 5 and info.get("B") == N_RAYS * NUM_STEPS[0]  # noqa: E731
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches = timed_loop(step_device, args.steps, "grid_encode_forward", pred)
+    clocks = sampler.stop() if rank == 0 else {}
+    spans = _lib.stats.durations_ms()
+    for i in range(min(3, args.warmup)):
+        step_e2e(i)
+    e2e_ms, _ = timed_loop(step_e2e, args.steps)
+
+    if rank != 0:
+        return
+    ms_per_step = total_ms / args.steps
+    value = world * N_RAYS * args.steps / (total_ms / 1e3)
+    e2e_value = world * N_RAYS * args.steps / (e2e_ms / 1e3)
+    peak, peak_src = load_peaks()
+    roofline = None
+    if spans:
+        B = N_RAYS * NUM_STEPS[0]
+        alg = algorithmic_bytes_encode(B, 5, 2)
+        avg_ms = sum(ms for ms, _ in spans) / len(spans)
+        achieved = alg / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "grid_forward_kernel<float,3,2,...> (proposal level 0, B=1048576, L=5)",
+                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                    "avg_launch_ms": avg_ms, "launches_timed": len(spans)}
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "configs[1]: stage-1 RGB training step, 8192 rays/GPU x (128,64,32) samples "
+                               "(2^18 final samples), L16 T2^19 F2 main grid + 2 L5 T2^17 proposal grids, "
+                               "fwd+bwd+grad all-reduce+Adam, random-init tables",
+                   "rays_per_gpu_per_step": N_RAYS, "l2": "flushed (256 MiB write) between timed iterations",
+                   "parallelism": f"ray-sharded data parallel x{world}"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": 3 * N_RAYS * 3 * 4, "d2h_bytes_per_step": 4, "last_loss": last_loss[0]},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,51 +31,76 @@ PRIMES = [1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 21652197
 
 
 # ----------------------------------------------------------------------------- encoders
+def _level_corners(x, level, offs, S, H, D, gridtype, align_corners, interp):
+    """Rows (absolute) [2^D, B] and weights [2^D, B] of every corner of one level (gridencoder.cu:132-186)."""
+    dev = x.device
+    res, rows, mult, hashed, _ = grid_np.level_geometry(offs, level, S, H, D, gridtype)
+    if align_corners:  # :144-146
+        pos = x * float(res - 1)
+        pg = torch.clamp(torch.floor(pos), max=res - 2)
+    else:  # :148-149
+        pos = torch.clamp(x * float(res) - 0.5, min=0.0, max=float(res - 1))
+        pg = torch.floor(pos)
+    frac = pos - pg
+    if interp == 1:
+        frac = frac * frac * (3.0 - 2.0 * frac)
+    pg = pg.to(torch.int64)
+    # all 2^D corners at once: bit d of corner k selects the upper cell border in dimension d (:171-186)
+    bits = torch.tensor([[(k >> d) & 1 for d in range(D)] for k in range(1 << D)], device=dev)   # [2^D, D]
+    up = bits.bool().unsqueeze(1)                                                                 # [2^D, 1, D]
+    coord = torch.where(up, torch.clamp(pg + 1, max=res - 1).unsqueeze(0), pg.unsqueeze(0))      # [2^D, B, D]
+    wd = torch.where(up, frac.unsqueeze(0), (1 - frac).unsqueeze(0))                              # [2^D, B, D]
+    w = wd[..., 0]
+    for d in range(1, D):
+        w = w * wd[..., d]
+    terms = (coord * torch.tensor([int(m) for m in mult], device=dev)) & 0xFFFFFFFF
+    idx = terms[..., 0]
+    for d in range(1, D):
+        idx = (idx ^ terms[..., d]) if hashed else ((idx + terms[..., d]) & 0xFFFFFFFF)
+    return idx % rows + offs[level], w  # :78, :101
+
+
+class _GridEncodeTorch(torch.autograd.Function):
+    """kernel_grid / kernel_grid_backward (gridencoder.cu:82-202, 252-349) with torch gathers and
+    ``index_add_`` scatters; the integer index math runs once, outside autograd."""
+
+    @staticmethod
+    def forward(ctx, x01, table, offs, S, H, gridtype, align_corners, interp, max_level):
+        B, D = x01.shape
+        C = table.shape[1]
+        L = len(offs) - 1
+        x = x01.to(torch.float32)
+        keep = ~((x < 0) | (x > 1)).any(dim=1)  # :106-112
+        out = torch.zeros(B, L, C, dtype=table.dtype, device=x.device)
+        saved = []
+        for level in range(max_level):
+            idx, w = _level_corners(x, level, offs, S, H, D, gridtype, align_corners, interp)
+            w = w * keep.to(w.dtype)  # :114-118 (forward zero) and :279-284 (gradient dropped)
+            out[:, level] = (w.unsqueeze(-1).to(table.dtype) * table[idx]).sum(0)  # :188-192
+            saved.append((idx, w))
+        ctx.saved = saved
+        ctx.table_shape, ctx.table_dtype = table.shape, table.dtype
+        return out.reshape(B, L * C)
+
+    @staticmethod
+    def backward(ctx, grad):
+        B = grad.shape[0]
+        C = ctx.table_shape[1]
+        g = grad.reshape(B, -1, C)
+        gt = torch.zeros(ctx.table_shape, dtype=ctx.table_dtype, device=grad.device)
+        for level, (idx, w) in enumerate(ctx.saved):  # :313-347
+            upd = w.unsqueeze(-1).to(g.dtype) * g[:, level].unsqueeze(0)
+            gt.index_add_(0, idx.reshape(-1), upd.reshape(-1, C))
+        return None, gt, None, None, None, None, None, None, None
+
+
 def grid_encode(x01, table, offsets, S, H, gridtype=0, align_corners=False, interp=0, max_level=None):
-    """Differentiable (w.r.t. ``table``) torch restatement of kernel_grid (gridencoder.cu:82-202) and
-    the permute of grid.py:63.  x01 [B,D] in [0,1]; returns [B, L*C] in table dtype."""
-    B, D = x01.shape
-    C = table.shape[1]
+    """Differentiable (w.r.t. ``table``) torch restatement of the grid encoder and the permute of grid.py:63.
+    x01 [B,D] in [0,1]; returns [B, L*C] in table dtype."""
     offs = [int(v) for v in offsets]
     L = len(offs) - 1
     max_level = L if max_level is None else min(max_level, L)
-    dev = x01.device
-    x = x01.to(torch.float32)
-    oob = ((x < 0) | (x > 1)).any(dim=1)  # :106-112
-    outs = []
-    for level in range(L):
-        if level >= max_level:
-            outs.append(torch.zeros(B, C, dtype=table.dtype, device=dev))
-            continue
-        res, rows, mult, hashed, _ = grid_np.level_geometry(offs, level, S, H, D, gridtype)
-        if align_corners:  # :144-146
-            pos = x * float(res - 1)
-            pg = torch.clamp(torch.floor(pos), max=res - 2)
-        else:  # :148-149
-            pos = torch.clamp(x * float(res) - 0.5, min=0.0, max=float(res - 1))
-            pg = torch.floor(pos)
-        frac = pos - pg
-        if interp == 1:
-            frac = frac * frac * (3.0 - 2.0 * frac)
-        pg = pg.to(torch.int64)
-        acc = torch.zeros(B, C, dtype=table.dtype, device=dev)
-        for k in range(1 << D):  # :171-192
-            w = torch.ones(B, dtype=torch.float32, device=dev)
-            idx = torch.zeros(B, dtype=torch.int64, device=dev)
-            for d in range(D):
-                if (k >> d) & 1:
-                    w = w * frac[:, d]
-                    coord = torch.clamp(pg[:, d] + 1, max=res - 1)
-                else:
-                    w = w * (1 - frac[:, d])
-                    coord = pg[:, d]
-                term = (coord * int(mult[d])) & 0xFFFFFFFF
-                idx = (idx ^ term) if hashed else ((idx + term) & 0xFFFFFFFF)
-            idx = idx % rows + offs[level]  # :78, :101
-            acc = acc + w.unsqueeze(1).to(table.dtype) * table[idx]
-        acc = torch.where(oob.unsqueeze(1), torch.zeros_like(acc), acc)  # :114-118
-        outs.append(acc)
-    return torch.stack(outs, dim=1).reshape(B, L * C)
+    return _GridEncodeTorch.apply(x01, table, offs, S, H, gridtype, align_corners, interp, max_level)
 
 
 class GridEncoderRef(nn.Module):

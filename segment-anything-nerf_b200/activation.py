@@ -18,7 +18,7 @@ class _TruncExp(Function):
         xc = x.contiguous()
         y = torch.empty_like(xc)
         lib = _lib.load()
-        with torch.cuda.device(xc.device):
+        with torch.cuda.device(xc.device), _lib.stats.span("trunc_exp_forward", n=xc.numel()):
             rc = lib.sanerf_trunc_exp_forward(xc.data_ptr(), y.data_ptr(), xc.numel(), 1, 0,
                                               _lib.current_stream(xc.device))
         _lib.check(rc, "trunc_exp_forward")
@@ -32,7 +32,7 @@ class _TruncExp(Function):
         g = g.contiguous()
         dx = torch.empty_like(x)
         lib = _lib.load()
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _lib.stats.span("trunc_exp_backward", n=x.numel()):
             rc = lib.sanerf_trunc_exp_backward(g.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), 1, 0,
                                                _lib.current_stream(x.device))
         _lib.check(rc, "trunc_exp_backward")

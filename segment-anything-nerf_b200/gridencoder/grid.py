@@ -70,7 +70,8 @@ class _GridEncode(Function):
         outputs = torch.empty(B, L * C, device=inputs.device, dtype=table.dtype)
         dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=table.dtype) if calc_grad_inputs else None
         lib = _lib.load()
-        with torch.cuda.device(inputs.device):
+        with torch.cuda.device(inputs.device), _lib.stats.span("grid_encode_forward", B=B, L=L, C=C, D=D,
+                                                               half=table.dtype == torch.float16):
             rc = lib.sanerf_grid_encode_forward(
                 inputs.data_ptr(), table.data_ptr(), offsets.data_ptr(), outputs.data_ptr(), B, D, C, L,
                 max_level, S, H, _lib.ptr(dy_dx), int(gridtype), int(bool(align_corners)), int(interpolation),
@@ -93,7 +94,8 @@ class _GridEncode(Function):
         grad_table = torch.zeros_like(table)
         grad_inputs = torch.empty(B, D, device=inputs.device, dtype=table.dtype) if dy_dx is not None else None
         lib = _lib.load()
-        with torch.cuda.device(inputs.device):
+        with torch.cuda.device(inputs.device), _lib.stats.span("grid_encode_backward", B=B, L=L, C=C, D=D,
+                                                               half=table.dtype == torch.float16):
             rc = lib.sanerf_grid_encode_backward(
                 grad.data_ptr(), inputs.data_ptr(), table.data_ptr(), offsets.data_ptr(), grad_table.data_ptr(),
                 B, D, C, L, max_level, S, H, _lib.ptr(dy_dx), _lib.ptr(grad_inputs), gridtype, int(align_corners),

@@ -94,6 +94,51 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what}: {kind}: {msg}")
 
 
+class LaunchStats:
+    """Counts C-ABI kernel launches and, when asked, brackets the launches of ONE named entry point with CUDA
+    events on the launching stream (bench.py uses this for the roofline of the dominant kernel)."""
+
+    def __init__(self):
+        self.count = 0
+        self.watch = None          # (name, predicate) or None
+        self.spans = []            # [(start_event, end_event, info)]
+
+    def reset(self, watch=None, predicate=None):
+        self.count = 0
+        self.watch = (watch, predicate) if watch else None
+        self.spans = []
+
+    def span(self, name, **info):
+        return _Span(self, name, info)
+
+    def durations_ms(self):
+        return [(s.elapsed_time(e), info) for s, e, info in self.spans]
+
+
+class _Span:
+    def __init__(self, stats, name, info):
+        self.stats, self.name, self.info, self.ev = stats, name, info, None
+
+    def __enter__(self):
+        st = self.stats
+        st.count += 1
+        if st.watch and st.watch[0] == self.name and (st.watch[1] is None or st.watch[1](self.info)):
+            import torch
+
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            self.stats.spans.append((self.ev[0], self.ev[1], self.info))
+        return False
+
+
+stats = LaunchStats()
+
+
 def ptr(t):
     """Device pointer of a tensor (or NULL for None)."""
     return None if t is None else t.data_ptr()

@@ -44,7 +44,7 @@ class _Composite(Function):
         out = torch.empty(N, C, device=dev, dtype=torch.float32)
         n_alive = torch.empty(N, device=dev, dtype=torch.int32)
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _lib.stats.span("composite_forward", N=N, T=T, C=C):
             rc = lib.sanerf_composite_forward(
                 sigmas.data_ptr(), deltas.data_ptr(), ts.data_ptr(), _lib.ptr(feats), _lib.ptr(ray_offsets),
                 N, T, C, int(bool(last_sample_opaque)), float(t_thresh), weights.data_ptr(),
@@ -68,7 +68,7 @@ class _Composite(Function):
         need_feats = C > 0 and ctx.needs_input_grad[3]
         grad_feats = torch.empty_like(feats) if need_feats else None
         lib = _lib.load()
-        with torch.cuda.device(sigmas.device):
+        with torch.cuda.device(sigmas.device), _lib.stats.span("composite_backward", N=N, T=T, C=C):
             rc = lib.sanerf_composite_backward(
                 sigmas.data_ptr(), deltas.data_ptr(), ts.data_ptr(), _lib.ptr(feats), _lib.ptr(ray_offsets),
                 N, T, C, int(opaque), t_thresh, weights.data_ptr(), _lib.ptr(g_weights), _lib.ptr(g_weights_sum),

@@ -1,0 +1,154 @@
+"""Training / inference steps of the render hot path, single- and multi-GPU.
+
+Stage-1 RGB step = what the reference's ``Trainer.train_step`` + ``train_one_epoch`` do per iteration
+(nerf/utils.py:897-930, 1811-1836): render with jittered proposal sampling, MSE + proposal + distortion
+losses, backward, Adam(eps=1e-15).  Stage-2 SAM step = the ``with_sam`` branch (nerf/utils.py:1095-1106) on
+frozen stage-1 parameters with a synthetic [64,64,256] regression target.
+
+Multi-GPU: one process per GPU, rays sharded by rank, full parameter replica, ONE NCCL
+all-reduce (sum) over a flat fp32 gradient bucket per step, identical Adam updates on every rank.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def default_opt(**overrides):
+    """The flags the shipped system actually runs with (main.py:222-226 hard overrides + defaults)."""
+    opt = types.SimpleNamespace(
+        bound=128, contract=True, min_near=0.2, density_thresh=10, num_steps=[128, 64, 32],
+        background="last_sample", with_sam=False, with_mask=False, sum_after_mlp=False,
+        sam_use_view_direction=True, mask_mlp_type="default", lambda_proposal=1.0, lambda_distort=0.02,
+        max_ray_batch=16384, num_rays=4096, num_points=2 ** 18, lr=1e-2, iters=20000)
+    opt.__dict__.update(overrides)
+    return opt
+
+
+class FlatGradBucket:
+    """All trainable gradients as views of one flat fp32 buffer, so the data-parallel exchange is a single
+    all-reduce (57 MB in stage 1, 170 MB in stage 2 — SURVEY §5)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, device=ref.device, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, world_size):
+        if world_size > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(world_size)
+
+
+class RGBTrainer:
+    """Stage-1 step: ``step(rays_o, rays_d, gt_rgb) -> loss`` (device tensors), with optional DDP-style sharding."""
+
+    def __init__(self, model, lr=1e-2, iters=20000, world_size=1):
+        self.model = model.train()
+        self.world_size = world_size
+        self.global_step = 0
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.bucket = FlatGradBucket(params)
+        # Adam(eps=1e-15) + LambdaLR 0.1**min(iter/iters,1)  (main.py:296,312-313)
+        self.optimizer = torch.optim.Adam(model.get_params(lr), eps=1e-15, fused=True)
+        self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lambda it: 0.1 ** min(it / iters, 1))
+
+    def loss(self, rays_o, rays_d, gt_rgb, update_proposal=True, perturb=True):
+        out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=perturb,
+                                update_proposal=update_proposal)
+        loss = F.mse_loss(out["image"], gt_rgb, reduction="none").mean()
+        if "proposal_loss" in out:
+            loss = loss + self.model.opt.lambda_proposal * out["proposal_loss"]
+        if "distort_loss" in out:
+            loss = loss + self.model.opt.lambda_distort * out["distort_loss"]
+        return loss, out
+
+    def step(self, rays_o, rays_d, gt_rgb):
+        self.global_step += 1
+        update_proposal = self.global_step <= 3000 or self.global_step % 5 == 0   # nerf/utils.py:910-911
+        self.bucket.zero()
+        loss, _ = self.loss(rays_o, rays_d, gt_rgb, update_proposal)
+        loss.backward()
+        self.bucket.all_reduce_mean(self.world_size)
+        self.optimizer.step()
+        self.scheduler.step()
+        return loss.detach()
+
+
+class SAMTrainer:
+    """Stage-2 step on frozen stage-1 parameters: render the [h,w] low-resolution rays' 256-d feature map and
+    regress a target feature map (nerf/utils.py:1095-1106; the ViT-H target is replaced by a given tensor)."""
+
+    def __init__(self, model, lr=1e-2, iters=5000, world_size=1):
+        assert model.opt.with_sam
+        self.model = model.train()
+        self.world_size = world_size
+        trainable = set()
+        for m in (model.s_grid, model.samvit_mlp):
+            trainable.update(id(p) for p in m.parameters())
+        for p in model.parameters():                      # main.py:255-262: freeze what stage 1 trained
+            p.requires_grad_(id(p) in trainable)
+        self.bucket = FlatGradBucket([p for p in model.parameters() if p.requires_grad])
+        groups = [{"params": [p for p in m.parameters()], "lr": lr} for m in (model.s_grid, model.samvit_mlp)]
+        self.optimizer = torch.optim.Adam(groups, eps=1e-15, fused=True)
+        self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lambda it: 0.1 ** min(it / iters, 1))
+
+    def step(self, rays_o, rays_d, target, h, w):
+        """target: [1, 256, H_t, W_t]; prediction is bilinearly resized to it (nerf/utils.py:1100-1106)."""
+        self.bucket.zero()
+        out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=False, update_proposal=False,
+                                return_feats=1, H=h, W=w)
+        pred = out["samvit"].permute(2, 0, 1).unsqueeze(0)
+        if pred.shape[-2:] != target.shape[-2:]:
+            pred = F.interpolate(pred, target.shape[-2:], mode="bilinear")
+        loss = F.mse_loss(pred, target)
+        loss.backward()
+        self.bucket.all_reduce_mean(self.world_size)
+        self.optimizer.step()
+        self.scheduler.step()
+        return loss.detach()
+
+
+@torch.no_grad()
+def render_frame(model, rays_o, rays_d, feat_rays_o=None, feat_rays_d=None, h=64, w=64):
+    """Interactive frame (nerf/utils.py:1647-1712): staged full-resolution RGB + depth, plus the low-resolution
+    256-d SAM feature map when feature rays are given."""
+    model.eval()
+    out = model.render(rays_o, rays_d, staged=True, bg_color=1, perturb=False)
+    res = {"image": out["image"], "depth": out["depth"]}
+    if feat_rays_o is not None:
+        f = model.render(feat_rays_o, feat_rays_d, staged=False, bg_color=1, perturb=False, return_feats=1, H=h, W=w)
+        res["samvit"] = f["samvit"]
+    return res
+
+
+def shard_rays(n_total, rank, world_size):
+    """Contiguous [start, stop) slice of ``n_total`` rays / pixels owned by ``rank`` (tiles for inference,
+    ray shards for training); sizes differ by at most one."""
+    base, rem = divmod(n_total, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_frame(local, n_total, rank, world_size):
+    """Inference: every rank renders its tile; one all_gather stitches [rays, C] tensors."""
+    if world_size == 1:
+        return local
+    sizes = [shard_rays(n_total, r, world_size) for r in range(world_size)]
+    longest = max(b - a for a, b in sizes)
+    pad = torch.zeros(longest, *local.shape[1:], device=local.device, dtype=local.dtype)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:b - a] for p, (a, b) in zip(parts, sizes)], dim=0)

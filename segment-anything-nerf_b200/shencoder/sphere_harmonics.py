@@ -23,7 +23,7 @@ class _SHEncode(Function):
         outputs = torch.empty(B, n_out, dtype=inputs.dtype, device=inputs.device)
         dy_dx = torch.empty(B, D * n_out, dtype=inputs.dtype, device=inputs.device) if calc_grad_inputs else None
         lib = _lib.load()
-        with torch.cuda.device(inputs.device):
+        with torch.cuda.device(inputs.device), _lib.stats.span("sh_encode_forward", B=B):
             rc = lib.sanerf_sh_encode_forward(inputs.data_ptr(), outputs.data_ptr(), B, D, int(degree),
                                               _lib.ptr(dy_dx), 0, _lib.current_stream(inputs.device))
         _lib.check(rc, "sh_encode_forward")
