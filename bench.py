@@ -187,6 +187,25 @@ def algorithmic_bytes_encode(B, L, C, D=3, table_bytes=4, out_bytes=4):
     return B * (4 * D + L * (1 << D) * C * table_bytes + L * C * out_bytes)
 
 
+# name -> (C-ABI entry watched, predicate on the launch info, algorithmic bytes per launch, description)
+ROOFLINE_KERNELS = {
+    "main_backward": ("grid_encode_backward", lambda i: i.get("L") == 16 and i.get("B") == N_RAYS * NUM_STEPS[2],
+                      algorithmic_bytes_encode(N_RAYS * NUM_STEPS[2], 16, 2),
+                      "grid_backward_kernel<float,3,2,4,2> (main grid L16 F2 T2^19, B=262144): 1164 B/sample"),
+    "main_forward": ("grid_encode_forward", lambda i: i.get("L") == 16 and i.get("B") == N_RAYS * NUM_STEPS[2],
+                     algorithmic_bytes_encode(N_RAYS * NUM_STEPS[2], 16, 2),
+                     "grid_forward_kernel<float,3,2,4,2> (main grid L16 F2 T2^19, B=262144): 1164 B/sample"),
+    "prop0_forward": ("prop_density_forward", lambda i: i.get("B") == N_RAYS * NUM_STEPS[0],
+                      N_RAYS * NUM_STEPS[0] * (12 + 5 * 8 * 8 + 4),
+                      "prop_forward_kernel<5> (proposal level 0: encode L5 F2 + MLP + trunc_exp fused, B=1048576): "
+                      "12 B in + 320 B gathered + 4 B out per sample"),
+    "prop0_backward": ("prop_density_backward", lambda i: i.get("B") == N_RAYS * NUM_STEPS[0],
+                       N_RAYS * NUM_STEPS[0] * (12 + 4 + 2 * 5 * 8 * 8),
+                       "prop_backward_kernel<5> (proposal level 0 backward: recompute + scatter, B=1048576): "
+                       "16 B in + 320 B gathered + 320 B reduced per sample"),
+}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
@@ -242,12 +261,12 @@ def run_ours(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step_device(i)
-    # dominant kernel: proposal-level-0 grid encode (1,048,576 samples x L5) -- picked from the ncu launch list
-    pred = lambda info: info.get("L") == 5 and info.get("B") == N_RAYS * NUM_STEPS[0]  # noqa: E731
+    # dominant kernel of the step, picked from the ncu launch list (profiles/): see ROOFLINE_KERNELS
+    watch_name, pred, alg_bytes, watch_desc = ROOFLINE_KERNELS[args.roofline_kernel]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms, launches = timed_loop(step_device, args.steps, "grid_encode_forward", pred)
+    total_ms, launches = timed_loop(step_device, args.steps, watch_name, pred)
     clocks = sampler.stop() if rank == 0 else {}
     spans = _lib.stats.durations_ms()
     if args.no_e2e:
@@ -265,11 +284,10 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = load_peaks()
     roofline = None
     if spans:
-        B = N_RAYS * NUM_STEPS[0]
-        alg = algorithmic_bytes_encode(B, 5, 2)
+        alg = alg_bytes
         avg_ms = sum(ms for ms, _ in spans) / len(spans)
         achieved = alg / (avg_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "grid_forward_kernel<float,3,2,...> (proposal level 0, B=1048576, L=5)",
+        roofline = {"bound": "hbm", "kernel": watch_desc,
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
                     "avg_launch_ms": avg_ms, "launches_timed": len(spans)}
@@ -302,6 +320,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
+    ap.add_argument("--roofline-kernel", default="prop0_backward", choices=sorted(ROOFLINE_KERNELS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 

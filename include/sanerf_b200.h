@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 3
+#define SANERF_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -145,7 +145,9 @@ SANERF_API int sanerf_trunc_exp_backward(const float* g, const float* x, float* 
  * dense [N,T] block is the special case ray_offsets == NULL with uniform count T.
  *
  *  sigmas, deltas, ts   f32 [M]        density, interval length, mid-point distance
- *  feats                f32 [M, C]     per-sample channels (colour feature, SAM feature, ...); C may be 0
+ *  feats                f32 [M, C]     per-sample channels (colour feature, SAM feature, ...); C may be 0.
+ *                       Row stride `feat_stride` floats (0 = C): lets the kernel read columns of a wider
+ *                       matrix in place, e.g. the 15 geometry features at columns 1..15 of the 16-wide MLP output
  *  last_sample_opaque   != 0: the last sample of each ray gets delta*sigma := +inf (renderer.py:314-316)
  *  t_thresh             early ray termination: samples whose incoming transmittance < t_thresh
  *                       get weight 0 (0 disables; the reference never terminates — SURVEY §8 c5)
@@ -157,22 +159,79 @@ SANERF_API int sanerf_trunc_exp_backward(const float* g, const float* x, float* 
  *  n_alive      i32 [N]      number of samples with T_i >= t_thresh (may be NULL)
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_composite_forward(const float* sigmas, const float* deltas, const float* ts,
-                             const float* feats, const int32_t* ray_offsets, uint32_t N,
-                             uint32_t T, uint32_t C, int last_sample_opaque, float t_thresh,
+                             const float* feats, uint32_t feat_stride, const int32_t* ray_offsets,
+                             uint32_t N, uint32_t T, uint32_t C, int last_sample_opaque, float t_thresh,
                              float* weights, float* weights_sum, float* depth, float* out,
                              int32_t* n_alive, void* stream);
 
 /* Backward of the above.  Incoming gradients (any may be NULL = zero):
  *  g_weights [M], g_weights_sum [N], g_depth [N], g_out [N,C]
- * Produces grad_sigmas [M] and grad_feats [M,C] (grad_feats may be NULL).  deltas / ts carry no
- * gradient (bins are detached, renderer.py:275).
+ * Produces grad_sigmas [M] and grad_feats [M,C] with row stride `grad_feat_stride` (0 = C; grad_feats may be
+ * NULL).  deltas / ts carry no gradient (bins are detached, renderer.py:275).
  */
 SANERF_API int sanerf_composite_backward(const float* sigmas, const float* deltas, const float* ts,
-                              const float* feats, const int32_t* ray_offsets, uint32_t N,
-                              uint32_t T, uint32_t C, int last_sample_opaque, float t_thresh,
+                              const float* feats, uint32_t feat_stride, const int32_t* ray_offsets,
+                              uint32_t N, uint32_t T, uint32_t C, int last_sample_opaque, float t_thresh,
                               const float* weights, const float* g_weights,
                               const float* g_weights_sum, const float* g_depth, const float* g_out,
-                              float* grad_sigmas, float* grad_feats, void* stream);
+                              float* grad_sigmas, float* grad_feats, uint32_t grad_feat_stride,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Proposal sampling chain, one kernel per level (nerf/renderer.py:122-139 near/far, :250-253 spacing,
+ * :263-286 edges -> mid points / intervals / positions, :60-69 contraction, :84-119 sample_pdf,
+ * gridencoder/grid.py:156 unit-cube mapping).
+ *  rays_o, rays_d f32 [N,3]; aabb f32 [6]; cam_near_far f32 [.,2] with row stride cnf_stride (0 = one row
+ *  for all rays) or NULL; noise f32 uniform [0,1) [N, T+1] or NULL (= no perturbation).
+ * outputs: bins [N,T+1] in [0,1], t_mid [N,T], deltas [N,T], x01 [N,T,3] = (contract(o + d t) + bound)/(2 bound).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_sample_uniform(const float* rays_o, const float* rays_d, const float* aabb, float min_near,
+                          const float* cam_near_far, uint32_t cnf_stride, const float* noise, uint32_t N,
+                          uint32_t T, int contract, float bound, float* bins, float* t_mid, float* deltas,
+                          float* x01, void* stream);
+/* prev_bins [N,T0+1], prev_weights [N,T0]: the previous level's edges and compositing weights */
+SANERF_API int sanerf_sample_pdf(const float* rays_o, const float* rays_d, const float* aabb, float min_near,
+                      const float* cam_near_far, uint32_t cnf_stride, const float* prev_bins,
+                      const float* prev_weights, uint32_t T0, const float* noise, uint32_t N, uint32_t T,
+                      int contract, float bound, float* bins, float* t_mid, float* deltas, float* x01,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Proposal density, fused: hash-grid encode (D=3, F=2, L<=8, fp32) -> Linear(2L,16) -> ReLU -> Linear(16,1) ->
+ * trunc_exp (nerf/network.py:211-219, 248-252).  w1 f32 [16, 2L], w2 f32 [1,16] (nn.Linear layout, no bias).
+ * Backward accumulates into grad_table [rows,2], grad_w1 [16,2L], grad_w2 [16] (caller zero-fills).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_prop_density_forward(const float* x01, const float* table, const int32_t* offsets,
+                                const float* w1, const float* w2, uint32_t B, uint32_t L, float S,
+                                uint32_t H, float* sigma, void* stream);
+SANERF_API int sanerf_prop_density_backward(const float* x01, const float* table, const int32_t* offsets,
+                                 const float* w1, const float* w2, uint32_t B, uint32_t L, float S,
+                                 uint32_t H, const float* g_sigma, float* grad_table, float* grad_w1,
+                                 float* grad_w2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampling regularisers: loss value AND d loss / d weights in one kernel each.
+ *  proposal loss (nerf/renderer.py:30-57) of ONE proposal level (t_p [N,Tp+1], w_p [N,Tp]) against the final
+ *  level (t_ref [N,Tr+1], w_ref [N,Tr]); distortion loss (renderer.py:17-27 + torch_efficient_distloss).
+ *  loss_out: one float, ACCUMULATED into (caller zero-fills); g_* may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_proposal_loss(const float* t_ref, const float* w_ref, uint32_t Tr, const float* t_p,
+                         const float* w_p, uint32_t Tp, uint32_t N, float* loss_out, float* g_wp,
+                         void* stream);
+SANERF_API int sanerf_distortion_loss(const float* bins, const float* w, uint32_t T, uint32_t N, float* loss_out,
+                           float* g_w, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused Adam over one flat fp32 buffer (main.py:296 Adam(eps=1e-15), :312-313 LambdaLR 0.1^min(it/iters,1)).
+ * sanerf_adam_schedule advances the device-side step counter and writes dyn = {lr_t, 1-b1^t, 1-b2^t};
+ * sanerf_adam_step applies the update (gradient pre-multiplied by grad_scale, e.g. 1/world_size) and can zero
+ * the gradient in the same pass.  Both are CUDA-graph replayable.
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_adam_schedule(int32_t* step, float* dyn, float lr0, float beta1, float beta2,
+                         float decay_iters, void* stream);
+SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint64_t n,
+                     const float* dyn, float beta1, float beta2, float eps, float grad_scale,
+                     int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

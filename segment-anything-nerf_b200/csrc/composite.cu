@@ -41,6 +41,8 @@ struct CompositeArgs {
     uint32_t N, T, C;
     int last_opaque;
     float t_thresh;
+    uint32_t fs;    // feats row stride (floats)
+    uint32_t gfs;   // grad_feats row stride (floats)
 };
 
 struct SampleTerms {
@@ -110,12 +112,12 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_forward_kernel(
         if (C > 0) {
             if constexpr (KC > 0) {
                 const uint32_t cnt = min(32u, n - base);
-                const float* rows = a.feats + (start + base) * C;
+                const float* rows = a.feats + (start + base) * a.fs;
 #pragma unroll 4
                 for (uint32_t j = 0; j < cnt; ++j) {
                     const float wj = __shfl_sync(kFull, s.w, j);
                     if (wj == 0.0f) continue;  // terminated / transparent sample: row never read
-                    const float* row = rows + (size_t)j * C;
+                    const float* row = rows + (size_t)j * a.fs;
 #pragma unroll
                     for (int q = 0; q < KC; ++q) {
                         const uint32_t c = lane + 32u * q;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_forward_kernel(
                 }
             } else {
                 if (s.valid && s.w != 0.0f) {
-                    const float* row = a.feats + (start + base + lane) * C;
+                    const float* row = a.feats + (start + base + lane) * a.fs;
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         if ((uint32_t)q < C) acc[q] = __fmaf_rn(s.w, __ldg(row + q), acc[q]);
@@ -218,21 +220,21 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_backward_kernel(
         if (C > 0 && g.g_out) {
             if constexpr (KC > 0) {
                 const uint32_t cnt = min(32u, n - base);
-                const float* rows = a.feats + (start + base) * C;
-                float* grows = grad_feats ? grad_feats + (start + base) * C : nullptr;
+                const float* rows = a.feats + (start + base) * a.fs;
+                float* grows = grad_feats ? grad_feats + (start + base) * a.gfs : nullptr;
                 float part[32];
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) {
                     float p = 0.0f;
                     if (j < cnt) {
                         const float wj = __shfl_sync(kFull, s.w, j);
-                        const float* row = rows + (size_t)j * C;
+                        const float* row = rows + (size_t)j * a.fs;
 #pragma unroll
                         for (int q = 0; q < KC; ++q) {
                             const uint32_t c = lane + 32u * q;
                             if (c < C) {
                                 p = __fmaf_rn(go[q], __ldg(row + c), p);
-                                if (grows) grows[(size_t)j * C + c] = wj * go[q];
+                                if (grows) grows[(size_t)j * a.gfs + c] = wj * go[q];
                             }
                         }
                     }
@@ -241,8 +243,8 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_backward_kernel(
                 dot = butterfly_transpose_sum(part, lane);
             } else {
                 if (s.valid) {
-                    const float* row = a.feats + (start + base + lane) * C;
-                    float* grow = grad_feats ? grad_feats + (start + base + lane) * C : nullptr;
+                    const float* row = a.feats + (start + base + lane) * a.fs;
+                    float* grow = grad_feats ? grad_feats + (start + base + lane) * a.gfs : nullptr;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if ((uint32_t)q < C) {
@@ -255,8 +257,8 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_backward_kernel(
         } else if (C > 0 && grad_feats) {
             // no gradient reaches `out`: grad_feats is all zero
             const uint32_t cnt = min(32u, n - base);
-            float* grows = grad_feats + (start + base) * C;
-            for (uint32_t e = lane; e < cnt * C; e += 32) grows[e] = 0.0f;
+            float* grows = grad_feats + (start + base) * a.gfs;
+            for (uint32_t e = lane; e < cnt * C; e += 32) grows[(size_t)(e / C) * a.gfs + (e % C)] = 0.0f;
         }
         if (s.valid) {
             float gi = dot + g_ws;
@@ -318,8 +320,8 @@ __global__ void composite_backward_long_kernel(const CompositeArgs a, const Comp
         float gi = g_ws + g_dp * a.ts[start + i] + (g.g_weights ? g.g_weights[start + i] : 0.0f);
         for (uint32_t c = 0; c < C; ++c) {
             const float go = g.g_out ? g.g_out[(size_t)r * C + c] : 0.0f;
-            gi += go * a.feats[(start + i) * C + c];
-            if (grad_feats) grad_feats[(start + i) * C + c] = w * go;
+            gi += go * a.feats[(start + i) * a.fs + c];
+            if (grad_feats) grad_feats[(start + i) * a.gfs + c] = w * go;
         }
         if (!alive || !fin) gi = 0.0f;
         grad_sigmas[start + i] = gi * (T * expf(-x));
@@ -340,7 +342,7 @@ __global__ void composite_backward_long_kernel(const CompositeArgs a, const Comp
         if (!alive) w = 0.0f;
         float gi = g_ws + g_dp * a.ts[start + i] + (g.g_weights ? g.g_weights[start + i] : 0.0f);
         for (uint32_t c = 0; c < C; ++c)
-            gi += (g.g_out ? g.g_out[(size_t)r * C + c] : 0.0f) * a.feats[(start + i) * C + c];
+            gi += (g.g_out ? g.g_out[(size_t)r * C + c] : 0.0f) * a.feats[(start + i) * a.fs + c];
         if (!alive || !fin) gi = 0.0f;
         prefix += gi * w;
         float ds = a.deltas[start + i] * (grad_sigmas[start + i] - (total - prefix));
@@ -377,7 +379,7 @@ static int check_composite_args(const float* sigmas, const float* deltas, const 
 }
 
 extern "C" int sanerf_composite_forward(const float* sigmas, const float* deltas, const float* ts,
-                                        const float* feats, const int32_t* ray_offsets, uint32_t N, uint32_t T,
+                                        const float* feats, uint32_t feat_stride, const int32_t* ray_offsets, uint32_t N, uint32_t T,
                                         uint32_t C, int last_sample_opaque, float t_thresh, float* weights,
                                         float* weights_sum, float* depth, float* out, int32_t* n_alive,
                                         void* stream) {
@@ -388,7 +390,9 @@ extern "C" int sanerf_composite_forward(const float* sigmas, const float* deltas
     SANERF_REQUIRE_PTR(weights_sum);
     SANERF_REQUIRE_PTR(depth);
     if (C > 0) SANERF_REQUIRE_PTR(out);
-    CompositeArgs a{sigmas, deltas, ts, feats, ray_offsets, N, T, C, last_sample_opaque, t_thresh};
+    if (feat_stride != 0 && feat_stride < C) return fail(SANERF_ERR_INVALID_ARG, "composite: feat_stride < C");
+    CompositeArgs a{sigmas, deltas, ts, feats, ray_offsets, N, T, C, last_sample_opaque, t_thresh,
+                    feat_stride ? feat_stride : C, C};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t blocks = div_up(N, (uint32_t)kRaysPerBlock);
     const int threads = 32 * kRaysPerBlock;
@@ -401,16 +405,20 @@ extern "C" int sanerf_composite_forward(const float* sigmas, const float* deltas
 }
 
 extern "C" int sanerf_composite_backward(const float* sigmas, const float* deltas, const float* ts,
-                                         const float* feats, const int32_t* ray_offsets, uint32_t N, uint32_t T,
+                                         const float* feats, uint32_t feat_stride, const int32_t* ray_offsets, uint32_t N, uint32_t T,
                                          uint32_t C, int last_sample_opaque, float t_thresh, const float* weights,
                                          const float* g_weights, const float* g_weights_sum, const float* g_depth,
-                                         const float* g_out, float* grad_sigmas, float* grad_feats, void* stream) {
+                                         const float* g_out, float* grad_sigmas, float* grad_feats,
+                                         uint32_t grad_feat_stride, void* stream) {
     (void)weights;  // recomputed from sigmas/deltas in registers (cheaper than re-reading)
     if (N == 0) return SANERF_OK;
     int rc = check_composite_args(sigmas, deltas, ts, feats, C);
     if (rc != SANERF_OK) return rc;
     SANERF_REQUIRE_PTR(grad_sigmas);
-    CompositeArgs a{sigmas, deltas, ts, feats, ray_offsets, N, T, C, last_sample_opaque, t_thresh};
+    if ((feat_stride != 0 && feat_stride < C) || (grad_feat_stride != 0 && grad_feat_stride < C))
+        return fail(SANERF_ERR_INVALID_ARG, "composite: feature stride < C");
+    CompositeArgs a{sigmas, deltas, ts, feats, ray_offsets, N, T, C, last_sample_opaque, t_thresh,
+                    feat_stride ? feat_stride : C, grad_feat_stride ? grad_feat_stride : C};
     CompositeGrads g{g_weights, g_weights_sum, g_depth, g_out};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (T > 32u * kMaxChunks) {

@@ -1,0 +1,235 @@
+// Sampling regularisers of the training step, fused (sm_100a): inter-level proposal loss and
+// distortion loss, each ONE warp-per-ray kernel that returns the loss AND d loss / d weights.
+//
+// Replaces the cumsum / searchsorted / take_along_dim / clamp chains of nerf/renderer.py:30-57 (proposal_loss)
+// and renderer.py:17-27 + torch_efficient_distloss (distort_loss), forward and backward (~40 torch kernels).
+//
+//  proposal:  for every reference interval k of a ray:  bound_k = sum of proposal weights over the proposal
+//             intervals overlapping it (outer measure);  L = mean_k max(w_ref_k - bound_k, 0)^2 / (w_ref_k + 1e-8)
+//             dL/dw_p[i] = - sum_{k : lo_k <= i <= hi_k} 2 max(w_ref_k - bound_k, 0) / (w_ref_k + 1e-8) / (N T_ref)
+//  distortion (Mip-NeRF 360 eq. 15, O(T) form of Sun et al. 2022):
+//             L = 1/N sum_rays [ 1/3 sum_i d_i w_i^2 + 2 sum_i w_i (m_i W_<i - WM_<i) ]
+//             dL/dw_i = 1/N [ 2/3 d_i w_i + 2 ( m_i (W_<i - W_>i) + WM_>i - WM_<i ) ]
+#include "common.cuh"
+
+namespace sanerf {
+
+constexpr int kLossWarps = 4;
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+// inclusive scan of per-lane values laid out as element i = base + lane, carried across chunks
+__device__ __forceinline__ float warp_incl_scan(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(kFullMask, v, o);
+        if (lane >= (uint32_t)o) v += t;
+    }
+    return v;
+}
+
+// searchsorted(a[0..n), x, right=True): first index with a[idx] > x
+__device__ __forceinline__ uint32_t upper_bound(const float* a, uint32_t n, float x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] > x) hi = mid; else lo = mid + 1u;
+    }
+    return lo;
+}
+
+// shared per warp: t_p[Tp+1] | cum[Tp+1] (exclusive prefix, cum[0]=0 .. cum[Tp]=total) | diff[Tp+1]
+__global__ void __launch_bounds__(32 * kLossWarps) proposal_loss_kernel(
+    const float* __restrict__ t_ref, const float* __restrict__ w_ref, uint32_t Tr, const float* __restrict__ t_p,
+    const float* __restrict__ w_p, uint32_t Tp, uint32_t N, float* __restrict__ loss_out, float* __restrict__ g_wp) {
+    extern __shared__ float smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * kLossWarps + warp;
+    if (r >= N) return;
+    float* tp = smem + (size_t)warp * 3u * (Tp + 1u);
+    float* cum = tp + (Tp + 1u);
+    float* diff = cum + (Tp + 1u);
+    const float scale = 1.0f / ((float)N * (float)Tr);     // .mean() over [N, Tr]
+
+    for (uint32_t i = lane; i <= Tp; i += 32) { tp[i] = __ldg(t_p + (size_t)r * (Tp + 1u) + i); diff[i] = 0.0f; }
+    float carry = 0.0f;
+    for (uint32_t base = 0; base < Tp; base += 32) {
+        const uint32_t i = base + lane;
+        const float v = (i < Tp) ? __ldg(w_p + (size_t)r * Tp + i) : 0.0f;
+        const float inc = warp_incl_scan(v, lane);
+        if (i < Tp) cum[i + 1u] = carry + inc;
+        carry += __shfl_sync(kFullMask, inc, 31);
+    }
+    if (lane == 0) cum[0] = 0.0f;
+    __syncwarp();
+
+    float loss = 0.0f;
+    for (uint32_t k = lane; k < Tr; k += 32) {
+        const float a = __ldg(t_ref + (size_t)r * (Tr + 1u) + k), b = __ldg(t_ref + (size_t)r * (Tr + 1u) + k + 1u);
+        const float wr = __ldg(w_ref + (size_t)r * Tr + k);
+        // inds_lo = clamp(searchsorted(t_p[:-1], a, right) - 1, 0, Tp-1); inds_hi = clamp(searchsorted(t_p[1:], b, right), 0, Tp-1)
+        const uint32_t ub_lo = upper_bound(tp, Tp, a);
+        const uint32_t lo = (ub_lo == 0u) ? 0u : min(ub_lo - 1u, Tp - 1u);
+        const uint32_t hi = min(upper_bound(tp + 1, Tp, b), Tp - 1u);
+        const float bound = cum[hi + 1u] - cum[lo];          // cw1[1:][hi] - cw1[:-1][lo]
+        const float excess = fmaxf(wr - bound, 0.0f);
+        const float denom = wr + 1e-8f;
+        loss += excess * excess / denom;
+        if (excess > 0.0f && g_wp != nullptr) {
+            const float c = -2.0f * excess / denom * scale;
+            // d bound / d w_p[i] = 1 for lo <= i <= hi when hi >= lo; if hi < lo the difference of prefix sums
+            // is minus the sum over (hi, lo): keep the exact derivative of the expression
+            if (hi >= lo) { atomicAdd(diff + lo, c); atomicAdd(diff + hi + 1u, -c); }
+            else { atomicAdd(diff + hi + 1u, -c); atomicAdd(diff + lo, c); }
+        }
+    }
+    loss = warp_sum(loss);
+    if (lane == 0) atomicAdd(loss_out, loss * scale);
+    if (g_wp == nullptr) return;
+    __syncwarp();
+    carry = 0.0f;
+    for (uint32_t base = 0; base < Tp; base += 32) {
+        const uint32_t i = base + lane;
+        const float v = (i < Tp) ? diff[i] : 0.0f;
+        const float inc = warp_incl_scan(v, lane);
+        if (i < Tp) g_wp[(size_t)r * Tp + i] = carry + inc;
+        carry += __shfl_sync(kFullMask, inc, 31);
+    }
+}
+
+__global__ void __launch_bounds__(32 * kLossWarps) distortion_loss_kernel(
+    const float* __restrict__ bins, const float* __restrict__ w, uint32_t T, uint32_t N, float* __restrict__ loss_out,
+    float* __restrict__ g_w) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * kLossWarps + warp;
+    if (r >= N) return;
+    const float inv_n = 1.0f / (float)N;
+    const float* b = bins + (size_t)r * (T + 1u);
+    const float* wr = w + (size_t)r * T;
+    // totals first (needed for the suffix terms of the gradient)
+    float w_tot = 0.0f, wm_tot = 0.0f;
+    for (uint32_t i = lane; i < T; i += 32) {
+        const float d = __ldg(b + i + 1u) - __ldg(b + i);
+        const float m = __ldg(b + i) + d * 0.5f;
+        const float wi = __ldg(wr + i);
+        w_tot += wi;
+        wm_tot = __fmaf_rn(wi, m, wm_tot);
+    }
+    w_tot = warp_sum(w_tot);
+    wm_tot = warp_sum(wm_tot);
+    float loss = 0.0f, cw = 0.0f, cwm = 0.0f;
+    for (uint32_t base = 0; base < T; base += 32) {
+        const uint32_t i = base + lane;
+        float d = 0.0f, m = 0.0f, wi = 0.0f;
+        if (i < T) {
+            d = __ldg(b + i + 1u) - __ldg(b + i);
+            m = __ldg(b + i) + d * 0.5f;
+            wi = __ldg(wr + i);
+        }
+        const float iw = warp_incl_scan(wi, lane), iwm = warp_incl_scan(wi * m, lane);
+        const float w_pre = cw + iw - wi, wm_pre = cwm + iwm - wi * m;     // exclusive prefixes
+        if (i < T) {
+            loss += d * wi * wi * (1.0f / 3.0f) + 2.0f * wi * (m * w_pre - wm_pre);
+            if (g_w != nullptr) {
+                const float w_suf = w_tot - (w_pre + wi), wm_suf = wm_tot - (wm_pre + wi * m);
+                g_w[(size_t)r * T + i] = inv_n * ((2.0f / 3.0f) * d * wi + 2.0f * (m * (w_pre - w_suf) + (wm_suf - wm_pre)));
+            }
+        }
+        cw += __shfl_sync(kFullMask, iw, 31);
+        cwm += __shfl_sync(kFullMask, iwm, 31);
+    }
+    loss = warp_sum(loss);
+    if (lane == 0) atomicAdd(loss_out, loss * inv_n);
+}
+
+// ---- fused Adam over a flat parameter buffer -------------------------------------------------------
+// torch.optim.Adam semantics (no weight decay, no amsgrad):  m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+// p -= lr / (1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  `dyn` = {lr_t, 1-b1^t, 1-b2^t} lives on the device so
+// that a captured CUDA graph can be replayed with a moving step count / learning-rate schedule.
+__global__ void adam_schedule_kernel(int32_t* step, float* dyn, float lr0, float beta1, float beta2, float decay_iters) {
+    const int32_t t = *step + 1;
+    *step = t;
+    // LambdaLR(0.1 ** min(iter / iters, 1)) evaluated at iter = t-1 (main.py:312-313; scheduler steps after the optimizer)
+    const float frac = (decay_iters > 0.0f) ? fminf((float)(t - 1) / decay_iters, 1.0f) : 0.0f;
+    dyn[0] = lr0 * powf(0.1f, frac);
+    dyn[1] = 1.0f - powf(beta1, (float)t);
+    dyn[2] = 1.0f - powf(beta2, (float)t);
+}
+
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, size_t n4, size_t n,
+                                                        const float* __restrict__ dyn, float beta1, float beta2,
+                                                        float eps, float grad_scale, int zero_grad) {
+    const float lr = __ldg(dyn), bc1 = __ldg(dyn + 1), bc2 = __ldg(dyn + 2);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    auto update = [&](float& pp, float gg, float& mm, float& vv) {
+        gg *= grad_scale;
+        mm = beta1 * mm + (1.0f - beta1) * gg;
+        vv = beta2 * vv + (1.0f - beta2) * gg * gg;
+        pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+    };
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        update(pp.x, gg.x, mm.x, vv.x); update(pp.y, gg.y, mm.y, vv.y);
+        update(pp.z, gg.z, mm.z, vv.z); update(pp.w, gg.w, mm.w, vv.w);
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        update(p[i], g[i], m[i], v[i]);
+        if (zero_grad) g[i] = 0.0f;
+    }
+}
+
+}  // namespace sanerf
+
+using namespace sanerf;
+
+extern "C" int sanerf_proposal_loss(const float* t_ref, const float* w_ref, uint32_t Tr, const float* t_p,
+                                    const float* w_p, uint32_t Tp, uint32_t N, float* loss_out, float* g_wp,
+                                    void* stream) {
+    if (N == 0 || Tr == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(t_ref); SANERF_REQUIRE_PTR(w_ref); SANERF_REQUIRE_PTR(t_p); SANERF_REQUIRE_PTR(w_p);
+    SANERF_REQUIRE_PTR(loss_out);
+    if (Tp == 0) return fail(SANERF_ERR_INVALID_ARG, "proposal_loss: proposal level has no samples");
+    const size_t smem = (size_t)kLossWarps * 3u * (Tp + 1u) * sizeof(float);
+    if (smem > 48 * 1024) return fail(SANERF_ERR_INVALID_ARG, "proposal_loss: Tp too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    proposal_loss_kernel<<<div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, smem, st>>>(t_ref, w_ref, Tr, t_p, w_p, Tp,
+                                                                                         N, loss_out, g_wp);
+    return check_launch("proposal_loss_kernel");
+}
+
+extern "C" int sanerf_distortion_loss(const float* bins, const float* w, uint32_t T, uint32_t N, float* loss_out,
+                                      float* g_w, void* stream) {
+    if (N == 0 || T == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(bins); SANERF_REQUIRE_PTR(w); SANERF_REQUIRE_PTR(loss_out);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    distortion_loss_kernel<<<div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, 0, st>>>(bins, w, T, N, loss_out, g_w);
+    return check_launch("distortion_loss_kernel");
+}
+
+extern "C" int sanerf_adam_schedule(int32_t* step, float* dyn, float lr0, float beta1, float beta2, float decay_iters,
+                                    void* stream) {
+    SANERF_REQUIRE_PTR(step); SANERF_REQUIRE_PTR(dyn);
+    adam_schedule_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step, dyn, lr0, beta1, beta2, decay_iters);
+    return check_launch("adam_schedule_kernel");
+}
+
+extern "C" int sanerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint64_t n,
+                                const float* dyn, float beta1, float beta2, float eps, float grad_scale,
+                                int zero_grad, void* stream) {
+    if (n == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(params); SANERF_REQUIRE_PTR(grads); SANERF_REQUIRE_PTR(exp_avg); SANERF_REQUIRE_PTR(exp_avg_sq);
+    SANERF_REQUIRE_PTR(dyn);
+    const uintptr_t align = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq;
+    if (align & 15u) return fail(SANERF_ERR_MISALIGNED, "adam_step: buffers must be 16-byte aligned");
+    const size_t n4 = (size_t)n / 4;
+    size_t blocks = div_up(n4 > 0 ? n4 : (size_t)1, (size_t)256);
+    const size_t cap = (size_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    adam_step_kernel<<<(uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad);
+    return check_launch("adam_step_kernel");
+}

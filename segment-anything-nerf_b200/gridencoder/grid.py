@@ -88,6 +88,8 @@ class _GridEncode(Function):
     def backward(ctx, grad):
         inputs, table, offsets, dy_dx = ctx.saved_tensors
         B, D, C, L, S, H, gridtype, interpolation, max_level, align_corners = ctx.meta
+        if not ctx.needs_input_grad[1] and dy_dx is None:
+            return (None,) * 10                     # frozen table (stage 2 freezes the stage-1 grids)
         grad = grad.contiguous()
         if grad.dtype != table.dtype:
             grad = grad.to(table.dtype)

@@ -10,7 +10,8 @@ import torch.nn.functional as F
 
 from activation import trunc_exp
 from encoding import get_encoder
-from shencoder import SHEncoder
+from gridencoder.grid import grid_encode
+from sanerf_b200 import fused
 
 from .renderer import NeRFRenderer
 
@@ -114,6 +115,27 @@ class NeRFNetwork(NeRFRenderer):
         sh = self.view_encoder(rays_d)                                   # normalises internally
         color = torch.cat([feat, sh.unsqueeze(1).expand(-1, xyz.shape[1], -1)], dim=-1)
         return {"sigma": sigma, "geo_feat": feat, "color": color, "grid_output": grid_output}
+
+    # ---- fast-path hooks used by NeRFRenderer._run_fused: positions already mapped to [0,1]^3 -------------
+    @staticmethod
+    def _encode_unit(enc, x01):
+        flat = x01.reshape(-1, enc.input_dim)
+        out = grid_encode(flat, enc.embeddings, enc.offsets, enc.per_level_scale, enc.base_resolution, False,
+                          enc.gridtype_id, enc.align_corners, enc.interp_id, None)
+        return out.view(*x01.shape[:-1], enc.output_dim)
+
+    def density_unit(self, x01, proposal):
+        enc, mlp = self.prop_encoders[proposal], self.prop_mlp[proposal]
+        if fused.prop_density_supported(enc, mlp):
+            return fused.prop_density(x01, enc, mlp)
+        return trunc_exp(mlp(self._encode_unit(enc, x01)).squeeze(-1))
+
+    def head_unit(self, x01):
+        """[N,T,3] -> [N,T,16]: grid_mlp(grid(x)); column 0 is the density logit (network.py:223-227)."""
+        return self.grid_mlp(self._encode_unit(self.grid, x01))
+
+    def features_unit(self, x01):
+        return self._encode_unit(self.s_grid, x01)
 
     def density(self, x, proposal=-1):
         if 0 <= proposal < len(self.prop_encoders):

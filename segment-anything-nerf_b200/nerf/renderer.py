@@ -10,6 +10,10 @@ statement are those of the reference (cited inline); what changes is the executi
   (renderer.py:309-338, :377);
 * the view direction is SH-encoded once per ray and broadcast, not once per sample
   (network.py:237 evaluates the same direction T times);
+* with ``opt.fused`` (default on) each sampling level is ONE kernel (near/far, spacing, jitter or inverse-CDF
+  resampling, mid points, intervals, positions, contraction, unit-cube mapping), the proposal density is ONE
+  kernel (grid encode -> MLP -> trunc_exp), ``trunc_exp`` + compositing read the MLP head in place, and the
+  proposal / distortion losses are one kernel each (``sanerf_b200/fused.py``);
 * mask heads (stage 3) are not part of this path.
 """
 import math
@@ -17,6 +21,7 @@ import math
 import torch
 import torch.nn as nn
 
+from sanerf_b200 import fused
 from sanerf_b200.ops import composite
 
 
@@ -123,6 +128,7 @@ class NeRFRenderer(nn.Module):
         self.register_buffer("aabb_infer", box.clone())
         # early ray termination is opt-in: the reference declares --T_thresh but never reads it
         self.t_thresh = float(getattr(opt, "t_thresh_composite", 0.0))
+        self.fused = bool(getattr(opt, "fused", True))
 
     def forward(self, x, d, **kwargs):
         raise NotImplementedError()
@@ -189,6 +195,12 @@ class NeRFRenderer(nn.Module):
             bg_color = 1
         s_near, s_far = _spacing(near), _spacing(far)
 
+        use_fused = (self.fused and not self.opt.sum_after_mlp and rays_o.is_cuda and rays_o.dtype == torch.float32
+                     and not torch.is_autocast_enabled() and hasattr(self, "head_unit"))
+        if use_fused:
+            return self._run_fused(rays_o, rays_d, bg_color, perturb, cam_near_far, update_proposal, return_feats,
+                                   H, W, opaque_last, steps)
+
         all_bins, all_weights = [], []
         bins = weights = None
         for level, T in enumerate(steps):
@@ -248,6 +260,64 @@ class NeRFRenderer(nn.Module):
                 geo_sum = composite(sigmas, deltas, t_mid, field["geo_feat"].contiguous(),
                                     last_sample_opaque=opaque_last)[3]
                 f = torch.cat([f_sam, geo_sum, image, depth.unsqueeze(-1)], dim=-1)        # renderer.py:383
+            samvit = self.samvit_mlp(f)
+            if return_feats > 0:
+                results["samvit"] = samvit.view(H, W, -1)
+        return results
+
+    def _run_fused(self, rays_o, rays_d, bg_color, perturb, cam_near_far, update_proposal, return_feats, H, W,
+                   opaque_last, steps):
+        """Same computation as ``run`` with one kernel per sampling level, fused proposal density, in-place head
+        compositing and fused losses.  Random draws are taken in the reference's order ([N,T+1] uniforms per level)."""
+        N, device = rays_o.shape[0], rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        if bg_color is None:
+            bg_color = 1
+        common = dict(cam_near_far=cam_near_far, contract=self.opt.contract, bound=float(self.bound))
+        all_bins, all_weights = [], []
+        bins = weights = None
+        last = len(steps) - 1
+        for level, T in enumerate(steps):
+            noise = torch.rand(N, T + 1, device=device) if perturb else None
+            if level == 0:
+                bins, t_mid, deltas, x01 = fused.sample_uniform(rays_o, rays_d, aabb, self.min_near, T, noise, **common)
+            else:
+                bins, t_mid, deltas, x01 = fused.sample_pdf(rays_o, rays_d, aabb, self.min_near, bins, weights, T,
+                                                            noise, **common)
+            if level != last:
+                with torch.set_grad_enabled(update_proposal and torch.is_grad_enabled()):
+                    sigmas = self.density_unit(x01, level)
+                weights = composite(sigmas, deltas, t_mid, None, last_sample_opaque=opaque_last)[0]
+            else:
+                head = self.head_unit(x01)                                        # [N,T,16]: sigma logit + 15 features
+                sigmas, weights, weights_sum, depth, geo_sum, n_alive = fused.head_composite(
+                    head, deltas, t_mid, opaque_last, self.t_thresh)
+                sh = self.view_encoder(rays_d)                                    # once per ray
+                f_image = torch.cat([geo_sum, weights_sum.unsqueeze(-1) * sh], dim=-1)   # = sum_i w_i [geo_i, sh]
+                if self.opt.with_sam:
+                    features = self.features_unit(x01)                            # [N,T,128]
+            if self.training:
+                all_bins.append(bins)
+                all_weights.append(weights)
+
+        results = {}
+        image = torch.sigmoid(self.view_mlp(f_image))
+        if self.training and not self.opt.with_mask and not self.opt.with_sam:
+            results["num_points"] = N * steps[-1]
+            results["weights"] = weights
+            if self.opt.lambda_proposal > 0 and update_proposal:
+                results["proposal_loss"] = fused.proposal_loss(all_bins, all_weights)
+            if self.opt.lambda_distort > 0:
+                results["distort_loss"] = fused.distort_loss(bins, weights)
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        results.update(weights_sum=weights_sum, depth=depth, image=image, n_alive=n_alive)
+        if self.opt.with_sam:
+            f_sam = composite(sigmas, deltas, t_mid, features, last_sample_opaque=opaque_last,
+                              t_thresh=self.t_thresh)[3]
+            if self.opt.sam_use_view_direction:
+                f = torch.cat([f_sam, f_image, image, depth.unsqueeze(-1)], dim=-1)
+            else:
+                f = torch.cat([f_sam, geo_sum, image, depth.unsqueeze(-1)], dim=-1)
             samvit = self.samvit_mlp(f)
             if return_feats > 0:
                 results["samvit"] = samvit.view(H, W, -1)

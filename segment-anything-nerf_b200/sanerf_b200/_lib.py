@@ -16,7 +16,7 @@ _HEADER = os.path.join(os.path.dirname(_PKG_DIR), "include", "sanerf_b200.h")
 
 SANERF_F32, SANERF_F16 = 0, 1
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_u32, c_u64, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                           ctypes.c_uint64, ctypes.c_float)
@@ -43,11 +43,25 @@ _SIGNATURES = {
     "sanerf_freq_encode_backward": [c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_void_p, c_void_p],
     "sanerf_trunc_exp_forward": [c_void_p, c_void_p, c_u64, c_u32, c_u32, c_void_p],
     "sanerf_trunc_exp_backward": [c_void_p, c_void_p, c_void_p, c_u64, c_u32, c_u32, c_void_p],
-    "sanerf_composite_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32,
+    "sanerf_composite_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_void_p, c_u32, c_u32, c_u32,
                                  c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    "sanerf_composite_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32,
+    "sanerf_composite_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_void_p, c_u32, c_u32, c_u32,
                                   c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p],
+                                  c_void_p, c_u32, c_void_p],
+    "sanerf_sample_uniform": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_u32, c_void_p, c_u32, c_u32, c_int,
+                              c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sanerf_sample_pdf": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_u32, c_void_p, c_void_p, c_u32, c_void_p,
+                          c_u32, c_u32, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sanerf_prop_density_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_float, c_u32,
+                                    c_void_p, c_void_p],
+    "sanerf_prop_density_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_float, c_u32,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sanerf_proposal_loss": [c_void_p, c_void_p, c_u32, c_void_p, c_void_p, c_u32, c_u32, c_void_p, c_void_p,
+                             c_void_p],
+    "sanerf_distortion_loss": [c_void_p, c_void_p, c_u32, c_u32, c_void_p, c_void_p, c_void_p],
+    "sanerf_adam_schedule": [c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p],
+    "sanerf_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_u64, c_void_p, c_float, c_float, c_float,
+                         c_float, c_int, c_void_p],
 }
 _RESTYPES = {"sanerf_last_error": ctypes.c_char_p, "sanerf_status_string": ctypes.c_char_p}
 

@@ -1,0 +1,297 @@
+"""Fused operators of the training / rendering step (additive to the reference surface).
+
+Each one collapses a chain of torch kernels of ``nerf/renderer.py`` / ``nerf/network.py`` / the Trainer into one
+or two sm_100a kernels behind the C ABI:
+
+* ``sample_uniform`` / ``sample_pdf``   — renderer.py:122-139, 250-286, 60-69, 84-119 (one kernel per level)
+* ``prop_density``                      — network.py:248-252: grid encode -> MLP(2L,16,1) -> trunc_exp
+* ``head_composite``                    — network.py:226-227 + renderer.py:309-338: trunc_exp on column 0 of the
+                                          16-wide MLP output and compositing of columns 1..15, read in place
+* ``proposal_loss`` / ``distort_loss``  — renderer.py:17-57 (loss and d loss / d weights together)
+* ``FusedAdam``                         — main.py:296,312-313: Adam(eps=1e-15) + LambdaLR on flat buffers
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+
+def _stream(t):
+    return _lib.current_stream(t.device)
+
+
+# ----------------------------------------------------------------------------------------- sampling
+def _sample_outputs(N, T, dev):
+    return (torch.empty(N, T + 1, device=dev), torch.empty(N, T, device=dev), torch.empty(N, T, device=dev),
+            torch.empty(N, T, 3, device=dev))
+
+
+def _cnf(cam_near_far):
+    if cam_near_far is None:
+        return None, 0
+    c = cam_near_far.contiguous().float()
+    return c, (0 if c.shape[0] == 1 else 2)
+
+
+@torch.no_grad()
+def sample_uniform(rays_o, rays_d, aabb, min_near, T, noise=None, cam_near_far=None, contract=True, bound=2.0):
+    """Level-0 sampling: returns bins [N,T+1], t_mid [N,T], deltas [N,T], x01 [N,T,3] (already in the grid's unit cube)."""
+    N, dev = rays_o.shape[0], rays_o.device
+    bins, t_mid, deltas, x01 = _sample_outputs(N, T, dev)
+    cnf, stride = _cnf(cam_near_far)
+    lib = _lib.load()
+    with torch.cuda.device(dev), _lib.stats.span("sample_uniform", N=N, T=T):
+        rc = lib.sanerf_sample_uniform(rays_o.data_ptr(), rays_d.data_ptr(), aabb.data_ptr(), float(min_near),
+                                       _lib.ptr(cnf), stride, _lib.ptr(noise), N, T, int(bool(contract)), float(bound),
+                                       bins.data_ptr(), t_mid.data_ptr(), deltas.data_ptr(), x01.data_ptr(),
+                                       _stream(rays_o))
+    _lib.check(rc, "sample_uniform")
+    return bins, t_mid, deltas, x01
+
+
+@torch.no_grad()
+def sample_pdf(rays_o, rays_d, aabb, min_near, prev_bins, prev_weights, T, noise=None, cam_near_far=None,
+               contract=True, bound=2.0):
+    """Inverse-CDF resampling of T+1 edges from the previous level, plus the same outputs as ``sample_uniform``."""
+    N, dev = rays_o.shape[0], rays_o.device
+    T0 = prev_weights.shape[1]
+    bins, t_mid, deltas, x01 = _sample_outputs(N, T, dev)
+    cnf, stride = _cnf(cam_near_far)
+    prev_bins, prev_weights = prev_bins.contiguous(), prev_weights.detach().contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(dev), _lib.stats.span("sample_pdf", N=N, T=T):
+        rc = lib.sanerf_sample_pdf(rays_o.data_ptr(), rays_d.data_ptr(), aabb.data_ptr(), float(min_near),
+                                   _lib.ptr(cnf), stride, prev_bins.data_ptr(), prev_weights.data_ptr(), T0,
+                                   _lib.ptr(noise), N, T, int(bool(contract)), float(bound), bins.data_ptr(),
+                                   t_mid.data_ptr(), deltas.data_ptr(), x01.data_ptr(), _stream(rays_o))
+    _lib.check(rc, "sample_pdf")
+    return bins, t_mid, deltas, x01
+
+
+# ----------------------------------------------------------------------------------------- proposal density
+class _PropDensity(Function):
+    @staticmethod
+    def forward(ctx, x01, table, offsets, w1, w2, S, H):
+        x01 = x01.contiguous()
+        B = x01.numel() // 3
+        L = offsets.numel() - 1
+        sigma = torch.empty(x01.shape[:-1], device=x01.device, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(x01.device), _lib.stats.span("prop_density_forward", B=B, L=L):
+            rc = lib.sanerf_prop_density_forward(x01.data_ptr(), table.data_ptr(), offsets.data_ptr(), w1.data_ptr(),
+                                                 w2.data_ptr(), B, L, float(S), int(H), sigma.data_ptr(), _stream(x01))
+        _lib.check(rc, "prop_density_forward")
+        ctx.save_for_backward(x01, table, offsets, w1, w2)
+        ctx.meta = (B, L, float(S), int(H))
+        return sigma
+
+    @staticmethod
+    def backward(ctx, g_sigma):
+        x01, table, offsets, w1, w2 = ctx.saved_tensors
+        B, L, S, H = ctx.meta
+        g_sigma = g_sigma.contiguous()
+        g_table, g_w1, g_w2 = torch.zeros_like(table), torch.zeros_like(w1), torch.zeros_like(w2)
+        lib = _lib.load()
+        with torch.cuda.device(x01.device), _lib.stats.span("prop_density_backward", B=B, L=L):
+            rc = lib.sanerf_prop_density_backward(x01.data_ptr(), table.data_ptr(), offsets.data_ptr(), w1.data_ptr(),
+                                                  w2.data_ptr(), B, L, S, H, g_sigma.data_ptr(), g_table.data_ptr(),
+                                                  g_w1.data_ptr(), g_w2.data_ptr(), _stream(x01))
+        _lib.check(rc, "prop_density_backward")
+        return None, g_table, None, g_w1, g_w2, None, None
+
+
+def prop_density_supported(encoder, mlp):
+    """The fused kernel covers the proposal networks the reference builds (network.py:211-219)."""
+    net = getattr(mlp, "net", None)
+    return (encoder.input_dim == 3 and encoder.level_dim == 2 and encoder.num_levels <= 8
+            and encoder.gridtype_id == 0 and encoder.interp_id == 0 and not encoder.align_corners
+            and encoder.embeddings.dtype == torch.float32 and net is not None and len(net) == 2
+            and net[0].bias is None and net[1].bias is None and net[0].out_features == 16
+            and net[0].in_features == 2 * encoder.num_levels and net[1].out_features == 1
+            and not torch.is_autocast_enabled())
+
+
+def prop_density(x01, encoder, mlp):
+    """sigma = trunc_exp(mlp(encoder(x))) for positions already mapped to [0,1]^3."""
+    return _PropDensity.apply(x01, encoder.embeddings, encoder.offsets, mlp.net[0].weight, mlp.net[1].weight,
+                              float(np.log2(encoder.per_level_scale)), int(encoder.base_resolution))
+
+
+# ----------------------------------------------------------------------------------------- head + composite
+class _HeadComposite(Function):
+    """f [N,T,W] = MLP output: column 0 -> sigma = exp(.), columns 1..W-1 composited in place (row stride W)."""
+
+    @staticmethod
+    def forward(ctx, f, deltas, ts, last_sample_opaque, t_thresh):
+        f = f.contiguous()
+        N, T, W = f.shape
+        C = W - 1
+        dev = f.device
+        deltas, ts = deltas.contiguous(), ts.contiguous()
+        sigma = torch.empty(N, T, device=dev)
+        weights = torch.empty(N, T, device=dev)
+        weights_sum, depth = torch.empty(N, device=dev), torch.empty(N, device=dev)
+        out = torch.empty(N, C, device=dev)
+        n_alive = torch.empty(N, device=dev, dtype=torch.int32)
+        lib = _lib.load()
+        st = _stream(f)
+        with torch.cuda.device(dev):
+            with _lib.stats.span("trunc_exp_forward", n=N * T):
+                rc = lib.sanerf_trunc_exp_forward(f.data_ptr(), sigma.data_ptr(), N * T, W, 0, st)
+            _lib.check(rc, "trunc_exp_forward")
+            with _lib.stats.span("composite_forward", N=N, T=T, C=C):
+                rc = lib.sanerf_composite_forward(sigma.data_ptr(), deltas.data_ptr(), ts.data_ptr(),
+                                                  f.data_ptr() + 4, W, None, N, T, C, int(bool(last_sample_opaque)),
+                                                  float(t_thresh), weights.data_ptr(), weights_sum.data_ptr(),
+                                                  depth.data_ptr(), out.data_ptr(), n_alive.data_ptr(), st)
+            _lib.check(rc, "composite_forward")
+        ctx.save_for_backward(f, sigma, deltas, ts, weights)
+        ctx.meta = (N, T, W, bool(last_sample_opaque), float(t_thresh))
+        ctx.mark_non_differentiable(n_alive)
+        return sigma, weights, weights_sum, depth, out, n_alive
+
+    @staticmethod
+    def backward(ctx, g_sigma_direct, g_weights, g_weights_sum, g_depth, g_out, _g_alive):
+        f, sigma, deltas, ts, weights = ctx.saved_tensors
+        N, T, W, opaque, t_thresh = ctx.meta
+        C = W - 1
+        dev = f.device
+        cont = lambda t: None if t is None else t.contiguous()  # noqa: E731
+        g_weights, g_weights_sum, g_depth, g_out = cont(g_weights), cont(g_weights_sum), cont(g_depth), cont(g_out)
+        grad_f = torch.empty_like(f)
+        grad_sigma = torch.empty(N, T, device=dev)
+        lib = _lib.load()
+        st = _stream(f)
+        with torch.cuda.device(dev):
+            with _lib.stats.span("composite_backward", N=N, T=T, C=C):
+                rc = lib.sanerf_composite_backward(sigma.data_ptr(), deltas.data_ptr(), ts.data_ptr(), f.data_ptr() + 4,
+                                                   W, None, N, T, C, int(opaque), t_thresh, weights.data_ptr(),
+                                                   _lib.ptr(g_weights), _lib.ptr(g_weights_sum), _lib.ptr(g_depth),
+                                                   _lib.ptr(g_out), grad_sigma.data_ptr(), grad_f.data_ptr() + 4, W, st)
+            _lib.check(rc, "composite_backward")
+            if g_sigma_direct is not None:
+                grad_sigma = grad_sigma + g_sigma_direct
+            with _lib.stats.span("trunc_exp_backward", n=N * T):
+                rc = lib.sanerf_trunc_exp_backward(grad_sigma.data_ptr(), f.data_ptr(), grad_f.data_ptr(), N * T, W, 0, st)
+            _lib.check(rc, "trunc_exp_backward")
+        return grad_f, None, None, None, None
+
+
+def head_composite(f, deltas, ts, last_sample_opaque=True, t_thresh=0.0):
+    """Returns sigma [N,T], weights [N,T], weights_sum [N], depth [N], out [N,W-1], n_alive [N]."""
+    return _HeadComposite.apply(f, deltas, ts, last_sample_opaque, t_thresh)
+
+
+# ----------------------------------------------------------------------------------------- losses
+class _ProposalLoss(Function):
+    """sum over proposal levels of the inter-level loss; weights of the final level are constants."""
+
+    @staticmethod
+    def forward(ctx, t_ref, w_ref, *levels):
+        t_ref, w_ref = t_ref.contiguous(), w_ref.detach().contiguous()
+        N, Tr = w_ref.shape
+        loss = torch.zeros(1, device=w_ref.device)
+        grads = []
+        lib = _lib.load()
+        with torch.cuda.device(w_ref.device):
+            for t_p, w_p in zip(levels[0::2], levels[1::2]):
+                t_p, w_p = t_p.contiguous(), w_p.contiguous()
+                g = torch.empty_like(w_p)
+                with _lib.stats.span("proposal_loss", N=N, Tp=w_p.shape[1]):
+                    rc = lib.sanerf_proposal_loss(t_ref.data_ptr(), w_ref.data_ptr(), Tr, t_p.data_ptr(), w_p.data_ptr(),
+                                                  w_p.shape[1], N, loss.data_ptr(), g.data_ptr(), _stream(w_ref))
+                _lib.check(rc, "proposal_loss")
+                grads.append(g)
+        ctx.save_for_backward(*grads)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        out = [None, None]
+        for gw in ctx.saved_tensors:
+            out += [None, gw * g]
+        return tuple(out)
+
+
+def proposal_loss(all_bins, all_weights):
+    """renderer.py:30-57 — last entries are the (detached) final level."""
+    args = []
+    for b, w in zip(all_bins[:-1], all_weights[:-1]):
+        args += [b, w]
+    return _ProposalLoss.apply(all_bins[-1], all_weights[-1], *args)
+
+
+class _DistortLoss(Function):
+    @staticmethod
+    def forward(ctx, bins, weights):
+        bins, weights = bins.contiguous(), weights.contiguous()
+        N, T = weights.shape
+        loss = torch.zeros(1, device=weights.device)
+        g = torch.empty_like(weights)
+        lib = _lib.load()
+        with torch.cuda.device(weights.device), _lib.stats.span("distortion_loss", N=N, T=T):
+            rc = lib.sanerf_distortion_loss(bins.data_ptr(), weights.data_ptr(), T, N, loss.data_ptr(), g.data_ptr(),
+                                            _stream(weights))
+        _lib.check(rc, "distortion_loss")
+        ctx.save_for_backward(g)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, ctx.saved_tensors[0] * g
+
+
+def distort_loss(bins, weights):
+    """renderer.py:17-27."""
+    return _DistortLoss.apply(bins, weights)
+
+
+# ----------------------------------------------------------------------------------------- optimizer
+class FusedAdam:
+    """Adam(eps=1e-15) + LambdaLR(0.1**min(it/iters,1)) over parameters flattened into ONE fp32 buffer.
+
+    Parameters and gradients become views of ``flat_param`` / ``flat_grad`` (the gradient bucket doubles as the
+    NCCL all-reduce buffer); one kernel updates everything and clears the gradient in the same pass.  The step
+    counter and the schedule live on the device, so a captured CUDA graph replays with a moving learning rate.
+    """
+
+    def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]     # keep every view 16-byte aligned
+        total = sum(sizes)
+        self.flat_param = torch.zeros(total, device=dev)
+        self.flat_grad = torch.zeros(total, device=dev)
+        self.exp_avg = torch.zeros(total, device=dev)
+        self.exp_avg_sq = torch.zeros(total, device=dev)
+        off = 0
+        for p, n in zip(self.params, sizes):
+            view = self.flat_param[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += n
+        self.lr, self.betas, self.eps, self.decay_iters = float(lr), betas, float(eps), float(decay_iters)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.dyn = torch.zeros(4, device=dev)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def step(self, grad_scale=1.0, zero_grad=True):
+        lib = _lib.load()
+        dev = self.flat_param.device
+        st = _lib.current_stream(dev)
+        with torch.cuda.device(dev):
+            with _lib.stats.span("adam_schedule"):
+                rc = lib.sanerf_adam_schedule(self.step_count.data_ptr(), self.dyn.data_ptr(), self.lr, self.betas[0],
+                                              self.betas[1], self.decay_iters, st)
+            _lib.check(rc, "adam_schedule")
+            with _lib.stats.span("adam_step", n=self.flat_param.numel()):
+                rc = lib.sanerf_adam_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.dyn.data_ptr(),
+                                          self.betas[0], self.betas[1], self.eps, float(grad_scale), int(zero_grad), st)
+            _lib.check(rc, "adam_step")

@@ -46,7 +46,7 @@ class _Composite(Function):
         lib = _lib.load()
         with torch.cuda.device(dev), _lib.stats.span("composite_forward", N=N, T=T, C=C):
             rc = lib.sanerf_composite_forward(
-                sigmas.data_ptr(), deltas.data_ptr(), ts.data_ptr(), _lib.ptr(feats), _lib.ptr(ray_offsets),
+                sigmas.data_ptr(), deltas.data_ptr(), ts.data_ptr(), _lib.ptr(feats), 0, _lib.ptr(ray_offsets),
                 N, T, C, int(bool(last_sample_opaque)), float(t_thresh), weights.data_ptr(),
                 weights_sum.data_ptr(), depth.data_ptr(), out.data_ptr() if C else None, n_alive.data_ptr(),
                 _lib.current_stream(dev))
@@ -70,9 +70,9 @@ class _Composite(Function):
         lib = _lib.load()
         with torch.cuda.device(sigmas.device), _lib.stats.span("composite_backward", N=N, T=T, C=C):
             rc = lib.sanerf_composite_backward(
-                sigmas.data_ptr(), deltas.data_ptr(), ts.data_ptr(), _lib.ptr(feats), _lib.ptr(ray_offsets),
+                sigmas.data_ptr(), deltas.data_ptr(), ts.data_ptr(), _lib.ptr(feats), 0, _lib.ptr(ray_offsets),
                 N, T, C, int(opaque), t_thresh, weights.data_ptr(), _lib.ptr(g_weights), _lib.ptr(g_weights_sum),
-                _lib.ptr(g_depth), _lib.ptr(g_out), grad_sigmas.data_ptr(), _lib.ptr(grad_feats),
+                _lib.ptr(g_depth), _lib.ptr(g_out), grad_sigmas.data_ptr(), _lib.ptr(grad_feats), 0,
                 _lib.current_stream(sigmas.device))
         _lib.check(rc, "composite_backward")
         return grad_sigmas, None, None, grad_feats, None, None, None, None

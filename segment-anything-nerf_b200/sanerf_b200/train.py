@@ -16,6 +16,8 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from .fused import FusedAdam
+
 
 def default_opt(**overrides):
     """The flags the shipped system actually runs with (main.py:222-226 hard overrides + defaults)."""
@@ -28,29 +30,6 @@ def default_opt(**overrides):
     return opt
 
 
-class FlatGradBucket:
-    """All trainable gradients as views of one flat fp32 buffer, so the data-parallel exchange is a single
-    all-reduce (57 MB in stage 1, 170 MB in stage 2 — SURVEY §5)."""
-
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        ref = self.params[0]
-        self.flat = torch.zeros(total, device=ref.device, dtype=torch.float32)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-
-    def zero(self):
-        self.flat.zero_()
-
-    def all_reduce_mean(self, world_size):
-        if world_size > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(world_size)
-
-
 class RGBTrainer:
     """Stage-1 step: ``step(rays_o, rays_d, gt_rgb) -> loss`` (device tensors), with optional DDP-style sharding."""
 
@@ -59,10 +38,9 @@ class RGBTrainer:
         self.world_size = world_size
         self.global_step = 0
         params = [p for p in model.parameters() if p.requires_grad]
-        self.bucket = FlatGradBucket(params)
-        # Adam(eps=1e-15) + LambdaLR 0.1**min(iter/iters,1)  (main.py:296,312-313)
-        self.optimizer = torch.optim.Adam(model.get_params(lr), eps=1e-15, fused=True)
-        self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lambda it: 0.1 ** min(it / iters, 1))
+        # Adam(eps=1e-15) + LambdaLR 0.1**min(iter/iters,1)  (main.py:296,312-313) on flat buffers; the flat
+        # gradient doubles as the all-reduce bucket and is cleared by the optimizer kernel
+        self.optimizer = FusedAdam(params, lr=lr, eps=1e-15, decay_iters=iters)
 
     def loss(self, rays_o, rays_d, gt_rgb, update_proposal=True, perturb=True):
         out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=perturb,
@@ -77,12 +55,11 @@ class RGBTrainer:
     def step(self, rays_o, rays_d, gt_rgb):
         self.global_step += 1
         update_proposal = self.global_step <= 3000 or self.global_step % 5 == 0   # nerf/utils.py:910-911
-        self.bucket.zero()
         loss, _ = self.loss(rays_o, rays_d, gt_rgb, update_proposal)
-        loss.backward()
-        self.bucket.all_reduce_mean(self.world_size)
-        self.optimizer.step()
-        self.scheduler.step()
+        loss.backward()                                   # accumulates into the (pre-zeroed) flat gradient
+        if self.world_size > 1:
+            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+        self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
         return loss.detach()
 
 
@@ -99,14 +76,11 @@ class SAMTrainer:
             trainable.update(id(p) for p in m.parameters())
         for p in model.parameters():                      # main.py:255-262: freeze what stage 1 trained
             p.requires_grad_(id(p) in trainable)
-        self.bucket = FlatGradBucket([p for p in model.parameters() if p.requires_grad])
-        groups = [{"params": [p for p in m.parameters()], "lr": lr} for m in (model.s_grid, model.samvit_mlp)]
-        self.optimizer = torch.optim.Adam(groups, eps=1e-15, fused=True)
-        self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lambda it: 0.1 ** min(it / iters, 1))
+        self.optimizer = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=lr, eps=1e-15,
+                                   decay_iters=iters)
 
     def step(self, rays_o, rays_d, target, h, w):
         """target: [1, 256, H_t, W_t]; prediction is bilinearly resized to it (nerf/utils.py:1100-1106)."""
-        self.bucket.zero()
         out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=False, update_proposal=False,
                                 return_feats=1, H=h, W=w)
         pred = out["samvit"].permute(2, 0, 1).unsqueeze(0)
@@ -114,9 +88,9 @@ class SAMTrainer:
             pred = F.interpolate(pred, target.shape[-2:], mode="bilinear")
         loss = F.mse_loss(pred, target)
         loss.backward()
-        self.bucket.all_reduce_mean(self.world_size)
-        self.optimizer.step()
-        self.scheduler.step()
+        if self.world_size > 1:
+            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+        self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
         return loss.detach()
 
 
