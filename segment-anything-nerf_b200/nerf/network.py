@@ -73,6 +73,9 @@ class NeRFNetwork(NeRFRenderer):
         if getattr(opt, "with_mask", False):
             raise NotImplementedError("mask heads (stage 3) are outside the B200 render path")
         self.geom_feat_dim = 15
+        # tensor-core field head (sanerf_b200/fused.py): "fp32" = 3xTF32 split products (fp32 parity), "tf32" = one pass
+        self.tc_head = bool(getattr(opt, "tc_head", True))
+        self.mlp_precision = getattr(opt, "mlp_precision", "fp32")
 
         self.grid, self.grid_in_dim = get_encoder("hashgrid", input_dim=3, level_dim=2, num_levels=16,
                                                   log2_hashmap_size=19, desired_resolution=2048 * self.bound)
@@ -132,6 +135,8 @@ class NeRFNetwork(NeRFRenderer):
 
     def head_unit(self, x01):
         """[N,T,3] -> [N,T,16]: grid_mlp(grid(x)); column 0 is the density logit (network.py:223-227)."""
+        if self.tc_head and fused.field_head_supported(self.grid, self.grid_mlp):
+            return fused.field_head(x01, self.grid, self.grid_mlp, self.mlp_precision)
         return self.grid_mlp(self._encode_unit(self.grid, x01))
 
     def features_unit(self, x01):

@@ -120,6 +120,79 @@ def prop_density(x01, encoder, mlp):
                               float(np.log2(encoder.per_level_scale)), int(encoder.base_resolution))
 
 
+# ----------------------------------------------------------------------------------------- field head (tensor cores)
+PRECISION_IDS = {"fp32": 0, "tf32": 1}
+
+
+class _FieldHead(Function):
+    """out [.., 16] = grid_mlp(grid(x)) in ONE tcgen05 kernel; backward = one tcgen05 kernel (data + weight
+    gradients of the MLP) + the hash-grid scatter."""
+
+    @staticmethod
+    def forward(ctx, x01, table, offsets, w1, w2, w3, S, H, precision):
+        x01 = x01.contiguous()
+        B = x01.numel() // 3
+        dev = x01.device
+        need_grad = any(ctx.needs_input_grad[1:6])
+        out = torch.empty(*x01.shape[:-1], 16, device=dev, dtype=torch.float32)
+        enc = torch.empty(B, 32, device=dev, dtype=torch.float32) if need_grad else None
+        w1, w2, w3 = w1.contiguous(), w2.contiguous(), w3.contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(dev), _lib.stats.span("field_head_forward", B=B):
+            rc = lib.sanerf_field_head_forward(x01.data_ptr(), table.data_ptr(), offsets.data_ptr(), float(S), int(H),
+                                               None, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, _lib.ptr(enc),
+                                               out.data_ptr(), int(precision), _stream(x01))
+        _lib.check(rc, "field_head_forward")
+        if need_grad:
+            ctx.save_for_backward(x01, table, offsets, w1, w2, w3, enc)
+            ctx.meta = (B, float(S), int(H), int(precision))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x01, table, offsets, w1, w2, w3, enc = ctx.saved_tensors
+        B, S, H, precision = ctx.meta
+        dev = x01.device
+        g_out = g_out.contiguous()
+        g_enc = torch.empty(B, 32, device=dev, dtype=torch.float32)
+        g_w1, g_w2, g_w3 = torch.zeros_like(w1), torch.zeros_like(w2), torch.zeros_like(w3)
+        lib = _lib.load()
+        st = _stream(x01)
+        with torch.cuda.device(dev):
+            with _lib.stats.span("field_head_backward", B=B):
+                rc = lib.sanerf_field_head_backward(enc.data_ptr(), g_out.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                                                    w3.data_ptr(), B, g_enc.data_ptr(), g_w1.data_ptr(), g_w2.data_ptr(),
+                                                    g_w3.data_ptr(), precision, st)
+            _lib.check(rc, "field_head_backward")
+            g_table = None
+            if ctx.needs_input_grad[1]:
+                g_table = torch.zeros_like(table)
+                with _lib.stats.span("grid_encode_backward", B=B, L=16, C=2, D=3, half=False):
+                    rc = lib.sanerf_grid_encode_backward(g_enc.data_ptr(), x01.data_ptr(), table.data_ptr(),
+                                                         offsets.data_ptr(), g_table.data_ptr(), B, 3, 2, 16, 16, S, H,
+                                                         None, None, 0, 0, 0, _lib.SANERF_F32, _lib.LAYOUT_BLC, st)
+                _lib.check(rc, "grid_encode_backward")
+        return None, g_table, None, g_w1, g_w2, g_w3, None, None, None
+
+
+def field_head_supported(encoder, mlp):
+    """The fused kernel covers the main grid + grid_mlp the reference builds (network.py:102-103)."""
+    net = getattr(mlp, "net", None)
+    return (encoder.input_dim == 3 and encoder.level_dim == 2 and encoder.num_levels == 16
+            and encoder.gridtype_id == 0 and encoder.interp_id == 0 and not encoder.align_corners
+            and encoder.embeddings.dtype == torch.float32 and net is not None and len(net) == 3
+            and all(l.bias is None for l in net) and tuple(net[0].weight.shape) == (64, 32)
+            and tuple(net[1].weight.shape) == (64, 64) and tuple(net[2].weight.shape) == (16, 64)
+            and not torch.is_autocast_enabled())
+
+
+def field_head(x01, encoder, mlp, precision="fp32"):
+    """[.., 3] positions in [0,1]^3 -> [.., 16] = mlp(encoder(x)) (column 0: density logit, 1..15: geometry feature)."""
+    return _FieldHead.apply(x01, encoder.embeddings, encoder.offsets, mlp.net[0].weight, mlp.net[1].weight,
+                            mlp.net[2].weight, float(np.log2(encoder.per_level_scale)), int(encoder.base_resolution),
+                            PRECISION_IDS[precision])
+
+
 # ----------------------------------------------------------------------------------------- head + composite
 class _HeadComposite(Function):
     """f [N,T,W] = MLP output: column 0 -> sigma = exp(.), columns 1..W-1 composited in place (row stride W)."""

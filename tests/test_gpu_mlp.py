@@ -1,0 +1,153 @@
+"""tcgen05 (UMMA) tile products and the fused tensor-core MLP head against plain fp32 matmuls."""
+import pytest
+import torch
+
+from sanerf_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _selftest(mode, M, N, K, A, B):
+    lib = _lib.load()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    rc = lib.sanerf_umma_selftest(mode, M, N, K, A.data_ptr(), B.data_ptr(), D.data_ptr(),
+                                  _lib.current_stream(A.device))
+    _lib.check(rc, "umma_selftest")
+    torch.cuda.synchronize()
+    return D
+
+
+def _ints(*shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-8, 9, shape, generator=g).float().cuda()      # exact in tf32, products exact in fp32
+
+
+@pytest.mark.parametrize("N,K", [(64, 32), (64, 64), (16, 64), (32, 8), (128, 128)])
+def test_umma_k_major_exact(cuda, N, K):
+    A, B = _ints(128, K, seed=1), _ints(N, K, seed=2)
+    D = _selftest(0, 128, N, K, A, B)
+    assert torch.equal(D, A @ B.t())
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 32, 128), (64, 64, 128), (64, 16, 128), (128, 64, 64), (64, 16, 8)])
+def test_umma_mn_major_exact(cuda, M, N, K):
+    At, Bt = _ints(K, M, seed=3), _ints(K, N, seed=4)
+    D = _selftest(1, M, N, K, At, Bt)
+    assert torch.equal(D, At.t() @ Bt)
+
+
+@pytest.mark.parametrize("N,K", [(64, 64), (16, 64), (64, 32)])
+def test_umma_a_from_tmem_exact(cuda, N, K):
+    A, B = _ints(128, K, seed=5), _ints(N, K, seed=6)
+    D = _selftest(2, 128, N, K, A, B)
+    assert torch.equal(D, A @ B.t())
+
+
+def test_umma_3xtf32_is_fp32_accurate(cuda):
+    g = torch.Generator().manual_seed(7)
+    A, B = torch.randn(128, 64, generator=g).cuda(), torch.randn(64, 64, generator=g).cuda()
+    ref = (A.double() @ B.double().t())
+    one = _selftest(0, 128, 64, 64, A, B).double()
+    three = _selftest(3, 128, 64, 64, A, B).double()
+    err1 = ((one - ref).abs().max() / ref.abs().max()).item()
+    err3 = ((three - ref).abs().max() / ref.abs().max()).item()
+    assert err1 < 5e-3                      # single-pass tf32: ~2^-10 relative operand truncation
+    assert err3 < 2e-6, (err1, err3)        # split product: fp32-level
+
+
+# ------------------------------------------------------------------------------------------ fused field head
+def _head_setup(B, seed=0, table_scale=1.0):
+    from gridencoder import GridEncoder
+    torch.manual_seed(seed)
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                      desired_resolution=4096).cuda()
+    with torch.no_grad():
+        enc.embeddings.normal_(0, table_scale)
+    w1 = (torch.randn(64, 32) / 32 ** 0.5).cuda().requires_grad_(True)
+    w2 = (torch.randn(64, 64) / 64 ** 0.5).cuda().requires_grad_(True)
+    w3 = (torch.randn(16, 64) / 64 ** 0.5).cuda().requires_grad_(True)
+    x01 = torch.rand(B, 3, device="cuda")
+    x01[::97] = 1.5            # out-of-range samples encode to zero (gridencoder.cu:105-130)
+    return enc, w1, w2, w3, x01
+
+
+def _head_call(x01, enc, w1, w2, w3, precision, enc_in=None, want_enc=True):
+    import numpy as np
+    lib = _lib.load()
+    B = x01.shape[0] if x01 is not None else enc_in.shape[0]
+    out = torch.full((B, 16), float("nan"), device="cuda")
+    enc_out = torch.full((B, 32), float("nan"), device="cuda") if want_enc else None
+    rc = lib.sanerf_field_head_forward(_lib.ptr(x01), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
+                                       float(np.log2(enc.per_level_scale)), int(enc.base_resolution), _lib.ptr(enc_in),
+                                       w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, _lib.ptr(enc_out), out.data_ptr(),
+                                       precision, _lib.current_stream(out.device))
+    _lib.check(rc, "field_head_forward")
+    torch.cuda.synchronize()
+    return out, enc_out
+
+
+def _mlp64(e, w1, w2, w3):
+    h = torch.relu(e.double() @ w1.double().t())
+    h = torch.relu(h @ w2.double().t())
+    return h @ w3.double().t()
+
+
+@pytest.mark.parametrize("B", [1000, 128 * 148 * 3 + 77])
+def test_field_head_forward_matches_fp32_path(cuda, B):
+    from gridencoder.grid import grid_encode
+    enc, w1, w2, w3, x01 = _head_setup(B)
+    ref_enc = grid_encode(x01, enc.embeddings, enc.offsets, enc.per_level_scale, enc.base_resolution).detach()
+    ref = _mlp64(ref_enc, w1, w2, w3)
+    out, enc_out = _head_call(x01, enc, w1.detach(), w2.detach(), w3.detach(), 0)
+    assert torch.equal(enc_out, ref_enc)                       # the gather is the reference kernel's arithmetic
+    scale = ref.abs().max().item()
+    assert ((out.double() - ref).abs().max().item()) < 2e-6 * scale     # 3xTF32: fp32-level
+    fast, _ = _head_call(x01, enc, w1.detach(), w2.detach(), w3.detach(), 1, want_enc=False)
+    assert ((fast.double() - ref).abs().max().item()) < 1e-2 * scale    # single tf32 pass
+    # encoding supplied by the caller instead of gathered
+    out2, _ = _head_call(None, enc, w1.detach(), w2.detach(), w3.detach(), 0, enc_in=ref_enc, want_enc=False)
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("B", [300, 128 * 148 * 2 + 5])
+def test_field_head_backward_matches_autograd(cuda, B):
+    enc, w1, w2, w3, x01 = _head_setup(B, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    e = torch.randn(B, 32, device="cuda", generator=g)
+    g_out = torch.randn(B, 16, device="cuda", generator=g)
+    e64 = e.double().requires_grad_(True)
+    ws = [w.detach().double().requires_grad_(True) for w in (w1, w2, w3)]
+    (_mlp64(e64, *ws) * g_out.double()).sum().backward()
+    lib = _lib.load()
+    g_enc = torch.full((B, 32), float("nan"), device="cuda")
+    gw = [torch.zeros_like(w) for w in (w1, w2, w3)]
+    rc = lib.sanerf_field_head_backward(e.data_ptr(), g_out.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B,
+                                        g_enc.data_ptr(), gw[0].data_ptr(), gw[1].data_ptr(), gw[2].data_ptr(), 0,
+                                        _lib.current_stream(e.device))
+    _lib.check(rc, "field_head_backward")
+    torch.cuda.synchronize()
+    def rel(a, b):
+        return ((a.double() - b).abs().max() / b.abs().max()).item()
+    assert rel(g_enc, e64.grad) < 5e-6
+    for got, ref, name in zip(gw, ws, ("w1", "w2", "w3")):
+        assert rel(got, ref.grad) < 1e-5, name
+
+
+def test_field_head_autograd_equals_unfused(cuda):
+    """The drop-in check: the model's head with the fused kernel == GridEncoder + nn.Linear MLP, values and grads."""
+    from nerf.network import MLP
+    from sanerf_b200 import fused
+    enc, _, _, _, x01 = _head_setup(5000, seed=4, table_scale=0.3)
+    mlp = MLP(32, 16, 64, 3, bias=False).cuda()
+    x = x01.view(50, 100, 3)
+    out = fused.field_head(x, enc, mlp)
+    from gridencoder.grid import grid_encode
+    ref = mlp(grid_encode(x.reshape(-1, 3), enc.embeddings, enc.offsets, enc.per_level_scale,
+                          enc.base_resolution).view(50, 100, 32))
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5 * ref.abs().max().item())
+    go = torch.randn_like(ref)
+    params = [enc.embeddings] + [l.weight for l in mlp.net]
+    g_ref = torch.autograd.grad(ref, params, go)
+    g_new = torch.autograd.grad(out, params, go)
+    for a, b in zip(g_new, g_ref):
+        assert ((a - b).norm() / b.norm()).item() < 1e-4
