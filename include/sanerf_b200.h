@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 5
+#define SANERF_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -241,19 +241,24 @@ SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
  *  x01 f32 [B,3] in [0,1]^3 (grid.py:156 mapping already applied), or NULL to read the encoding from enc_in [B,32];
  *  enc_out f32 [B,32] or NULL: the encoding, saved for the backward (bit-identical to sanerf_grid_encode_forward);
  *  precision 0: fp32 parity (every product as a 3-term tf32 split, fp32 accumulate), 1: one tf32 pass.
- * Backward: from enc [B,32] and g_out [B,16] produces g_enc [B,32] (feed it to sanerf_grid_encode_backward, layout
- * [B,L*C]) and ACCUMULATES the weight gradients into g_w1 / g_w2 / g_w3 (caller zero-fills).
+ *  h1_out / h2_out f32 [B,64] or both NULL: the post-ReLU activations of layers 1 and 2, saved for the backward.
+ * Backward: from enc [B,32], h1, h2 [B,64] and g_out [B,16] produces g_enc [B,32] (feed it to
+ * sanerf_grid_encode_backward, layout [B,L*C]) and ACCUMULATES the weight gradients into g_w1 / g_w2 / g_w3
+ * (caller zero-fills).  Data gradients: A operand in tensor memory x transposed weight; weight gradients: MN-major
+ * operands in the 128-byte-swizzle / 32-byte-atom layout, accumulated in tensor memory over the CTA's tiles.
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_field_head_forward(const float* x01, const float* table, const int32_t* offsets, float S,
                               uint32_t H, const float* enc_in, const float* w1, const float* w2, const float* w3,
-                              uint32_t B, float* enc_out, float* out, int precision, void* stream);
-SANERF_API int sanerf_field_head_backward(const float* enc, const float* g_out, const float* w1, const float* w2,
-                               const float* w3, uint32_t B, float* g_enc, float* g_w1, float* g_w2, float* g_w3,
-                               int precision, void* stream);
+                              uint32_t B, float* enc_out, float* h1_out, float* h2_out, float* out, int precision,
+                              void* stream);
+SANERF_API int sanerf_field_head_backward(const float* enc, const float* h1, const float* h2, const float* g_out,
+                               const float* w1, const float* w2, const float* w3, uint32_t B, float* g_enc,
+                               float* g_w1, float* g_w2, float* g_w3, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics (no reference equivalent): one tcgen05 tile product D[M,N] with operands staged the way the fused
- * MLP kernels stage them.  mode 0: A[M,K], B[N,K] both K-major; 1: At[K,M], Bt[K,N] both MN-major (M = 64 or 128);
+ * MLP kernels stage them.  mode 0: A[M,K], B[N,K] both K-major; 1: At[K,M], Bt[K,N] both MN-major (M = 64 or 128;
+ * 128-byte swizzle with 32-byte atoms, the only MN-major form 32-bit operands have);
  * 2: as 0 with A resident in TMEM; 3: as 0 with the 3xTF32 split.  M = 128 otherwise; N, K multiples of 16 / 8.
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_umma_selftest(int mode, uint32_t M, uint32_t N, uint32_t K, const float* A, const float* B,

@@ -46,6 +46,8 @@ struct HeadFwdParams {
     const float* w2;         // [64,64]
     const float* w3;         // [16,64]
     float* enc_out;          // [B,32] or NULL
+    float* h1_out;           // [B,64] or NULL: relu(layer 1), saved for the backward
+    float* h2_out;           // [B,64] or NULL: relu(layer 2)
     float* out;              // [B,16]
     uint32_t B, H;
     float S;
@@ -111,15 +113,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // TMEM accumulator (64 columns of this thread's lane) -> ReLU -> hi/lo planes of the chunk-major H tile
-__device__ __forceinline__ void relu_to_smem(uint32_t tmem_lane_col, uint8_t* h_hi, uint8_t* h_lo, uint32_t row, bool split) {
+// `save` = this sample's row of the [B,64] activation kept for the backward (or NULL)
+__device__ __forceinline__ void relu_to_smem(uint32_t tmem_lane_col, uint8_t* h_hi, uint8_t* h_lo, uint32_t row, bool split,
+                                             float* save) {
 #pragma unroll
     for (uint32_t c0 = 0; c0 < head::kHid; c0 += 16) {
         float v[16];
         umma::tmem_ld16(tmem_lane_col + c0, v);
 #pragma unroll
-        for (uint32_t j = 0; j < 16; j += 4)
-            put_chunk(h_hi, h_lo, head::kTile, row, (c0 + j) >> 2, fmaxf(v[j], 0.0f), fmaxf(v[j + 1], 0.0f),
-                      fmaxf(v[j + 2], 0.0f), fmaxf(v[j + 3], 0.0f), split);
+        for (uint32_t j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j += 4) {
+            put_chunk(h_hi, h_lo, head::kTile, row, (c0 + j) >> 2, v[j], v[j + 1], v[j + 2], v[j + 3], split);
+            if (save != nullptr) *reinterpret_cast<float4*>(save + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
     }
 }
 
@@ -246,7 +253,9 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             }
             umma::mbar_wait(umma::smem_u32(&s_mma), mma_phase); mma_phase ^= 1u;
             umma::fence_after_sync();
-            relu_to_smem(lane_base + cD1, h_hi, h_lo, tid, split);
+            const uint32_t b = tile * kTile + tid;
+            const bool keep = (p.h1_out != nullptr) && b < p.B;
+            relu_to_smem(lane_base + cD1, h_hi, h_lo, tid, split, keep ? p.h1_out + (size_t)b * kHid : nullptr);
             umma::fence_proxy_async();
             umma::fence_before_sync();
             named_bar_sync(1, kMlpWarps * 32);
@@ -257,7 +266,8 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             }
             umma::mbar_wait(umma::smem_u32(&s_mma), mma_phase); mma_phase ^= 1u;
             umma::fence_after_sync();
-            relu_to_smem(lane_base + cD2, h_hi, h_lo, tid, split);   // layer 2 has completed: H may be overwritten
+            relu_to_smem(lane_base + cD2, h_hi, h_lo, tid, split,    // layer 2 has completed: H may be overwritten
+                         keep ? p.h2_out + (size_t)b * kHid : nullptr);
             umma::fence_proxy_async();
             umma::fence_before_sync();
             named_bar_sync(1, kMlpWarps * 32);
@@ -270,7 +280,6 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             umma::fence_after_sync();
             float v[16];
             umma::tmem_ld16(lane_base + cD3, v);
-            const uint32_t b = tile * kTile + tid;
             if (b < p.B) {
                 float4* dst = reinterpret_cast<float4*>(p.out + (size_t)b * kOut);
 #pragma unroll
@@ -286,27 +295,44 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
 
 
 // ================================================= backward =================================================
-// Per 128-sample tile (all operands chunk-major in shared memory, hi/lo planes; X and Y are 128x64 buffers):
-//   0. enc -> Y (as A1), g_out -> G3
-//   1. D1 = A1 W1^T                  H1 = relu(D1) -> X          (mask1 kept in registers)
-//   2. D2 = H1 W2^T                  H2 = relu(D2) -> Y          (mask2)
-//   3. dW3^T += H2^T G3 ; DG2 = G3 W3        G2 = DG2 * mask2 -> Y
-//   4. dW2   += G2^T H1 ; DG1 = G2 W2        G1 = DG1 * mask1 -> X ;  enc -> Y (as A1 again)
-//   5. dW1   += G1^T A1 ; DGE = G1 W1        g_enc = DGE -> HBM
-// The three weight gradients accumulate in TMEM (M = 64 accumulators) over all tiles of the persistent CTA and are
-// added to HBM once per CTA.  The same shared-memory image of a tile serves as K-major operand (rows = samples) in
-// the data-gradient products and as MN-major operand (contraction over the 128 samples) in the weight-gradient
-// products; the same image of a weight serves forward (K-major B) and backward (MN-major B).
+// Inputs per sample: enc [32], H1 = relu(D1) [64], H2 = relu(D2) [64] (saved by the forward), g_out [16].
+// Per 128-sample tile:
+//   3. dW3^T += H2^T G3 ;  DG2 = G3 W3        G2 = DG2 * [H2 > 0]
+//   4. dW2   += G2^T H1 ;  DG1 = G2 W2        G1 = DG1 * [H1 > 0]
+//   5. dW1   += G1^T A1 ;  DGE = G1 W1        g_enc = DGE -> HBM
+// Operand placement
+//   * data-gradient products (contraction over features): A = the gradient tile in TENSOR MEMORY (lane = sample,
+//     columns = features, hi/lo planes written with tcgen05.st), B = the TRANSPOSED weight, K-major in shared memory;
+//   * weight-gradient products (contraction over the 128 samples): both operands MN-major in shared memory.  32-bit
+//     MN-major operands exist only in the 128-byte-swizzle / 32-byte-atom layout (umma::mn32_off), so every
+//     activation / gradient tile is written once more in that layout: a row of the tile is a contraction row, each
+//     thread writes its own sample's row with 16-byte stores.
+//   * the three weight gradients accumulate in tensor memory (M = 64 accumulators) over all tiles of the persistent
+//     CTA and are added to HBM once per CTA.
+// Warps 0-3 own the TMEM lanes (thread t <-> sample t of the tile: masks, splits, epilogues); warps 4-7 prefetch the
+// NEXT tile's H1 / H2 / g_out rows into registers while the current tile computes and dump them into shared / tensor
+// memory at the tile boundary.
 namespace head {
-constexpr uint32_t kG3 = kTile * kOut * 4;
-constexpr uint32_t oX = oW3 + 2 * kW3, oY = oX + 2 * kH, oG3 = oY + 2 * kH;
-constexpr uint32_t kBwdSmem = oG3 + 2 * kG3;
-constexpr uint32_t cDG2 = 128, cDG1 = 192, cDGE = 256, cW1 = 288, cW2 = 320, cW3 = 384, kBwdTmemCols = 512;
-constexpr uint32_t kBwdThreads = 128;
+constexpr uint32_t kMn64 = kTile * 128u * 2u;      // one plane of a 64-wide MN-major tile (two 32-wide blocks)
+constexpr uint32_t kMn32 = kTile * 128u;           // one plane of a 32-wide (or padded 16-wide) MN-major tile
+constexpr uint32_t kMnLbo = kTile * 128u, kMnSbo = 512u;
+// transposed weights (K-major, chunk-major, hi then lo): W3^T [64][16], W2^T [64][64], W1^T [32][64]
+constexpr uint32_t oT3 = 0, oT2 = oT3 + 2 * kW3, oT1 = oT2 + 2 * kW2;
+constexpr uint32_t oBufA = oT1 + 2 * kW1;          // H1 (64-wide), later A1 (32-wide)
+constexpr uint32_t oBufB = oBufA + 2 * kMn64;      // H2, then G2, then G1 (64-wide)
+constexpr uint32_t oBufG = oBufB + 2 * kMn64;      // G3 (16-wide, padded)
+constexpr uint32_t kBwdSmem = oBufG + 2 * kMn32 + 1024;     // + slack to align the base to 1024 bytes
+static_assert(oBufA % 1024 == 0 && oBufB % 1024 == 0 && oBufG % 1024 == 0, "swizzled tiles need aligned bases");
+static_assert(kBwdSmem <= 227 * 1024, "backward tiles exceed shared memory");
+// TMEM columns: A-operand staging (hi, lo), data-gradient accumulator, weight-gradient accumulators (M = 64)
+constexpr uint32_t cAhi = 0, cAlo = 64, cDG = 128, cW2 = 192, cW1 = 256, cW3 = 288, kBwdTmemCols = 512;
+constexpr uint32_t kBwdThreads = 256;
 }  // namespace head
 
 struct HeadBwdParams {
     const float* enc;     // [B,32]
+    const float* h1;      // [B,64]
+    const float* h2;      // [B,64]
     const float* g_out;   // [B,16]
     const float* w1;
     const float* w2;
@@ -319,207 +345,255 @@ struct HeadBwdParams {
     int precision;
 };
 
-// D[M, N] (+)= At^T . Bt : both operands MN-major views of chunk-major tiles whose ROWS are the contraction index
-template <uint32_t M, uint32_t N, uint32_t KROWS>
-__device__ __forceinline__ void issue_gemm_mn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_sbo, uint32_t b_hi,
-                                              uint32_t b_lo, uint32_t b_sbo, bool split, uint32_t acc) {
-    constexpr uint32_t idesc = umma::idesc_tf32(M, N, 1, 1);
-#pragma unroll
-    for (uint32_t ks = 0; ks < KROWS / 8; ++ks) {
-        const uint32_t o = ks * 128u;
+// stage the TRANSPOSE of an nn.Linear weight [rows=out, cols=in] as a K-major B operand with `cols` rows
+__device__ __forceinline__ void stage_weight_t(const float* __restrict__ w, uint8_t* plane_hi, uint32_t rows, uint32_t cols,
+                                               bool split, uint32_t tid, uint32_t nthreads) {
+    uint8_t* plane_lo = plane_hi + rows * cols * 4;
+    for (uint32_t i = tid; i < rows * cols; i += nthreads) {
+        const uint32_t r = i / cols, c = i - r * cols;          // W[r][c] -> tile row c, contraction index r
+        const uint32_t off = umma::tile_off(cols, c, r);
+        const float v = __ldg(w + i);
         if (split) {
-            umma::mma_tf32(tmem_d, umma::smem_desc(a_lo + o, 128u, a_sbo), umma::smem_desc(b_hi + o, 128u, b_sbo), idesc, acc);
-            umma::mma_tf32(tmem_d, umma::smem_desc(a_hi + o, 128u, a_sbo), umma::smem_desc(b_lo + o, 128u, b_sbo), idesc, 1u);
-            acc = 1;
+            float hi, lo;
+            umma::split_tf32(v, hi, lo);
+            *reinterpret_cast<float*>(plane_hi + off) = hi;
+            *reinterpret_cast<float*>(plane_lo + off) = lo;
+        } else {
+            *reinterpret_cast<float*>(plane_hi + off) = round_tf32(v);
         }
-        umma::mma_tf32(tmem_d, umma::smem_desc(a_hi + o, 128u, a_sbo), umma::smem_desc(b_hi + o, 128u, b_sbo), idesc, acc);
-        acc = 1;
     }
 }
 
-// D[128, N] = A[128, K] . W[K, N] : A K-major (rows = samples), W = chunk-major weight tile with W_ROWS = K rows,
-// read as an MN-major B operand
+// four consecutive features f..f+3 (f % 4 == 0) of contraction row k -> hi / lo planes of an MN-major tile
+__device__ __forceinline__ void put_mn(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t k, uint32_t f, float a, float b,
+                                       float c, float d, bool split) {
+    const uint32_t off = umma::mn32_off(head::kTile, k, f);
+    if (split) {
+        float h0, h1, h2, h3, l0, l1, l2, l3;
+        umma::split_tf32(a, h0, l0); umma::split_tf32(b, h1, l1); umma::split_tf32(c, h2, l2); umma::split_tf32(d, h3, l3);
+        *reinterpret_cast<float4*>(hi_plane + off) = make_float4(h0, h1, h2, h3);
+        *reinterpret_cast<float4*>(lo_plane + off) = make_float4(l0, l1, l2, l3);
+    } else {
+        *reinterpret_cast<float4*>(hi_plane + off) = make_float4(round_tf32(a), round_tf32(b), round_tf32(c), round_tf32(d));
+    }
+}
+
+// 16 consecutive features of this thread's sample -> TMEM A-operand planes (hi at col, lo at col + 64)
+__device__ __forceinline__ void put_tmem16(uint32_t lane_base, uint32_t col, const float (&v)[16], bool split) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        if (split) umma::split_tf32(v[j], hi[j], lo[j]);
+        else hi[j] = round_tf32(v[j]);
+    }
+    umma::tmem_st16(lane_base + head::cAhi + col, hi);
+    if (split) umma::tmem_st16(lane_base + head::cAlo + col, lo);
+}
+
+// D[128, N] = A[tmem: 128 lanes x K columns] . Wt[N, K]^T ; Wt = transposed weight tile (K-major, WT_ROWS = N rows)
 template <uint32_t N, uint32_t K>
-__device__ __forceinline__ void issue_gemm_kn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo,
-                                              bool split) {
-    constexpr uint32_t idesc = umma::idesc_tf32(128, N, 0, 1);
-    constexpr uint32_t a_lbo = head::kTile * 16u, w_sbo = K * 16u;
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t b_hi,
+                                              uint32_t b_lo, bool split) {
+    constexpr uint32_t idesc = umma::idesc_tf32(128, N, 0, 0);
+    constexpr uint32_t b_lbo = N * 16u;
     uint32_t acc = 0;
 #pragma unroll
     for (uint32_t ks = 0; ks < K / 8; ++ks) {
-        const uint32_t ao = ks * 2u * a_lbo, wo = ks * 128u;
+        const uint32_t bo = ks * 2u * b_lbo;
         if (split) {
-            umma::mma_tf32(tmem_d, umma::smem_desc(a_lo + ao, a_lbo, 128u), umma::smem_desc(w_hi + wo, 128u, w_sbo), idesc, acc);
-            umma::mma_tf32(tmem_d, umma::smem_desc(a_hi + ao, a_lbo, 128u), umma::smem_desc(w_lo + wo, 128u, w_sbo), idesc, 1u);
+            umma::mma_tf32_ts(tmem_d, tmem_a_lo + ks * 8u, umma::smem_desc(b_hi + bo, b_lbo, 128u), idesc, acc);
+            umma::mma_tf32_ts(tmem_d, tmem_a_hi + ks * 8u, umma::smem_desc(b_lo + bo, b_lbo, 128u), idesc, 1u);
             acc = 1;
         }
-        umma::mma_tf32(tmem_d, umma::smem_desc(a_hi + ao, a_lbo, 128u), umma::smem_desc(w_hi + wo, 128u, w_sbo), idesc, acc);
+        umma::mma_tf32_ts(tmem_d, tmem_a_hi + ks * 8u, umma::smem_desc(b_hi + bo, b_lbo, 128u), idesc, acc);
         acc = 1;
     }
 }
 
-// accumulator -> ReLU -> tile, remembering the sign pattern
-__device__ __forceinline__ uint64_t relu_to_smem_mask(uint32_t tmem_lane_col, uint8_t* h_hi, uint8_t* h_lo, uint32_t row,
-                                                      bool split) {
-    uint64_t mask = 0;
+// D[64, N] (+)= At^T . Bt : MN-major swizzled tiles whose 128 rows are the contraction index
+template <uint32_t N>
+__device__ __forceinline__ void issue_gemm_mn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                              bool split, uint32_t acc) {
+    constexpr uint32_t idesc = umma::idesc_tf32(64, N, 1, 1);
+    using namespace head;
 #pragma unroll
-    for (uint32_t c0 = 0; c0 < head::kHid; c0 += 16) {
-        float v[16];
-        umma::tmem_ld16(tmem_lane_col + c0, v);
-#pragma unroll
-        for (uint32_t j = 0; j < 16; ++j) {
-            mask |= (v[j] > 0.0f) ? (1ull << (c0 + j)) : 0ull;
-            v[j] = fmaxf(v[j], 0.0f);
+    for (uint32_t ks = 0; ks < kTile / 8; ++ks) {
+        const uint32_t o = ks * 2u * kMnSbo;
+        if (split) {
+            umma::mma_tf32(tmem_d, umma::smem_desc_mn32(a_lo + o, kMnLbo, kMnSbo), umma::smem_desc_mn32(b_hi + o, kMnLbo, kMnSbo), idesc, acc);
+            umma::mma_tf32(tmem_d, umma::smem_desc_mn32(a_hi + o, kMnLbo, kMnSbo), umma::smem_desc_mn32(b_lo + o, kMnLbo, kMnSbo), idesc, 1u);
+            acc = 1;
         }
-#pragma unroll
-        for (uint32_t j = 0; j < 16; j += 4)
-            put_chunk(h_hi, h_lo, head::kTile, row, (c0 + j) >> 2, v[j], v[j + 1], v[j + 2], v[j + 3], split);
+        umma::mma_tf32(tmem_d, umma::smem_desc_mn32(a_hi + o, kMnLbo, kMnSbo), umma::smem_desc_mn32(b_hi + o, kMnLbo, kMnSbo), idesc, acc);
+        acc = 1;
     }
-    return mask;
 }
 
-// accumulator * mask -> tile
-__device__ __forceinline__ void masked_to_smem(uint32_t tmem_lane_col, uint64_t mask, uint8_t* g_hi, uint8_t* g_lo,
-                                               uint32_t row, bool split) {
-#pragma unroll
-    for (uint32_t c0 = 0; c0 < head::kHid; c0 += 16) {
-        float v[16];
-        umma::tmem_ld16(tmem_lane_col + c0, v);
-#pragma unroll
-        for (uint32_t j = 0; j < 16; ++j) v[j] = ((mask >> (c0 + j)) & 1ull) ? v[j] : 0.0f;
-#pragma unroll
-        for (uint32_t j = 0; j < 16; j += 4)
-            put_chunk(g_hi, g_lo, head::kTile, row, (c0 + j) >> 2, v[j], v[j + 1], v[j + 2], v[j + 3], split);
-    }
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(const HeadBwdParams p, const uint32_t tiles) {
     using namespace head;
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mma;
+    __shared__ __align__(8) uint64_t s_mask[2][kTile];
     __shared__ uint32_t s_tmem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool split = (p.precision == 0);
+    const bool owner = warp < 4;
+    const uint32_t row = tid & (kTile - 1);                 // sample row of the tile this thread serves
+    uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
 
     if (warp == 0) umma::tmem_alloc<kBwdTmemCols>(umma::smem_u32(&s_tmem));
     if (tid == 32) {
         umma::mbar_init(umma::smem_u32(&s_mma), 1);
         umma::fence_mbar_init();
     }
-    stage_weight(p.w1, smem + oW1, kHid, kIn, split, tid, kBwdThreads);
-    stage_weight(p.w2, smem + oW2, kHid, kHid, split, tid, kBwdThreads);
-    stage_weight(p.w3, smem + oW3, kOut, kHid, split, tid, kBwdThreads);
+    stage_weight_t(p.w3, smem + oT3, kOut, kHid, split, tid, kBwdThreads);
+    stage_weight_t(p.w2, smem + oT2, kHid, kHid, split, tid, kBwdThreads);
+    stage_weight_t(p.w1, smem + oT1, kHid, kIn, split, tid, kBwdThreads);
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    const uint32_t lane_base = umma::tmem_addr(tmem, warp * 32, 0);
-    const uint32_t sW1 = umma::smem_u32(smem + oW1), sW2 = umma::smem_u32(smem + oW2), sW3 = umma::smem_u32(smem + oW3);
-    const uint32_t sX = umma::smem_u32(smem + oX), sY = umma::smem_u32(smem + oY), sG3 = umma::smem_u32(smem + oG3);
-    uint8_t* X = smem + oX;
-    uint8_t* Y = smem + oY;
-    uint8_t* G3 = smem + oG3;
-    constexpr uint32_t kChunkStride = kTile * 16u;       // bytes between 4-column chunks of a 128-row tile
+    const uint32_t lane_base = umma::tmem_addr(tmem, (warp & 3u) * 32u, 0);
+    const uint32_t sT3 = umma::smem_u32(smem + oT3), sT2 = umma::smem_u32(smem + oT2), sT1 = umma::smem_u32(smem + oT1);
+    const uint32_t sA = umma::smem_u32(smem + oBufA), sB = umma::smem_u32(smem + oBufB), sG = umma::smem_u32(smem + oBufG);
+    uint8_t* bufA = smem + oBufA;
+    uint8_t* bufB = smem + oBufB;
+    uint8_t* bufG = smem + oBufG;
     uint32_t phase = 0;
 
-    // this thread's rows of the current tile, prefetched one tile ahead
-    float4 enc[8], nenc[8], ng[4];
-    auto fetch = [&](uint32_t tile, float4 (&e)[8], float4 (&g)[4]) {
-        const uint32_t b = tile * kTile + tid;
-        if (tile < tiles && b < p.B) {
-            const float4* pe = reinterpret_cast<const float4*>(p.enc + (size_t)b * kIn);
-            const float4* pg = reinterpret_cast<const float4*>(p.g_out + (size_t)b * kOut);
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) e[j] = __ldg(pe + j);
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) g[j] = __ldg(pg + j);
-        } else {
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) e[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto put_enc = [&](const float4 (&e)[8]) {        // A1 image in Y: hi plane at Y, lo plane at Y + kA1
-#pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) put_chunk(Y, Y + kA1, kTile, tid, j, e[j].x, e[j].y, e[j].z, e[j].w, split);
-    };
     auto mma_done = [&]() {
         umma::mbar_wait(umma::smem_u32(&s_mma), phase);
         phase ^= 1u;
         umma::fence_after_sync();
     };
-    auto publish = [&]() {                             // smem tiles written -> visible to the tensor core; TMEM reads done
+    auto publish = [&]() {       // tiles written (shared: generic -> async proxy; tensor memory: st complete), TMEM reads done
+        umma::tmem_st_wait();
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
     };
 
-    fetch(blockIdx.x, nenc, ng);
+    // loader registers: the next tile's H2, H1 and g_out rows
+    float4 rh2[16], rh1[16], rg[4];
+    auto prefetch = [&](uint32_t tile) {
+        const uint32_t b = tile * kTile + row;
+        if (tile < tiles && b < p.B) {
+            const float* ph2 = p.h2 + (size_t)b * kHid;
+            const float* ph1 = p.h1 + (size_t)b * kHid;
+            const float* pg = p.g_out + (size_t)b * kOut;
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) rg[j] = ldg_nc_f4(pg + 4 * j);
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j) rh2[j] = ldg_nc_f4(ph2 + 4 * j);
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j) rh1[j] = ldg_nc_f4(ph1 + 4 * j);
+        } else {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) rg[j] = z;
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j) { rh2[j] = z; rh1[j] = z; }
+        }
+    };
+    if (!owner) prefetch(blockIdx.x);
+
     for (uint32_t it = 0, tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
         const uint32_t first = (it == 0) ? 0u : 1u;
-        // ---- 0: stage this tile's rows, prefetch the next tile's
+        const uint32_t b = tile * kTile + row;
+        if (owner) {
+            // this tile's encoding row (kept in the otherwise unused rh1 registers): consumed after step 4, so the load
+            // latency is hidden
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) enc[j] = nenc[j];
-        put_enc(enc);
+            for (uint32_t j = 0; j < 8; ++j) rh1[j] = (b < p.B) ? ldg_nc_f4(p.enc + (size_t)b * kIn + 4 * j) : z;
+        } else {
+            // ---- dump the prefetched rows: H2 -> bufB, H1 -> bufA, G3 -> bufG + TMEM A planes; sign masks -> shared
+            uint64_t m1 = 0, m2 = 0;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) put_chunk(G3, G3 + kG3, kTile, tid, j, ng[j].x, ng[j].y, ng[j].z, ng[j].w, split);
-        fetch(tile + gridDim.x, nenc, ng);
-        publish();
-        // ---- 1
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm<kHid, kIn, kHid>(tmem + cD1, sY, sY + kA1, sW1, sW1 + kW1, split);
-            umma::commit(umma::smem_u32(&s_mma));
+            for (uint32_t j = 0; j < 16; ++j) {
+                m2 |= (uint64_t)((rh2[j].x > 0.f) | ((rh2[j].y > 0.f) << 1) | ((rh2[j].z > 0.f) << 2) | ((rh2[j].w > 0.f) << 3)) << (4 * j);
+                m1 |= (uint64_t)((rh1[j].x > 0.f) | ((rh1[j].y > 0.f) << 1) | ((rh1[j].z > 0.f) << 2) | ((rh1[j].w > 0.f) << 3)) << (4 * j);
+                put_mn(bufB, bufB + kMn64, row, 4 * j, rh2[j].x, rh2[j].y, rh2[j].z, rh2[j].w, split);
+                put_mn(bufA, bufA + kMn64, row, 4 * j, rh1[j].x, rh1[j].y, rh1[j].z, rh1[j].w, split);
+            }
+            s_mask[0][row] = m1;
+            s_mask[1][row] = m2;
+            float g16[16];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+                put_mn(bufG, bufG + kMn32, row, 4 * j, rg[j].x, rg[j].y, rg[j].z, rg[j].w, split);
+                g16[4 * j] = rg[j].x; g16[4 * j + 1] = rg[j].y; g16[4 * j + 2] = rg[j].z; g16[4 * j + 3] = rg[j].w;
+            }
+            put_tmem16(lane_base, 0, g16, split);
         }
-        mma_done();
-        const uint64_t mask1 = relu_to_smem_mask(lane_base + cD1, X, X + kH, tid, split);
         publish();
-        // ---- 2
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm<kHid, kHid, kHid>(tmem + cD2, sX, sX + kH, sW2, sW2 + kW2, split);
-            umma::commit(umma::smem_u32(&s_mma));
-        }
-        mma_done();
-        const uint64_t mask2 = relu_to_smem_mask(lane_base + cD2, Y, Y + kH, tid, split);
-        publish();
+        if (!owner) prefetch(tile + gridDim.x);
         // ---- 3
         if (tid == 0) {
             umma::fence_after_sync();
-            issue_gemm_mn<64, kOut, kTile>(tmem + cW3, sY, sY + kH, kChunkStride, sG3, sG3 + kG3, kChunkStride, split, first);
-            issue_gemm_kn<kHid, kOut>(tmem + cDG2, sG3, sG3 + kG3, sW3, sW3 + kW3, split);
+            issue_gemm_ts<kHid, kOut>(tmem + cDG, tmem + cAhi, tmem + cAlo, sT3, sT3 + kW3, split);
+            issue_gemm_mn<kOut>(tmem + cW3, sB, sB + kMn64, sG, sG + kMn32, split, first);
             umma::commit(umma::smem_u32(&s_mma));
         }
         mma_done();
-        masked_to_smem(lane_base + cDG2, mask2, Y, Y + kH, tid, split);
+        if (owner) {
+            const uint64_t mask2 = s_mask[1][row];
+#pragma unroll
+            for (uint32_t c0 = 0; c0 < kHid; c0 += 16) {
+                float v[16];
+                umma::tmem_ld16(lane_base + cDG + c0, v);
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) v[j] = ((mask2 >> (c0 + j)) & 1ull) ? v[j] : 0.0f;
+                put_tmem16(lane_base, c0, v, split);
+#pragma unroll
+                for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
+            }
+        }
         publish();
         // ---- 4
         if (tid == 0) {
             umma::fence_after_sync();
-            issue_gemm_mn<64, kHid, kTile>(tmem + cW2, sY, sY + kH, kChunkStride, sX, sX + kH, kChunkStride, split, first);
-            issue_gemm_kn<kHid, kHid>(tmem + cDG1, sY, sY + kH, sW2, sW2 + kW2, split);
+            issue_gemm_ts<kHid, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, sT2, sT2 + kW2, split);
+            issue_gemm_mn<kHid>(tmem + cW2, sB, sB + kMn64, sA, sA + kMn64, split, first);
             umma::commit(umma::smem_u32(&s_mma));
         }
         mma_done();
-        masked_to_smem(lane_base + cDG1, mask1, X, X + kH, tid, split);
-        put_enc(enc);
+        if (owner) {
+            const uint64_t mask1 = s_mask[0][row];
+#pragma unroll
+            for (uint32_t c0 = 0; c0 < kHid; c0 += 16) {
+                float v[16];
+                umma::tmem_ld16(lane_base + cDG + c0, v);
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) v[j] = ((mask1 >> (c0 + j)) & 1ull) ? v[j] : 0.0f;
+                put_tmem16(lane_base, c0, v, split);
+#pragma unroll
+                for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) put_mn(bufA, bufA + kMn32, row, 4 * j, rh1[j].x, rh1[j].y, rh1[j].z, rh1[j].w, split);
+        }
         publish();
         // ---- 5
         if (tid == 0) {
             umma::fence_after_sync();
-            issue_gemm_mn<64, kIn, kTile>(tmem + cW1, sX, sX + kH, kChunkStride, sY, sY + kA1, kChunkStride, split, first);
-            issue_gemm_kn<kIn, kHid>(tmem + cDGE, sX, sX + kH, sW1, sW1 + kW1, split);
+            issue_gemm_ts<kIn, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, sT1, sT1 + kW1, split);
+            issue_gemm_mn<kIn>(tmem + cW1, sB, sB + kMn64, sA, sA + kMn32, split, first);
             umma::commit(umma::smem_u32(&s_mma));
         }
         mma_done();
-        {
-            const uint32_t b = tile * kTile + tid;
+        if (owner) {
 #pragma unroll
             for (uint32_t c0 = 0; c0 < kIn; c0 += 16) {
                 float v[16];
-                umma::tmem_ld16(lane_base + cDGE + c0, v);
+                umma::tmem_ld16(lane_base + cDG + c0, v);
                 if (b < p.B) {
                     float4* dst = reinterpret_cast<float4*>(p.g_enc + (size_t)b * kIn + c0);
 #pragma unroll
@@ -527,37 +601,42 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
                 }
             }
         }
-        umma::fence_before_sync();
-        __syncthreads();        // every read of X / Y / G3 by step-5 MMAs is complete (mma_done) before the next tile stages
+        // the next tile's dump (other warps) may start at once: every MMA that read bufA / bufB / bufG / the A planes has
+        // completed; this tile's reads of cDG are ordered before the next MMAs by the fence in the next publish()
     }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
 
     // ---- weight gradients: M = 64 accumulators, row (16 w + l) lives in TMEM lane (32 w + l), l < 16
-    const uint32_t row = warp * 16 + lane;
-    const bool owns = lane < 16;
+    if (owner) {
+        const uint32_t wrow = warp * 16 + lane;
+        const bool owns = lane < 16;
 #pragma unroll
-    for (uint32_t c0 = 0; c0 < kIn; c0 += 16) {          // dW1[out=row][in=c]
-        float v[16];
-        umma::tmem_ld16(lane_base + cW1 + c0, v);
-        if (owns) {
+        for (uint32_t c0 = 0; c0 < kIn; c0 += 16) {          // dW1[out=wrow][in=c]
+            float v[16];
+            umma::tmem_ld16(lane_base + cW1 + c0, v);
+            if (owns) {
 #pragma unroll
-            for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w1 + row * kIn + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w1 + wrow * kIn + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
         }
-    }
 #pragma unroll
-    for (uint32_t c0 = 0; c0 < kHid; c0 += 16) {         // dW2[out=row][in=c]
-        float v[16];
-        umma::tmem_ld16(lane_base + cW2 + c0, v);
-        if (owns) {
+        for (uint32_t c0 = 0; c0 < kHid; c0 += 16) {         // dW2[out=wrow][in=c]
+            float v[16];
+            umma::tmem_ld16(lane_base + cW2 + c0, v);
+            if (owns) {
 #pragma unroll
-            for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w2 + row * kHid + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w2 + wrow * kHid + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
         }
-    }
-    {                                                    // dW3^T[in=row][out=c] -> g_w3[out][in]
-        float v[16];
-        umma::tmem_ld16(lane_base + cW3, v);
-        if (owns) {
+        {                                                    // dW3^T[in=wrow][out=c] -> g_w3[out][in]
+            float v[16];
+            umma::tmem_ld16(lane_base + cW3, v);
+            if (owns) {
 #pragma unroll
-            for (uint32_t j = 0; j < 16; ++j) red_add_f32(p.g_w3 + j * kHid + row, v[j]);
+                for (uint32_t j = 0; j < 16; ++j) red_add_f32(p.g_w3 + j * kHid + wrow, v[j]);
+            }
         }
     }
     umma::fence_before_sync();
@@ -571,7 +650,8 @@ using namespace sanerf;
 
 extern "C" int sanerf_field_head_forward(const float* x01, const float* table, const int32_t* offsets, float S, uint32_t H,
                                          const float* enc_in, const float* w1, const float* w2, const float* w3, uint32_t B,
-                                         float* enc_out, float* out, int precision, void* stream) {
+                                         float* enc_out, float* h1_out, float* h2_out, float* out, int precision,
+                                         void* stream) {
     if (B == 0) return SANERF_OK;
     if (x01 != nullptr) {
         SANERF_REQUIRE_PTR(table); SANERF_REQUIRE_PTR(offsets);
@@ -580,7 +660,8 @@ extern "C" int sanerf_field_head_forward(const float* x01, const float* table, c
     }
     SANERF_REQUIRE_PTR(w1); SANERF_REQUIRE_PTR(w2); SANERF_REQUIRE_PTR(w3); SANERF_REQUIRE_PTR(out);
     if (precision != 0 && precision != 1) return fail(SANERF_ERR_INVALID_ARG, "field_head: precision 0 (3xTF32) or 1 (TF32)");
-    HeadFwdParams p{x01, table, offsets, enc_in, w1, w2, w3, enc_out, out, B, H, S, precision};
+    if ((h1_out == nullptr) != (h2_out == nullptr)) return fail(SANERF_ERR_INVALID_ARG, "field_head: h1_out and h2_out go together");
+    HeadFwdParams p{x01, table, offsets, enc_in, w1, w2, w3, enc_out, h1_out, h2_out, out, B, H, S, precision};
     const uint32_t tiles = div_up(B, head::kTile);
     const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     cudaError_t e = cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kFwdSmem);
@@ -589,14 +670,15 @@ extern "C" int sanerf_field_head_forward(const float* x01, const float* table, c
     return check_launch("head_forward_kernel");
 }
 
-extern "C" int sanerf_field_head_backward(const float* enc, const float* g_out, const float* w1, const float* w2,
-                                          const float* w3, uint32_t B, float* g_enc, float* g_w1, float* g_w2, float* g_w3,
-                                          int precision, void* stream) {
+extern "C" int sanerf_field_head_backward(const float* enc, const float* h1, const float* h2, const float* g_out,
+                                          const float* w1, const float* w2, const float* w3, uint32_t B, float* g_enc,
+                                          float* g_w1, float* g_w2, float* g_w3, int precision, void* stream) {
     if (B == 0) return SANERF_OK;
-    SANERF_REQUIRE_PTR(enc); SANERF_REQUIRE_PTR(g_out); SANERF_REQUIRE_PTR(w1); SANERF_REQUIRE_PTR(w2); SANERF_REQUIRE_PTR(w3);
+    SANERF_REQUIRE_PTR(enc); SANERF_REQUIRE_PTR(h1); SANERF_REQUIRE_PTR(h2); SANERF_REQUIRE_PTR(g_out);
+    SANERF_REQUIRE_PTR(w1); SANERF_REQUIRE_PTR(w2); SANERF_REQUIRE_PTR(w3);
     SANERF_REQUIRE_PTR(g_enc); SANERF_REQUIRE_PTR(g_w1); SANERF_REQUIRE_PTR(g_w2); SANERF_REQUIRE_PTR(g_w3);
     if (precision != 0 && precision != 1) return fail(SANERF_ERR_INVALID_ARG, "field_head: precision 0 (3xTF32) or 1 (TF32)");
-    HeadBwdParams p{enc, g_out, w1, w2, w3, g_enc, g_w1, g_w2, g_w3, B, precision};
+    HeadBwdParams p{enc, h1, h2, g_out, w1, w2, w3, g_enc, g_w1, g_w2, g_w3, B, precision};
     const uint32_t tiles = div_up(B, head::kTile);
     const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     cudaError_t e = cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kBwdSmem);

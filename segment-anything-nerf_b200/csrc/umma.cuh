@@ -31,6 +31,23 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// 64-bit descriptor of an MN-major tf32 operand.  The tensor core accepts 32-bit MN-major operands ONLY in the
+// "128-byte swizzle with 32-byte atomicity" layout (layout type 1; CUTLASS: sm100_common.inl "for mn-major tf32
+// operands, SW128_32B is the only available smem layout" — the no-swizzle MN-major form silently yields zeros).
+//   lbo = bytes between consecutive 32-element blocks along M/N, sbo = bytes between consecutive groups of 4 K rows
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc(saddr, lbo_bytes, sbo_bytes) | (static_cast<uint64_t>(1) << 61);
+}
+
+// Byte offset of element (k = contraction row, f = M/N index) in an MN-major tf32 tile of KROWS contraction rows:
+// a 32-element block of f is a 128-byte line, 4 consecutive k form a 512-byte atom whose 32-byte chunks are XORed
+// with (k & 3) (Swizzle<2,5,2> on the byte address: the tile base must be 512-byte aligned), atoms stack along k
+// (sbo = 512) and 32-wide blocks of f follow each other every KROWS*128 bytes (lbo).
+__host__ __device__ __forceinline__ uint32_t mn32_off(uint32_t krows, uint32_t k, uint32_t f) {
+    return (f >> 5) * (krows * 128u) + (k >> 2) * 512u + (k & 3u) * 128u + ((((f & 31u) >> 3) ^ (k & 3u)) << 5) +
+           (f & 7u) * 4u;
+}
+
 // 32-bit instruction descriptor for kind::tf32, fp32 accumulate
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
     return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ | (a_mn_major << 15) |

@@ -136,21 +136,23 @@ class _FieldHead(Function):
         need_grad = any(ctx.needs_input_grad[1:6])
         out = torch.empty(*x01.shape[:-1], 16, device=dev, dtype=torch.float32)
         enc = torch.empty(B, 32, device=dev, dtype=torch.float32) if need_grad else None
+        h1 = torch.empty(B, 64, device=dev, dtype=torch.float32) if need_grad else None
+        h2 = torch.empty(B, 64, device=dev, dtype=torch.float32) if need_grad else None
         w1, w2, w3 = w1.contiguous(), w2.contiguous(), w3.contiguous()
         lib = _lib.load()
         with torch.cuda.device(dev), _lib.stats.span("field_head_forward", B=B):
             rc = lib.sanerf_field_head_forward(x01.data_ptr(), table.data_ptr(), offsets.data_ptr(), float(S), int(H),
                                                None, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, _lib.ptr(enc),
-                                               out.data_ptr(), int(precision), _stream(x01))
+                                               _lib.ptr(h1), _lib.ptr(h2), out.data_ptr(), int(precision), _stream(x01))
         _lib.check(rc, "field_head_forward")
         if need_grad:
-            ctx.save_for_backward(x01, table, offsets, w1, w2, w3, enc)
+            ctx.save_for_backward(x01, table, offsets, w1, w2, w3, enc, h1, h2)
             ctx.meta = (B, float(S), int(H), int(precision))
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        x01, table, offsets, w1, w2, w3, enc = ctx.saved_tensors
+        x01, table, offsets, w1, w2, w3, enc, h1, h2 = ctx.saved_tensors
         B, S, H, precision = ctx.meta
         dev = x01.device
         g_out = g_out.contiguous()
@@ -160,9 +162,9 @@ class _FieldHead(Function):
         st = _stream(x01)
         with torch.cuda.device(dev):
             with _lib.stats.span("field_head_backward", B=B):
-                rc = lib.sanerf_field_head_backward(enc.data_ptr(), g_out.data_ptr(), w1.data_ptr(), w2.data_ptr(),
-                                                    w3.data_ptr(), B, g_enc.data_ptr(), g_w1.data_ptr(), g_w2.data_ptr(),
-                                                    g_w3.data_ptr(), precision, st)
+                rc = lib.sanerf_field_head_backward(enc.data_ptr(), h1.data_ptr(), h2.data_ptr(), g_out.data_ptr(),
+                                                    w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, g_enc.data_ptr(),
+                                                    g_w1.data_ptr(), g_w2.data_ptr(), g_w3.data_ptr(), precision, st)
             _lib.check(rc, "field_head_backward")
             g_table = None
             if ctx.needs_input_grad[1]:
