@@ -255,19 +255,28 @@ def run_ours(args, rank, world, local_rank):
     last_loss = [0.0]
 
     def step_e2e(i):
-        ho, hd, hrgb = host_sets[i % n_sets]
-        o, d, rgb = (t.to(dev, non_blocking=True) for t in (ho, hd, hrgb))
-        last_loss[0] = trainer.step(o, d, rgb).item()              # D2H read of the step's result
+        ho, hd, hrgb = host_sets[i % n_sets]                       # pinned host buffers -> H2D inside the step
+        last_loss[0] = trainer.step(ho, hd, hrgb).item()           # D2H read of the step's result
 
     for i in range(args.warmup):
         step_device(i)
-    # dominant kernel of the step, picked from the ncu launch list (profiles/): see ROOFLINE_KERNELS
-    watch_name, pred, alg_bytes, watch_desc = ROOFLINE_KERNELS[args.roofline_kernel]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms, launches = timed_loop(step_device, args.steps, watch_name, pred)
+    total_ms, _ = timed_loop(step_device, args.steps)            # CUDA-graph replays: one launch per step on the host side
     clocks = sampler.stop() if rank == 0 else {}
+    # dominant kernel of the step, picked from the ncu launch list (profiles/): see ROOFLINE_KERNELS.  Kernels inside a
+    # graph cannot be bracketed by events, so the SAME step is replayed eagerly (same buffers, same kernels, same L2
+    # flush) right after the timed region with CUDA events around the watched launches on the launching stream.
+    watch_name, pred, alg_bytes, watch_desc = ROOFLINE_KERNELS[args.roofline_kernel]
+    plan = trainer.plan(N_RAYS)
+    if plan is not None:
+        plan.use_graph = False
+    _, launches_eager = timed_loop(step_device, max(3, min(args.steps, 10)), watch_name, pred)
+    n_eager = max(3, min(args.steps, 10))
+    launches = (launches_eager // n_eager) * args.steps          # C-ABI kernels per step x timed steps
+    if plan is not None:
+        plan.use_graph = True
     spans = _lib.stats.durations_ms()
     if args.no_e2e:
         e2e_ms = float("nan")
@@ -290,7 +299,9 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"bound": "hbm", "kernel": watch_desc,
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
-                    "avg_launch_ms": avg_ms, "launches_timed": len(spans)}
+                    "avg_launch_ms": avg_ms, "launches_timed": len(spans),
+                    "timing": "CUDA events around the kernel's launches in an eager replay of the same step after the "
+                              "timed region (the timed region itself replays a CUDA graph)"}
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -299,6 +310,7 @@ def run_ours(args, rank, world, local_rank):
                                "(2^18 final samples), L16 T2^19 F2 main grid + 2 L5 T2^17 proposal grids, "
                                "fwd+bwd+grad all-reduce+Adam, random-init tables",
                    "rays_per_gpu_per_step": N_RAYS, "l2": "flushed (256 MiB write) between timed iterations",
+                   "execution": "hand-scheduled step replayed as one CUDA graph per step" if plan is not None else "autograd",
                    "parallelism": f"ray-sharded data parallel x{world}"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,

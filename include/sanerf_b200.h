@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 6
+#define SANERF_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -213,13 +213,27 @@ SANERF_API int sanerf_prop_density_backward(const float* x01, const float* table
  * Sampling regularisers: loss value AND d loss / d weights in one kernel each.
  *  proposal loss (nerf/renderer.py:30-57) of ONE proposal level (t_p [N,Tp+1], w_p [N,Tp]) against the final
  *  level (t_ref [N,Tr+1], w_ref [N,Tr]); distortion loss (renderer.py:17-27 + torch_efficient_distloss).
- *  loss_out: one float, ACCUMULATED into (caller zero-fills); g_* may be NULL.
+ *  loss_out: one float, ACCUMULATED into (caller zero-fills); g_* may be NULL.  `weight` (lambda_proposal /
+ *  lambda_distort, main.py) multiplies the loss contribution AND the gradient.
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_proposal_loss(const float* t_ref, const float* w_ref, uint32_t Tr, const float* t_p,
-                         const float* w_p, uint32_t Tp, uint32_t N, float* loss_out, float* g_wp,
+                         const float* w_p, uint32_t Tp, uint32_t N, float weight, float* loss_out, float* g_wp,
                          void* stream);
-SANERF_API int sanerf_distortion_loss(const float* bins, const float* w, uint32_t T, uint32_t N, float* loss_out,
-                           float* g_w, void* stream);
+SANERF_API int sanerf_distortion_loss(const float* bins, const float* w, uint32_t T, uint32_t N, float weight,
+                           float* loss_out, float* g_w, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Deferred-shading view head + photometric loss, forward AND backward in one kernel (renderer.py:333-345, 358;
+ * network.py:107, 237; Trainer.train_step nerf/utils.py:897-930):
+ *   f = [geo_sum (15), weights_sum * SH4(normalize(rays_d)) (16)];  rgb = sigmoid(W3 relu(W2 relu(W1 f)));
+ *   image = rgb + (1 - weights_sum) * bg;  loss += loss_weight * mean((image - gt)^2).
+ * gt == NULL: forward only (image).  Otherwise also writes g_geo_sum [N,15], g_weights_sum [N] and ACCUMULATES
+ * loss (one float) and the weight gradients g_w1 [32,31], g_w2 [32,32], g_w3 [3,32] (caller zero-fills).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_view_head(const float* geo_sum, const float* weights_sum, const float* rays_d, const float* gt,
+                     const float* w1, const float* w2, const float* w3, float bg, float loss_weight, uint32_t N,
+                     float* image, float* loss, float* g_geo_sum, float* g_weights_sum, float* g_w1, float* g_w2,
+                     float* g_w3, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adam over one flat fp32 buffer (main.py:296 Adam(eps=1e-15), :312-313 LambdaLR 0.1^min(it/iters,1)).

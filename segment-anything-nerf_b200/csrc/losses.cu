@@ -40,7 +40,8 @@ __device__ __forceinline__ uint32_t upper_bound(const float* a, uint32_t n, floa
 // shared per warp: t_p[Tp+1] | cum[Tp+1] (exclusive prefix, cum[0]=0 .. cum[Tp]=total) | diff[Tp+1]
 __global__ void __launch_bounds__(32 * kLossWarps) proposal_loss_kernel(
     const float* __restrict__ t_ref, const float* __restrict__ w_ref, uint32_t Tr, const float* __restrict__ t_p,
-    const float* __restrict__ w_p, uint32_t Tp, uint32_t N, float* __restrict__ loss_out, float* __restrict__ g_wp) {
+    const float* __restrict__ w_p, uint32_t Tp, uint32_t N, float weight, float* __restrict__ loss_out,
+    float* __restrict__ g_wp) {
     extern __shared__ float smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kLossWarps + warp;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(32 * kLossWarps) proposal_loss_kernel(
     float* tp = smem + (size_t)warp * 3u * (Tp + 1u);
     float* cum = tp + (Tp + 1u);
     float* diff = cum + (Tp + 1u);
-    const float scale = 1.0f / ((float)N * (float)Tr);     // .mean() over [N, Tr]
+    const float scale = weight / ((float)N * (float)Tr);   // .mean() over [N, Tr], times lambda_proposal
 
     for (uint32_t i = lane; i <= Tp; i += 32) { tp[i] = __ldg(t_p + (size_t)r * (Tp + 1u) + i); diff[i] = 0.0f; }
     float carry = 0.0f;
@@ -97,12 +98,12 @@ __global__ void __launch_bounds__(32 * kLossWarps) proposal_loss_kernel(
 }
 
 __global__ void __launch_bounds__(32 * kLossWarps) distortion_loss_kernel(
-    const float* __restrict__ bins, const float* __restrict__ w, uint32_t T, uint32_t N, float* __restrict__ loss_out,
-    float* __restrict__ g_w) {
+    const float* __restrict__ bins, const float* __restrict__ w, uint32_t T, uint32_t N, float weight,
+    float* __restrict__ loss_out, float* __restrict__ g_w) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kLossWarps + warp;
     if (r >= N) return;
-    const float inv_n = 1.0f / (float)N;
+    const float inv_n = weight / (float)N;
     const float* b = bins + (size_t)r * (T + 1u);
     const float* wr = w + (size_t)r * T;
     // totals first (needed for the suffix terms of the gradient)
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
 using namespace sanerf;
 
 extern "C" int sanerf_proposal_loss(const float* t_ref, const float* w_ref, uint32_t Tr, const float* t_p,
-                                    const float* w_p, uint32_t Tp, uint32_t N, float* loss_out, float* g_wp,
-                                    void* stream) {
+                                    const float* w_p, uint32_t Tp, uint32_t N, float weight, float* loss_out,
+                                    float* g_wp, void* stream) {
     if (N == 0 || Tr == 0) return SANERF_OK;
     SANERF_REQUIRE_PTR(t_ref); SANERF_REQUIRE_PTR(w_ref); SANERF_REQUIRE_PTR(t_p); SANERF_REQUIRE_PTR(w_p);
     SANERF_REQUIRE_PTR(loss_out);
@@ -197,16 +198,16 @@ extern "C" int sanerf_proposal_loss(const float* t_ref, const float* w_ref, uint
     if (smem > 48 * 1024) return fail(SANERF_ERR_INVALID_ARG, "proposal_loss: Tp too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     proposal_loss_kernel<<<div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, smem, st>>>(t_ref, w_ref, Tr, t_p, w_p, Tp,
-                                                                                         N, loss_out, g_wp);
+                                                                                         N, weight, loss_out, g_wp);
     return check_launch("proposal_loss_kernel");
 }
 
-extern "C" int sanerf_distortion_loss(const float* bins, const float* w, uint32_t T, uint32_t N, float* loss_out,
-                                      float* g_w, void* stream) {
+extern "C" int sanerf_distortion_loss(const float* bins, const float* w, uint32_t T, uint32_t N, float weight,
+                                      float* loss_out, float* g_w, void* stream) {
     if (N == 0 || T == 0) return SANERF_OK;
     SANERF_REQUIRE_PTR(bins); SANERF_REQUIRE_PTR(w); SANERF_REQUIRE_PTR(loss_out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    distortion_loss_kernel<<<div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, 0, st>>>(bins, w, T, N, loss_out, g_w);
+    distortion_loss_kernel<<<div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, 0, st>>>(bins, w, T, N, weight, loss_out, g_w);
     return check_launch("distortion_loss_kernel");
 }
 

@@ -186,20 +186,20 @@ class NeRFRenderer(nn.Module):
         opaque_last = self.opt.background == "last_sample"
         steps = list(self.opt.num_steps)
 
-        near, far = near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer,
-                                       self.min_near)
-        if cam_near_far is not None:
-            near = torch.maximum(near, cam_near_far[:, [0]])
-            far = torch.minimum(far, cam_near_far[:, [1]])
         if bg_color is None:
             bg_color = 1
-        s_near, s_far = _spacing(near), _spacing(far)
-
         use_fused = (self.fused and not self.opt.sum_after_mlp and rays_o.is_cuda and rays_o.dtype == torch.float32
                      and not torch.is_autocast_enabled() and hasattr(self, "head_unit"))
         if use_fused:
             return self._run_fused(rays_o, rays_d, bg_color, perturb, cam_near_far, update_proposal, return_feats,
                                    H, W, opaque_last, steps)
+
+        near, far = near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer,
+                                       self.min_near)
+        if cam_near_far is not None:
+            near = torch.maximum(near, cam_near_far[:, [0]])
+            far = torch.minimum(far, cam_near_far[:, [1]])
+        s_near, s_far = _spacing(near), _spacing(far)
 
         all_bins, all_weights = [], []
         bins = weights = None

@@ -277,7 +277,7 @@ class _ProposalLoss(Function):
                 g = torch.empty_like(w_p)
                 with _lib.stats.span("proposal_loss", N=N, Tp=w_p.shape[1]):
                     rc = lib.sanerf_proposal_loss(t_ref.data_ptr(), w_ref.data_ptr(), Tr, t_p.data_ptr(), w_p.data_ptr(),
-                                                  w_p.shape[1], N, loss.data_ptr(), g.data_ptr(), _stream(w_ref))
+                                                  w_p.shape[1], N, 1.0, loss.data_ptr(), g.data_ptr(), _stream(w_ref))
                 _lib.check(rc, "proposal_loss")
                 grads.append(g)
         ctx.save_for_backward(*grads)
@@ -308,7 +308,7 @@ class _DistortLoss(Function):
         g = torch.empty_like(weights)
         lib = _lib.load()
         with torch.cuda.device(weights.device), _lib.stats.span("distortion_loss", N=N, T=T):
-            rc = lib.sanerf_distortion_loss(bins.data_ptr(), weights.data_ptr(), T, N, loss.data_ptr(), g.data_ptr(),
+            rc = lib.sanerf_distortion_loss(bins.data_ptr(), weights.data_ptr(), T, N, 1.0, loss.data_ptr(), g.data_ptr(),
                                             _stream(weights))
         _lib.check(rc, "distortion_loss")
         ctx.save_for_backward(g)

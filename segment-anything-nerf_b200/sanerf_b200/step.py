@@ -1,0 +1,262 @@
+"""Hand-scheduled stage-1 (RGB) training step: ~25 kernel launches on static buffers, replayed as ONE CUDA graph.
+
+Same computation as ``RGBTrainer.loss(...).backward(); optimizer.step()`` (the reference's ``Trainer.train_step`` +
+``train_one_epoch`` iteration, nerf/utils.py:897-930, 1811-1836, with ``NeRFRenderer.run`` renderer.py:221-390
+underneath), but without autograd, without torch glue kernels and without per-launch CPU work:
+
+  level 0/1:  sample -> proposal density (encode + MLP + trunc_exp, one kernel) -> weights (composite, C = 0)
+  level 2:    sample -> field head (gather + 3-layer MLP on tcgen05) -> trunc_exp -> composite of the 15 geometry channels
+              -> view head (SH, view MLP, sigmoid, background, MSE; forward AND backward in one kernel)
+  losses:     proposal loss (2 levels) and distortion loss, each returning its gradient, pre-multiplied by lambda
+  backward:   composite -> trunc_exp -> field head (tcgen05) -> hash-grid scatter; composite -> proposal density (x2)
+  update:     [NCCL all-reduce of the flat gradient bucket when world_size > 1] -> fused Adam (clears the gradient)
+
+Every gradient kernel accumulates straight into the views of ``FusedAdam.flat_grad`` (pre-zeroed by the optimizer
+kernel), so there is no ``zeros_like`` + add per parameter.  ``tests/test_gpu_step.py`` checks loss and every gradient
+against the autograd path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .fused import PRECISION_IDS, field_head_supported, prop_density_supported
+
+
+class UnsupportedConfig(RuntimeError):
+    """The model is not the reference's stage-1 configuration the hand-scheduled step is written for."""
+
+
+class FusedRGBStep:
+    def __init__(self, model, optimizer, n_rays, world_size=1, use_graph=True, perturb=True, bg_color=1.0):
+        opt = model.opt
+        if opt.with_sam or opt.with_mask or opt.sum_after_mlp:
+            raise UnsupportedConfig("FusedRGBStep covers the stage-1 RGB step (no SAM / mask heads, deferred shading)")
+        if not field_head_supported(model.grid, model.grid_mlp):
+            raise UnsupportedConfig("FusedRGBStep needs the reference's main grid + grid_mlp shapes")
+        for enc, mlp in zip(model.prop_encoders, model.prop_mlp):
+            if not prop_density_supported(enc, mlp):
+                raise UnsupportedConfig("FusedRGBStep needs the reference's proposal network shapes")
+        vw = [l.weight for l in model.view_mlp.net]
+        if [tuple(w.shape) for w in vw] != [(32, 31), (32, 32), (3, 32)] or any(l.bias is not None for l in model.view_mlp.net):
+            raise UnsupportedConfig("FusedRGBStep needs the reference's view_mlp (31 -> 32 -> 32 -> 3, no bias)")
+        self.model, self.optimizer, self.world_size = model, optimizer, world_size
+        self.N, self.steps = int(n_rays), [int(t) for t in opt.num_steps]
+        if len(self.steps) != 3:
+            raise UnsupportedConfig("FusedRGBStep expects two proposal levels and one final level")
+        self.perturb, self.bg = bool(perturb), float(bg_color)
+        self.precision = PRECISION_IDS[model.mlp_precision]
+        self.opaque = int(opt.background == "last_sample")
+        self.use_graph = bool(use_graph)
+        dev = self.dev = next(model.parameters()).device
+        N = self.N
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.rays_o, self.rays_d, self.gt = (torch.zeros(N, 3, **f32) for _ in range(3))
+        sizes = [N * (t + 1) for t in self.steps]
+        self.noise_flat = torch.zeros(sum(sizes), **f32)
+        self.noise, off = [], 0
+        for t, n in zip(self.steps, sizes):
+            self.noise.append(self.noise_flat[off:off + n].view(N, t + 1))
+            off += n
+        self.lv = []
+        for t in self.steps:
+            self.lv.append(dict(T=t, bins=torch.empty(N, t + 1, **f32), t_mid=torch.empty(N, t, **f32),
+                                deltas=torch.empty(N, t, **f32), x01=torch.empty(N, t, 3, **f32),
+                                sigma=torch.empty(N, t, **f32), weights=torch.empty(N, t, **f32),
+                                g_weights=torch.empty(N, t, **f32), g_sigma=torch.empty(N, t, **f32),
+                                ws=torch.empty(N, **f32), depth=torch.empty(N, **f32)))
+        B = N * self.steps[2]
+        self.head = torch.empty(B, 16, **f32)
+        self.g_head = torch.empty(B, 16, **f32)
+        self.enc, self.g_enc = torch.empty(B, 32, **f32), torch.empty(B, 32, **f32)
+        self.h1, self.h2 = torch.empty(B, 64, **f32), torch.empty(B, 64, **f32)
+        self.geo_sum, self.g_geo_sum = torch.empty(N, 15, **f32), torch.empty(N, 15, **f32)
+        self.g_ws = torch.empty(N, **f32)
+        self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)
+        self.image = torch.empty(N, 3, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.graphs = {}
+        self.eager_runs = {}
+        self.global_step = 0
+        for p in [model.grid.embeddings, *model.grid_mlp.parameters(), *model.view_mlp.parameters(),
+                  *model.prop_encoders.parameters(), *model.prop_mlp.parameters()]:
+            if p.grad is None or not p.grad.is_contiguous():
+                raise RuntimeError("FusedRGBStep needs parameters registered with FusedAdam (flat gradient views)")
+
+    # ------------------------------------------------------------------------------------------------------
+    def _launch(self, update_proposal):
+        """Enqueue the whole step on the current stream (eagerly, or under CUDA-graph capture)."""
+        m, lib, N = self.model, _lib.load(), self.N
+        st = _lib.current_stream(self.dev)
+        span, check, ptr = _lib.stats.span, _lib.check, _lib.ptr
+        aabb = m.aabb_train
+        bound, contract, min_near = float(m.bound), int(bool(m.opt.contract)), float(m.min_near)
+        lam_p = float(m.opt.lambda_proposal) if update_proposal else 0.0
+        lam_d = float(m.opt.lambda_distort)
+        self.loss.zero_()
+        if self.perturb:
+            self.noise_flat.uniform_()
+        o, d = self.rays_o.data_ptr(), self.rays_d.data_ptr()
+
+        # ---------------- forward: proposal levels
+        for li in (0, 1, 2):
+            L = self.lv[li]
+            T = L["T"]
+            noise = self.noise[li].data_ptr() if self.perturb else None
+            if li == 0:
+                with span("sample_uniform", N=N, T=T):
+                    rc = lib.sanerf_sample_uniform(o, d, aabb.data_ptr(), min_near, None, 0, noise, N, T, contract, bound,
+                                                   L["bins"].data_ptr(), L["t_mid"].data_ptr(), L["deltas"].data_ptr(),
+                                                   L["x01"].data_ptr(), st)
+                check(rc, "sample_uniform")
+            else:
+                P = self.lv[li - 1]
+                with span("sample_pdf", N=N, T=T):
+                    rc = lib.sanerf_sample_pdf(o, d, aabb.data_ptr(), min_near, None, 0, P["bins"].data_ptr(),
+                                               P["weights"].data_ptr(), P["T"], noise, N, T, contract, bound,
+                                               L["bins"].data_ptr(), L["t_mid"].data_ptr(), L["deltas"].data_ptr(),
+                                               L["x01"].data_ptr(), st)
+                check(rc, "sample_pdf")
+            if li < 2:
+                enc, mlp = m.prop_encoders[li], m.prop_mlp[li]
+                with span("prop_density_forward", B=N * T, L=enc.num_levels):
+                    rc = lib.sanerf_prop_density_forward(L["x01"].data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
+                                                         mlp.net[0].weight.data_ptr(), mlp.net[1].weight.data_ptr(), N * T,
+                                                         enc.num_levels, float(np.log2(enc.per_level_scale)),
+                                                         int(enc.base_resolution), L["sigma"].data_ptr(), st)
+                check(rc, "prop_density_forward")
+                with span("composite_forward", N=N, T=T, C=0):
+                    rc = lib.sanerf_composite_forward(L["sigma"].data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), None, 0,
+                                                      None, N, T, 0, self.opaque, 0.0, L["weights"].data_ptr(), L["ws"].data_ptr(),
+                                                      L["depth"].data_ptr(), None, None, st)
+                check(rc, "composite_forward")
+        # ---------------- forward: final level
+        L = self.lv[2]
+        T, B = L["T"], N * L["T"]
+        g, gm = m.grid, m.grid_mlp
+        S, H = float(np.log2(g.per_level_scale)), int(g.base_resolution)
+        w1, w2, w3 = (l.weight for l in gm.net)
+        with span("field_head_forward", B=B):
+            rc = lib.sanerf_field_head_forward(L["x01"].data_ptr(), g.embeddings.data_ptr(), g.offsets.data_ptr(), S, H, None,
+                                               w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, self.enc.data_ptr(),
+                                               self.h1.data_ptr(), self.h2.data_ptr(), self.head.data_ptr(), self.precision, st)
+        check(rc, "field_head_forward")
+        with span("trunc_exp_forward", n=B):
+            rc = lib.sanerf_trunc_exp_forward(self.head.data_ptr(), L["sigma"].data_ptr(), B, 16, 0, st)
+        check(rc, "trunc_exp_forward")
+        with span("composite_forward", N=N, T=T, C=15):
+            rc = lib.sanerf_composite_forward(L["sigma"].data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(),
+                                              self.head.data_ptr() + 4, 16, None, N, T, 15, self.opaque, float(m.t_thresh),
+                                              L["weights"].data_ptr(), L["ws"].data_ptr(), L["depth"].data_ptr(),
+                                              self.geo_sum.data_ptr(), self.n_alive.data_ptr(), st)
+        check(rc, "composite_forward")
+        v1, v2, v3 = (l.weight for l in m.view_mlp.net)
+        with span("view_head", N=N):
+            rc = lib.sanerf_view_head(self.geo_sum.data_ptr(), L["ws"].data_ptr(), d, self.gt.data_ptr(), v1.data_ptr(),
+                                      v2.data_ptr(), v3.data_ptr(), self.bg, 1.0, N, self.image.data_ptr(), self.loss.data_ptr(),
+                                      self.g_geo_sum.data_ptr(), self.g_ws.data_ptr(), v1.grad.data_ptr(), v2.grad.data_ptr(),
+                                      v3.grad.data_ptr(), st)
+        check(rc, "view_head")
+        # ---------------- sampling regularisers: loss + d loss / d weights, pre-multiplied by lambda
+        if lam_p > 0:
+            for li in (0, 1):
+                P = self.lv[li]
+                with span("proposal_loss", N=N, Tp=P["T"]):
+                    rc = lib.sanerf_proposal_loss(L["bins"].data_ptr(), L["weights"].data_ptr(), T, P["bins"].data_ptr(),
+                                                  P["weights"].data_ptr(), P["T"], N, lam_p, self.loss.data_ptr(),
+                                                  P["g_weights"].data_ptr(), st)
+                check(rc, "proposal_loss")
+        have_gw2 = lam_d > 0
+        if have_gw2:
+            with span("distortion_loss", N=N, T=T):
+                rc = lib.sanerf_distortion_loss(L["bins"].data_ptr(), L["weights"].data_ptr(), T, N, lam_d, self.loss.data_ptr(),
+                                                L["g_weights"].data_ptr(), st)
+            check(rc, "distortion_loss")
+        # ---------------- backward: final level
+        with span("composite_backward", N=N, T=T, C=15):
+            rc = lib.sanerf_composite_backward(L["sigma"].data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(),
+                                               self.head.data_ptr() + 4, 16, None, N, T, 15, self.opaque, float(m.t_thresh),
+                                               L["weights"].data_ptr(), L["g_weights"].data_ptr() if have_gw2 else None,
+                                               self.g_ws.data_ptr(), None, self.g_geo_sum.data_ptr(), L["g_sigma"].data_ptr(),
+                                               self.g_head.data_ptr() + 4, 16, st)
+        check(rc, "composite_backward")
+        with span("trunc_exp_backward", n=B):
+            rc = lib.sanerf_trunc_exp_backward(L["g_sigma"].data_ptr(), self.head.data_ptr(), self.g_head.data_ptr(), B, 16, 0, st)
+        check(rc, "trunc_exp_backward")
+        with span("field_head_backward", B=B):
+            rc = lib.sanerf_field_head_backward(self.enc.data_ptr(), self.h1.data_ptr(), self.h2.data_ptr(), self.g_head.data_ptr(),
+                                                w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, self.g_enc.data_ptr(),
+                                                w1.grad.data_ptr(), w2.grad.data_ptr(), w3.grad.data_ptr(), self.precision, st)
+        check(rc, "field_head_backward")
+        with span("grid_encode_backward", B=B, L=16, C=2, D=3, half=False):
+            rc = lib.sanerf_grid_encode_backward(self.g_enc.data_ptr(), L["x01"].data_ptr(), g.embeddings.data_ptr(),
+                                                 g.offsets.data_ptr(), g.embeddings.grad.data_ptr(), B, 3, 2, 16, 16, S, H, None,
+                                                 None, 0, 0, 0, _lib.SANERF_F32, _lib.LAYOUT_BLC, st)
+        check(rc, "grid_encode_backward")
+        # ---------------- backward: proposal levels (their only gradient source is the proposal loss)
+        if lam_p > 0:
+            for li in (1, 0):
+                P = self.lv[li]
+                Tp = P["T"]
+                enc, mlp = m.prop_encoders[li], m.prop_mlp[li]
+                with span("composite_backward", N=N, T=Tp, C=0):
+                    rc = lib.sanerf_composite_backward(P["sigma"].data_ptr(), P["deltas"].data_ptr(), P["t_mid"].data_ptr(), None, 0,
+                                                       None, N, Tp, 0, self.opaque, 0.0, P["weights"].data_ptr(),
+                                                       P["g_weights"].data_ptr(), None, None, None, P["g_sigma"].data_ptr(), None,
+                                                       0, st)
+                check(rc, "composite_backward")
+                with span("prop_density_backward", B=N * Tp, L=enc.num_levels):
+                    rc = lib.sanerf_prop_density_backward(P["x01"].data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
+                                                          mlp.net[0].weight.data_ptr(), mlp.net[1].weight.data_ptr(), N * Tp,
+                                                          enc.num_levels, float(np.log2(enc.per_level_scale)),
+                                                          int(enc.base_resolution), P["g_sigma"].data_ptr(),
+                                                          enc.embeddings.grad.data_ptr(), mlp.net[0].weight.grad.data_ptr(),
+                                                          mlp.net[1].weight.grad.data_ptr(), st)
+                check(rc, "prop_density_backward")
+
+    def _update(self):
+        if self.world_size > 1:
+            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+        self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
+
+    def gradients_only(self, rays_o, rays_d, gt, update_proposal=True):
+        """Forward + backward without the optimizer update (tests): gradients are left in the flat bucket."""
+        self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.gt.copy_(gt)
+        with torch.cuda.device(self.dev):
+            self._launch(update_proposal)
+        return self.loss[0]
+
+    def _graph(self, update_proposal):
+        key = bool(update_proposal)
+        if key not in self.graphs:
+            graph_whole = self.world_size == 1          # the NCCL exchange stays outside the graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(update_proposal)
+                if graph_whole:
+                    self._update()
+            self.graphs[key] = (g, graph_whole)
+        return self.graphs[key]
+
+    def __call__(self, rays_o, rays_d, gt):
+        """One training step; rays / targets may live on the host (pinned) or on the device.  Returns the loss
+        (a view of a static device buffer: read it before the next call)."""
+        self.global_step += 1
+        update_proposal = self.global_step <= 3000 or self.global_step % 5 == 0      # nerf/utils.py:910-911
+        self.rays_o.copy_(rays_o, non_blocking=True)
+        self.rays_d.copy_(rays_d, non_blocking=True)
+        self.gt.copy_(gt, non_blocking=True)
+        with torch.cuda.device(self.dev):
+            key = bool(update_proposal)
+            if self.use_graph and self.eager_runs.get(key, 0) >= 1:      # first step of each variant runs eagerly (warm-up)
+                g, whole = self._graph(update_proposal)
+                g.replay()
+                if not whole:
+                    self._update()
+            else:
+                self.eager_runs[key] = self.eager_runs.get(key, 0) + 1
+                self._launch(update_proposal)
+                self._update()
+        return self.loss[0]

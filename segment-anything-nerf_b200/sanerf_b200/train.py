@@ -33,10 +33,12 @@ def default_opt(**overrides):
 class RGBTrainer:
     """Stage-1 step: ``step(rays_o, rays_d, gt_rgb) -> loss`` (device tensors), with optional DDP-style sharding."""
 
-    def __init__(self, model, lr=1e-2, iters=20000, world_size=1):
+    def __init__(self, model, lr=1e-2, iters=20000, world_size=1, fused_step=True, use_graph=True):
         self.model = model.train()
         self.world_size = world_size
         self.global_step = 0
+        self.fused_step, self.use_graph = bool(fused_step), bool(use_graph)
+        self._plans = {}                                  # ray count -> FusedRGBStep (static buffers + CUDA graphs)
         params = [p for p in model.parameters() if p.requires_grad]
         # Adam(eps=1e-15) + LambdaLR 0.1**min(iter/iters,1)  (main.py:296,312-313) on flat buffers; the flat
         # gradient doubles as the all-reduce bucket and is cleared by the optimizer kernel
@@ -52,9 +54,30 @@ class RGBTrainer:
             loss = loss + self.model.opt.lambda_distort * out["distort_loss"]
         return loss, out
 
+    def plan(self, n_rays):
+        """The hand-scheduled, CUDA-graph-replayed step for ``n_rays`` rays (sanerf_b200/step.py), or None when the
+        model is not the reference's stage-1 configuration (then the autograd path below runs)."""
+        if not self.fused_step or not getattr(self.model, "tc_head", False) or not getattr(self.model, "fused", False):
+            return None
+        if n_rays not in self._plans:
+            from .step import FusedRGBStep, UnsupportedConfig
+            try:
+                self._plans[n_rays] = FusedRGBStep(self.model, self.optimizer, n_rays, world_size=self.world_size,
+                                                   use_graph=self.use_graph)
+            except UnsupportedConfig:
+                self._plans[n_rays] = None
+        return self._plans[n_rays]
+
     def step(self, rays_o, rays_d, gt_rgb):
+        plan = self.plan(rays_o.shape[0])
+        if plan is not None:
+            plan.global_step = self.global_step
+            self.global_step += 1
+            return plan(rays_o, rays_d, gt_rgb)
         self.global_step += 1
         update_proposal = self.global_step <= 3000 or self.global_step % 5 == 0   # nerf/utils.py:910-911
+        dev = self.optimizer.flat_param.device
+        rays_o, rays_d, gt_rgb = (t.to(dev, non_blocking=True) for t in (rays_o, rays_d, gt_rgb))
         loss, _ = self.loss(rays_o, rays_d, gt_rgb, update_proposal)
         loss.backward()                                   # accumulates into the (pre-zeroed) flat gradient
         if self.world_size > 1:

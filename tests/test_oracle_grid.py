@@ -110,11 +110,11 @@ def test_sh_closed_form_vs_reference_polynomials(ref_cpu):
 
 
 def test_product_sh_norm_table_matches_formula():
-    """The constants compiled into csrc/encoders_misc.cu are the closed-form N_l^m."""
+    """The constants compiled into csrc/sh_common.cuh are the closed-form N_l^m."""
     import os
     import re
     src = open(os.path.join(os.path.dirname(__file__), "..", "segment-anything-nerf_b200", "csrc",
-                            "encoders_misc.cu")).read()
+                            "sh_common.cuh")).read()
     body = src[src.index("kShNorm[8][8] = {"):]
     body = body[:body.index("};")]
     vals = [float(v) for v in re.findall(r"(-?\d+\.\d+(?:e[-+]?\d+)?)f", body)]
