@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 7
+#define SANERF_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -199,15 +199,17 @@ SANERF_API int sanerf_sample_pdf(const float* rays_o, const float* rays_d, const
 /* ------------------------------------------------------------------------------------------
  * Proposal density, fused: hash-grid encode (D=3, F=2, L<=8, fp32) -> Linear(2L,16) -> ReLU -> Linear(16,1) ->
  * trunc_exp (nerf/network.py:211-219, 248-252).  w1 f32 [16, 2L], w2 f32 [1,16] (nn.Linear layout, no bias).
- * Backward accumulates into grad_table [rows,2], grad_w1 [16,2L], grad_w2 [16] (caller zero-fills).
+ * enc_out f32 [B,2L] or NULL: the encoding, kept for the backward (`enc`; NULL there = re-gather it).
+ * Backward accumulates into grad_table [rows,2], grad_w1 [16,2L], grad_w2 [16] (caller zero-fills); consecutive
+ * samples of a ray that fall into the same cell are merged in the warp before the reductions are issued.
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_prop_density_forward(const float* x01, const float* table, const int32_t* offsets,
                                 const float* w1, const float* w2, uint32_t B, uint32_t L, float S,
-                                uint32_t H, float* sigma, void* stream);
+                                uint32_t H, float* sigma, float* enc_out, void* stream);
 SANERF_API int sanerf_prop_density_backward(const float* x01, const float* table, const int32_t* offsets,
                                  const float* w1, const float* w2, uint32_t B, uint32_t L, float S,
-                                 uint32_t H, const float* g_sigma, float* grad_table, float* grad_w1,
-                                 float* grad_w2, void* stream);
+                                 uint32_t H, const float* enc, const float* g_sigma, float* grad_table,
+                                 float* grad_w1, float* grad_w2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Sampling regularisers: loss value AND d loss / d weights in one kernel each.

@@ -32,13 +32,20 @@ struct GridBwdParams {
 template <typename T, uint32_t D, uint32_t C, uint32_t G, uint32_t CH>
 __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams p) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.B) return;
     const uint32_t level0 = blockIdx.y * G;
+    // fp32 tables with few values per cell: merge consecutive samples of a ray that share a cell before the
+    // reductions are issued (grid_common.cuh: warp_run_reduce).  Needs warp-uniform control flow: no early exits.
+    constexpr bool kAggregate = (sizeof(T) == 4) && ((1u << D) * CH <= 16u) && (CH == C);
+    const uint32_t lane = threadIdx.x & 31u;
 
     float x[D];
+    bool ok = b < p.B;
 #pragma unroll
-    for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(p.inputs + (size_t)b * D + d);
-    if (out_of_range<D>(x)) return;  // gridencoder.cu:279-284: gradient of OOB samples is dropped
+    for (uint32_t d = 0; d < D; ++d) x[d] = ok ? __ldg(p.inputs + (size_t)b * D + d) : 0.5f;
+    ok = ok && !out_of_range<D>(x);  // gridencoder.cu:279-284: gradient of OOB samples is dropped
+    if constexpr (!kAggregate) {
+        if (!ok) return;
+    }
 
     const T* __restrict__ grad = static_cast<const T*>(p.grad);
     T* __restrict__ gtab = static_cast<T*>(p.grad_table);
@@ -52,21 +59,53 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams 
         const LevelGeom<D> geo = level_geometry<D>(p.offsets, level, p.S, p.H, p.gridtype);
         const Cell<D> cell = locate<D>(geo, x, p.align_corners != 0, p.interp);
         T* __restrict__ slice = gtab + (size_t)(uint32_t)__ldg(p.offsets + level) * C;
-#pragma unroll 1
-        for (uint32_t c0 = 0; c0 < C; c0 += CH) {
+        if constexpr (kAggregate) {
             float gv[CH];
-            RowIO<T, CH>::load(src + c0, gv);
+#pragma unroll
+            for (uint32_t c = 0; c < CH; ++c) gv[c] = 0.0f;
+            if (ok) RowIO<T, CH>::load(src, gv);
             bool any = false;
 #pragma unroll
             for (uint32_t c = 0; c < CH; ++c) any |= (gv[c] != 0.0f);
-            if (!any) continue;
+            const bool contributes = ok && any;
+            float v[(1u << D) * CH];
 #pragma unroll
             for (uint32_t k = 0; k < (1u << D); ++k) {
-                const float w = corner_weight<D>(cell, k);
-                float upd[CH];
+                const float w = contributes ? corner_weight<D>(cell, k) : 0.0f;
 #pragma unroll
-                for (uint32_t c = 0; c < CH; ++c) upd[c] = w * gv[c];
-                RowIO<T, CH>::red(slice + (size_t)corner_row<D>(geo, cell, k) * C + c0, upd);
+                for (uint32_t c = 0; c < CH; ++c) v[k * CH + c] = w * gv[c];
+            }
+            uint32_t key[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) key[d] = cell.lo[d];
+            if (!contributes) key[0] = 0xffffffffu - lane;       // a key no cell has: its own (skipped) run
+            const bool head = warp_run_reduce<(1u << D) * CH, D>(v, key, lane);
+            if (head && contributes) {
+#pragma unroll
+                for (uint32_t k = 0; k < (1u << D); ++k) {
+                    float upd[CH];
+#pragma unroll
+                    for (uint32_t c = 0; c < CH; ++c) upd[c] = v[k * CH + c];
+                    RowIO<T, CH>::red(slice + (size_t)corner_row<D>(geo, cell, k) * C, upd);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < C; c0 += CH) {
+                float gv[CH];
+                RowIO<T, CH>::load(src + c0, gv);
+                bool any = false;
+#pragma unroll
+                for (uint32_t c = 0; c < CH; ++c) any |= (gv[c] != 0.0f);
+                if (!any) continue;
+#pragma unroll
+                for (uint32_t k = 0; k < (1u << D); ++k) {
+                    const float w = corner_weight<D>(cell, k);
+                    float upd[CH];
+#pragma unroll
+                    for (uint32_t c = 0; c < CH; ++c) upd[c] = w * gv[c];
+                    RowIO<T, CH>::red(slice + (size_t)corner_row<D>(geo, cell, k) * C + c0, upd);
+                }
             }
         }
     }

@@ -130,6 +130,35 @@ __device__ __forceinline__ float corner_weight(const Cell<D>& c, uint32_t corner
     return w;
 }
 
+// Warp-aggregated scatter.  Samples are ray-ordered, so on coarse levels several CONSECUTIVE lanes of a warp fall
+// into the same grid cell and would each fire the same 2^D reductions at the same addresses (the L2 atomic unit
+// serialises them: level 0 of a proposal grid costs 4x more with ray-ordered than with shuffled samples).  This is a
+// segmented suffix-reduction over runs of consecutive lanes with identical cell keys: afterwards the first lane of
+// each run ("head", return value) holds the run's sums in v[] and is the only one that issues reductions.
+// key[] = the per-dimension lower-corner contributions (Cell::lo): equal keys <=> equal rows for every corner.
+// Must be called by all 32 lanes.
+template <uint32_t NV, uint32_t D>
+__device__ __forceinline__ bool warp_run_reduce(float (&v)[NV], const uint32_t (&key)[D], uint32_t lane) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    bool head = (lane == 0u);
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) head |= (__shfl_up_sync(kFull, key[d], 1) != key[d]);
+    const uint32_t heads = __ballot_sync(kFull, head);
+    if (heads == kFull) return true;                                   // every run has length 1: nothing to merge
+    const uint32_t later = (lane == 31u) ? 0u : (heads >> (lane + 1u));    // bit i: lane + 1 + i starts a new run
+#pragma unroll
+    for (uint32_t step = 1; step < 32u; step <<= 1) {
+        const bool same = (lane + step < 32u) && ((later & ((1u << step) - 1u)) == 0u);
+        if (__ballot_sync(kFull, same) == 0u) break;                   // longest run already folded
+#pragma unroll
+        for (uint32_t i = 0; i < NV; ++i) {
+            const float t = __shfl_down_sync(kFull, v[i], step);
+            if (same) v[i] += t;
+        }
+    }
+    return head;
+}
+
 // Inclusive range test of the reference (gridencoder.cu:109): NaN passes.
 template <uint32_t D>
 __device__ __forceinline__ bool out_of_range(const float (&x)[D]) {

@@ -67,7 +67,8 @@ __device__ __forceinline__ void prop_encode(const PropParams& p, const float (&x
 }
 
 template <uint32_t L>
-__global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropParams p, float* __restrict__ sigma) {
+__global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropParams p, float* __restrict__ sigma,
+                                                                    float* __restrict__ enc_out) {
     constexpr uint32_t IN = 2 * L;
     __shared__ float s_w1[kPropHidden * IN];
     __shared__ float s_w2[kPropHidden];
@@ -81,6 +82,11 @@ __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropPa
     for (uint32_t d = 0; d < 3; ++d) x[d] = __ldg(p.x01 + (size_t)b * 3 + d);
     float enc[IN];
     prop_encode<L>(p, x, out_of_range<3>(x), enc);
+    if (enc_out != nullptr) {                // kept for the backward: 8 L bytes per sample instead of 8 L gathers
+#pragma unroll
+        for (uint32_t l = 0; l < L; ++l)
+            *reinterpret_cast<float2*>(enc_out + (size_t)b * IN + 2 * l) = make_float2(enc[2 * l], enc[2 * l + 1]);
+    }
     float pre = 0.0f;
 #pragma unroll
     for (uint32_t j = 0; j < kPropHidden; ++j) {
@@ -92,111 +98,182 @@ __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropPa
     sigma[b] = expf(pre);                    // trunc_exp forward (activation.py:10)
 }
 
-template <uint32_t L>
-__global__ void __launch_bounds__(kPropThreads) prop_backward_kernel(const PropParams p, const float* __restrict__ g_sigma,
-                                                                     float* __restrict__ grad_table,
-                                                                     float* __restrict__ grad_w1,
-                                                                     float* __restrict__ grad_w2, uint32_t tiles) {
+// Backward.  One thread = one sample (persistent grid-stride over 256-sample tiles); everything is warp-synchronous,
+// there is no CTA-wide barrier inside the loop:
+//  1. recompute the MLP forward and the gradient of the encoding from the encoding the forward saved (SAVED; 8 L
+//     bytes per sample) or, without it, from a full re-gather;
+//  2. weight gradients: the warp's 32 samples are staged in a warp-private shared-memory tile and every lane
+//     accumulates the L+1 entries of dW it owns (lane -> hidden unit j = lane % 16, input half = lane / 16) in
+//     registers ACROSS tiles; one cross-warp reduction and one atomic per entry per CTA at the very end;
+//  3. table gradient: per level, consecutive lanes in the same cell are merged first (warp_run_reduce), then the
+//     head lanes issue one red.global.add.v2.f32 per corner.
+constexpr uint32_t kPropRow = 36;                        // h[16] | enc half 0 (8) | enc half 1 (8) | dpre (4)
+
+template <uint32_t L, bool SAVED>
+__global__ void __launch_bounds__(kPropThreads, 2) prop_backward_kernel(const PropParams p, const float* __restrict__ enc_saved,
+                                                                        const float* __restrict__ g_sigma,
+                                                                        float* __restrict__ grad_table,
+                                                                        float* __restrict__ grad_w1,
+                                                                        float* __restrict__ grad_w2, uint32_t tiles) {
     constexpr uint32_t IN = 2 * L;
-    constexpr uint32_t ROW = kPropHidden + IN + 1;       // h[16] | enc[IN] | dpre (odd length: bank-conflict free)
+    constexpr uint32_t kWarps = kPropThreads / 32;
     __shared__ float s_w1[kPropHidden * IN];
     __shared__ float s_w2[kPropHidden];
-    __shared__ float s_rows[kPropThreads * ROW];
-    for (uint32_t i = threadIdx.x; i < kPropHidden * IN; i += blockDim.x) s_w1[i] = __ldg(p.w1 + i);
-    if (threadIdx.x < kPropHidden) s_w2[threadIdx.x] = __ldg(p.w2 + threadIdx.x);
+    __shared__ LevelGeom<3> s_geo[L];
+    __shared__ uint32_t s_base[L];
+    __shared__ __align__(16) float s_rows[kWarps * 32 * kPropRow];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t i = tid; i < kPropHidden * IN; i += blockDim.x) s_w1[i] = __ldg(p.w1 + i);
+    if (tid < kPropHidden) s_w2[tid] = __ldg(p.w2 + tid);
+    if (tid >= 32 && tid < 32 + L) {
+        s_geo[tid - 32] = level_geometry<3>(p.offsets, tid - 32, p.S, p.H, 0u);
+        s_base[tid - 32] = (uint32_t)__ldg(p.offsets + (tid - 32));
+    }
     __syncthreads();
 
-    // entries of dW owned by this thread in the reduction phase: e < 16*IN -> dW1[j][i]; then dW2[j]
-    constexpr uint32_t kEntries = kPropHidden * IN + kPropHidden;
-    constexpr uint32_t kOwn = (kEntries + kPropThreads - 1) / kPropThreads;
-    float acc[kOwn];
+    float* rows = s_rows + (size_t)warp * 32 * kPropRow;
+    float* row = rows + (size_t)lane * kPropRow;
+    const uint32_t own_j = lane & 15u, own_half = lane >> 4;
+    float acc1[L], acc2 = 0.0f;                         // dW1[own_j][own_half*L + q] / W2[own_j] ; dW2[own_j] (half 0)
 #pragma unroll
-    for (uint32_t q = 0; q < kOwn; ++q) acc[q] = 0.0f;
+    for (uint32_t q = 0; q < L; ++q) acc1[q] = 0.0f;
+    const float* __restrict__ table = p.table;
 
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint32_t b = tile * kPropThreads + threadIdx.x;
-        float* row = s_rows + (size_t)threadIdx.x * ROW;     // h[16] | enc[IN] | dpre
+        const uint32_t b = tile * kPropThreads + tid;
         const bool live = b < p.B;
         float x[3] = {0.5f, 0.5f, 0.5f};
         if (live) {
 #pragma unroll
             for (uint32_t d = 0; d < 3; ++d) x[d] = __ldg(p.x01 + (size_t)b * 3 + d);
         }
-        const bool oob = out_of_range<3>(x);
-        float enc[IN], h[kPropHidden];
-        prop_encode<L>(p, x, oob || !live, enc);
-        float pre = 0.0f;
+        const bool ok = live && !out_of_range<3>(x);
+        // ---- 1. forward recompute
+        float enc[IN];
+        if constexpr (SAVED) {
+#pragma unroll
+            for (uint32_t l = 0; l < L; ++l) {
+                const float2 e = live ? __ldg(reinterpret_cast<const float2*>(enc_saved + (size_t)b * IN + 2 * l))
+                                      : make_float2(0.0f, 0.0f);
+                enc[2 * l] = e.x;
+                enc[2 * l + 1] = e.y;
+            }
+        } else {
+#pragma unroll
+        for (uint32_t l = 0; l < L; ++l) {
+            const LevelGeom<3> geo = s_geo[l];
+            const Cell<3> cell = locate<3>(geo, x, false, 0u);
+            const size_t base = (size_t)s_base[l];
+            float a0 = 0.0f, a1 = 0.0f;
+            float2 val[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k)
+                val[k] = ok ? __ldg(reinterpret_cast<const float2*>(table + (base + corner_row<3>(geo, cell, k)) * 2))
+                            : make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {
+                const float w = corner_weight<3>(cell, k);
+                a0 = __fmaf_rn(w, val[k].x, a0);
+                a1 = __fmaf_rn(w, val[k].y, a1);
+            }
+            enc[2 * l] = a0;
+            enc[2 * l + 1] = a1;
+        }
+        }
+        // one pass over the weights: h_j and, for the backward, u_i = sum_j [h_j > 0] W2_j W1_ji  (d enc_i = dpre * u_i)
+        float h[kPropHidden], u[IN], pre = 0.0f;
+#pragma unroll
+        for (uint32_t i = 0; i < IN; ++i) u[i] = 0.0f;
 #pragma unroll
         for (uint32_t j = 0; j < kPropHidden; ++j) {
-            float a = 0.0f;
+            float wj[IN], a = 0.0f;
 #pragma unroll
-            for (uint32_t i = 0; i < IN; ++i) a = __fmaf_rn(s_w1[j * IN + i], enc[i], a);
+            for (uint32_t i = 0; i < IN; ++i) { wj[i] = s_w1[j * IN + i]; a = __fmaf_rn(wj[i], enc[i], a); }
             h[j] = fmaxf(a, 0.0f);
-            pre = __fmaf_rn(s_w2[j], h[j], pre);
+            const float w2j = s_w2[j];
+            pre = __fmaf_rn(w2j, h[j], pre);
+            const float gate = (a > 0.0f) ? w2j : 0.0f;                  // ReLU mask
+#pragma unroll
+            for (uint32_t i = 0; i < IN; ++i) u[i] = __fmaf_rn(gate, wj[i], u[i]);
         }
         // trunc_exp backward (activation.py:16)
         const float dpre = live ? __ldg(g_sigma + b) * expf(fminf(fmaxf(pre, -15.0f), 15.0f)) : 0.0f;
         float denc[IN];
 #pragma unroll
-        for (uint32_t i = 0; i < IN; ++i) denc[i] = 0.0f;
+        for (uint32_t i = 0; i < IN; ++i) denc[i] = dpre * u[i];
+        // ---- 2. weight gradients:  dW1[j][i] = W2[j] * sum_s [h_sj > 0] dpre_s enc_si ;  dW2[j] = sum_s dpre_s h_sj
 #pragma unroll
-        for (uint32_t j = 0; j < kPropHidden; ++j) {
-            const float dh = (h[j] > 0.0f) ? dpre * s_w2[j] : 0.0f;      // ReLU mask
-            row[j] = h[j];
+        for (uint32_t j = 0; j < kPropHidden; j += 4)
+            *reinterpret_cast<float4*>(row + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
 #pragma unroll
-            for (uint32_t i = 0; i < IN; ++i) denc[i] = __fmaf_rn(s_w1[j * IN + i], dh, denc[i]);
+        for (uint32_t half = 0; half < 2; ++half) {
+            float e[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) e[q] = (q < L) ? enc[half * L + q] : 0.0f;
+            *reinterpret_cast<float4*>(row + 16 + half * 8) = make_float4(e[0], e[1], e[2], e[3]);
+            if (L > 4) *reinterpret_cast<float4*>(row + 20 + half * 8) = make_float4(e[4], e[5], e[6], e[7]);
         }
+        row[32] = dpre;
+        __syncwarp();
+#pragma unroll 4
+        for (uint32_t s = 0; s < 32; ++s) {
+            const float* r = rows + s * kPropRow;
+            const float hs = r[own_j], dp = r[32];
+            const float m = (hs > 0.0f) ? dp : 0.0f;
+            const float4 e0 = *reinterpret_cast<const float4*>(r + 16 + own_half * 8);
+            float e[8] = {e0.x, e0.y, e0.z, e0.w, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (L > 4) {
+                const float4 e1 = *reinterpret_cast<const float4*>(r + 20 + own_half * 8);
+                e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
+            }
 #pragma unroll
-        for (uint32_t i = 0; i < IN; ++i) row[kPropHidden + i] = enc[i];
-        row[ROW - 1] = dpre;
-
-        // table gradient: scatter denc through the interpolation weights (gridencoder.cu:313-347)
-        if (live && !oob && dpre != 0.0f) {
+            for (uint32_t q = 0; q < L; ++q) acc1[q] = __fmaf_rn(m, e[q], acc1[q]);
+            acc2 = __fmaf_rn(dp, hs, acc2);
+        }
+        __syncwarp();
+        // ---- 3. table gradient (gridencoder.cu:313-347), warp-aggregated
+        const bool contributes = ok && dpre != 0.0f;
+        // the level loop stays rolled (register pressure): the gradient of the encoding is parked in this lane's row
 #pragma unroll
-            for (uint32_t l = 0; l < L; ++l) {
-                const LevelGeom<3> geo = level_geometry<3>(p.offsets, l, p.S, p.H, 0u);
-                const Cell<3> cell = locate<3>(geo, x, false, 0u);
-                float* slice = grad_table + (size_t)(uint32_t)__ldg(p.offsets + l) * 2;
+        for (uint32_t i = 0; i < IN; ++i) row[i] = denc[i];
+#pragma unroll 1
+        for (uint32_t l = 0; l < L; ++l) {
+            const LevelGeom<3> geo = s_geo[l];
+            const Cell<3> cell = locate<3>(geo, x, false, 0u);
+            const float d0 = row[2 * l], d1 = row[2 * l + 1];
+            float v[16];
 #pragma unroll
-                for (uint32_t k = 0; k < 8; ++k) {
-                    const float w = corner_weight<3>(cell, k);
-                    red_add_v2_f32(slice + (size_t)corner_row<3>(geo, cell, k) * 2, w * denc[2 * l], w * denc[2 * l + 1]);
-                }
+            for (uint32_t k = 0; k < 8; ++k) {
+                const float w = contributes ? corner_weight<3>(cell, k) : 0.0f;
+                v[2 * k] = w * d0;
+                v[2 * k + 1] = w * d1;
+            }
+            // lanes that do not contribute get a key no cell has (their own runs, which are skipped)
+            const uint32_t key[3] = {contributes ? cell.lo[0] : 0xffffffffu - lane, cell.lo[1], cell.lo[2]};
+            const bool head = warp_run_reduce<16, 3>(v, key, lane);
+            if (head && contributes) {
+                float* slice = grad_table + (size_t)s_base[l] * 2;
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k)
+                    red_add_v2_f32(slice + (size_t)corner_row<3>(geo, cell, k) * 2, v[2 * k], v[2 * k + 1]);
             }
         }
-        __syncthreads();
-        // weight gradients: each thread sweeps the tile's samples for the entries it owns
-        //   dW1[j][i] = W2[j] * sum_s [h_sj > 0] dpre_s enc_si      dW2[j] = sum_s dpre_s h_sj
-#pragma unroll
-        for (uint32_t q = 0; q < kOwn; ++q) {
-            const uint32_t e = threadIdx.x + q * kPropThreads;
-            if (e < kPropHidden * IN) {
-                const uint32_t ej = e / IN, ei = e - ej * IN;
-                float a = 0.0f;
-#pragma unroll 8
-                for (uint32_t s = 0; s < kPropThreads; ++s) {
-                    const float* r = s_rows + s * ROW;
-                    a = __fmaf_rn((r[ej] > 0.0f) ? r[ROW - 1] : 0.0f, r[kPropHidden + ei], a);
-                }
-                acc[q] += a * s_w2[ej];
-            } else if (e < kEntries) {
-                const uint32_t ej = e - kPropHidden * IN;
-                float a = 0.0f;
-#pragma unroll 8
-                for (uint32_t s = 0; s < kPropThreads; ++s) {
-                    const float* r = s_rows + s * ROW;
-                    a = __fmaf_rn(r[ROW - 1], r[ej], a);
-                }
-                acc[q] += a;
-            }
-        }
-        __syncthreads();
     }
+    // ---- cross-warp reduction of the weight gradients, one atomic per entry per CTA
+    __syncthreads();
+    float* scratch = s_rows;                              // [kWarps][32][L+1]
 #pragma unroll
-    for (uint32_t q = 0; q < kOwn; ++q) {
-        const uint32_t e = threadIdx.x + q * kPropThreads;
-        if (e < kPropHidden * IN) red_add_f32(grad_w1 + e, acc[q]);
-        else if (e < kEntries) red_add_f32(grad_w2 + (e - kPropHidden * IN), acc[q]);
+    for (uint32_t q = 0; q < L; ++q) scratch[(warp * 32 + lane) * (L + 1) + q] = acc1[q];
+    scratch[(warp * 32 + lane) * (L + 1) + L] = acc2;
+    __syncthreads();
+    for (uint32_t e = tid; e < 32 * (L + 1); e += blockDim.x) {
+        float a = 0.0f;
+#pragma unroll
+        for (uint32_t w = 0; w < kWarps; ++w) a += scratch[w * 32 * (L + 1) + e];
+        const uint32_t ln = e / (L + 1), q = e - ln * (L + 1);
+        const uint32_t j = ln & 15u, half = ln >> 4;
+        if (q < L) red_add_f32(grad_w1 + j * IN + half * L + q, a * s_w2[j]);
+        else if (half == 0) red_add_f32(grad_w2 + j, a);
     }
 }
 
@@ -225,7 +302,7 @@ using namespace sanerf;
 
 extern "C" int sanerf_prop_density_forward(const float* x01, const float* table, const int32_t* offsets,
                                            const float* w1, const float* w2, uint32_t B, uint32_t L, float S,
-                                           uint32_t H, float* sigma, void* stream) {
+                                           uint32_t H, float* sigma, float* enc_out, void* stream) {
     if (B == 0) return SANERF_OK;
     PropParams p{x01, table, offsets, w1, w2, B, L, H, S};
     int rc = check_prop(p);
@@ -233,14 +310,14 @@ extern "C" int sanerf_prop_density_forward(const float* x01, const float* table,
     SANERF_REQUIRE_PTR(sigma);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t blocks = div_up(B, kPropThreads);
-    SANERF_PROP_DISPATCH(L, (prop_forward_kernel<LL><<<blocks, kPropThreads, 0, st>>>(p, sigma)));
+    SANERF_PROP_DISPATCH(L, (prop_forward_kernel<LL><<<blocks, kPropThreads, 0, st>>>(p, sigma, enc_out)));
     return check_launch("prop_forward_kernel");
 }
 
 extern "C" int sanerf_prop_density_backward(const float* x01, const float* table, const int32_t* offsets,
                                             const float* w1, const float* w2, uint32_t B, uint32_t L, float S,
-                                            uint32_t H, const float* g_sigma, float* grad_table, float* grad_w1,
-                                            float* grad_w2, void* stream) {
+                                            uint32_t H, const float* enc, const float* g_sigma, float* grad_table,
+                                            float* grad_w1, float* grad_w2, void* stream) {
     if (B == 0) return SANERF_OK;
     PropParams p{x01, table, offsets, w1, w2, B, L, H, S};
     int rc = check_prop(p);
@@ -248,8 +325,14 @@ extern "C" int sanerf_prop_density_backward(const float* x01, const float* table
     SANERF_REQUIRE_PTR(g_sigma); SANERF_REQUIRE_PTR(grad_table); SANERF_REQUIRE_PTR(grad_w1); SANERF_REQUIRE_PTR(grad_w2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t tiles = div_up(B, kPropThreads);
-    const uint32_t blocks = tiles < (uint32_t)(kNumSMs * 4) ? tiles : (uint32_t)(kNumSMs * 4);
-    SANERF_PROP_DISPATCH(L, (prop_backward_kernel<LL><<<blocks, kPropThreads, 0, st>>>(p, g_sigma, grad_table, grad_w1,
-                                                                                      grad_w2, tiles)));
+    const uint32_t cap = (uint32_t)kNumSMs * 2u;                              // persistent: resident CTAs only
+    const uint32_t blocks = tiles < cap ? tiles : cap;
+    if (enc != nullptr) {
+        SANERF_PROP_DISPATCH(L, (prop_backward_kernel<LL, true><<<blocks, kPropThreads, 0, st>>>(p, enc, g_sigma, grad_table,
+                                                                                                grad_w1, grad_w2, tiles)));
+    } else {
+        SANERF_PROP_DISPATCH(L, (prop_backward_kernel<LL, false><<<blocks, kPropThreads, 0, st>>>(p, enc, g_sigma, grad_table,
+                                                                                                 grad_w1, grad_w2, tiles)));
+    }
     return check_launch("prop_backward_kernel");
 }

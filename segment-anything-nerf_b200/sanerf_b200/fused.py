@@ -79,26 +79,29 @@ class _PropDensity(Function):
         B = x01.numel() // 3
         L = offsets.numel() - 1
         sigma = torch.empty(x01.shape[:-1], device=x01.device, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad[1:5])
+        enc = torch.empty(B, 2 * L, device=x01.device, dtype=torch.float32) if need_grad else None
         lib = _lib.load()
         with torch.cuda.device(x01.device), _lib.stats.span("prop_density_forward", B=B, L=L):
             rc = lib.sanerf_prop_density_forward(x01.data_ptr(), table.data_ptr(), offsets.data_ptr(), w1.data_ptr(),
-                                                 w2.data_ptr(), B, L, float(S), int(H), sigma.data_ptr(), _stream(x01))
+                                                 w2.data_ptr(), B, L, float(S), int(H), sigma.data_ptr(), _lib.ptr(enc),
+                                                 _stream(x01))
         _lib.check(rc, "prop_density_forward")
-        ctx.save_for_backward(x01, table, offsets, w1, w2)
+        ctx.save_for_backward(x01, table, offsets, w1, w2, enc)
         ctx.meta = (B, L, float(S), int(H))
         return sigma
 
     @staticmethod
     def backward(ctx, g_sigma):
-        x01, table, offsets, w1, w2 = ctx.saved_tensors
+        x01, table, offsets, w1, w2, enc = ctx.saved_tensors
         B, L, S, H = ctx.meta
         g_sigma = g_sigma.contiguous()
         g_table, g_w1, g_w2 = torch.zeros_like(table), torch.zeros_like(w1), torch.zeros_like(w2)
         lib = _lib.load()
         with torch.cuda.device(x01.device), _lib.stats.span("prop_density_backward", B=B, L=L):
             rc = lib.sanerf_prop_density_backward(x01.data_ptr(), table.data_ptr(), offsets.data_ptr(), w1.data_ptr(),
-                                                  w2.data_ptr(), B, L, S, H, g_sigma.data_ptr(), g_table.data_ptr(),
-                                                  g_w1.data_ptr(), g_w2.data_ptr(), _stream(x01))
+                                                  w2.data_ptr(), B, L, S, H, _lib.ptr(enc), g_sigma.data_ptr(),
+                                                  g_table.data_ptr(), g_w1.data_ptr(), g_w2.data_ptr(), _stream(x01))
         _lib.check(rc, "prop_density_backward")
         return None, g_table, None, g_w1, g_w2, None, None
 

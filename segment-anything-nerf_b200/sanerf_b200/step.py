@@ -61,11 +61,12 @@ class FusedRGBStep:
             self.noise.append(self.noise_flat[off:off + n].view(N, t + 1))
             off += n
         self.lv = []
-        for t in self.steps:
+        for li, t in enumerate(self.steps):
             self.lv.append(dict(T=t, bins=torch.empty(N, t + 1, **f32), t_mid=torch.empty(N, t, **f32),
                                 deltas=torch.empty(N, t, **f32), x01=torch.empty(N, t, 3, **f32),
                                 sigma=torch.empty(N, t, **f32), weights=torch.empty(N, t, **f32),
                                 g_weights=torch.empty(N, t, **f32), g_sigma=torch.empty(N, t, **f32),
+                                enc=(torch.empty(N * t, 2 * model.prop_encoders[li].num_levels, **f32) if li < 2 else None),
                                 ws=torch.empty(N, **f32), depth=torch.empty(N, **f32)))
         B = N * self.steps[2]
         self.head = torch.empty(B, 16, **f32)
@@ -125,7 +126,8 @@ class FusedRGBStep:
                     rc = lib.sanerf_prop_density_forward(L["x01"].data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
                                                          mlp.net[0].weight.data_ptr(), mlp.net[1].weight.data_ptr(), N * T,
                                                          enc.num_levels, float(np.log2(enc.per_level_scale)),
-                                                         int(enc.base_resolution), L["sigma"].data_ptr(), st)
+                                                         int(enc.base_resolution), L["sigma"].data_ptr(),
+                                                         L["enc"].data_ptr() if update_proposal else None, st)
                 check(rc, "prop_density_forward")
                 with span("composite_forward", N=N, T=T, C=0):
                     rc = lib.sanerf_composite_forward(L["sigma"].data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), None, 0,
@@ -211,7 +213,7 @@ class FusedRGBStep:
                     rc = lib.sanerf_prop_density_backward(P["x01"].data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
                                                           mlp.net[0].weight.data_ptr(), mlp.net[1].weight.data_ptr(), N * Tp,
                                                           enc.num_levels, float(np.log2(enc.per_level_scale)),
-                                                          int(enc.base_resolution), P["g_sigma"].data_ptr(),
+                                                          int(enc.base_resolution), P["enc"].data_ptr(), P["g_sigma"].data_ptr(),
                                                           enc.embeddings.grad.data_ptr(), mlp.net[0].weight.grad.data_ptr(),
                                                           mlp.net[1].weight.grad.data_ptr(), st)
                 check(rc, "prop_density_backward")
