@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 8
+#define SANERF_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -255,9 +255,12 @@ SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
  *   W1 [64,32], W2 [64,64], W3 [16,64] = grid_mlp (network.py:103; nn.Linear layout [out,in], no bias, ReLU).
  * Replaces `h = self.grid(x); f = self.grid_mlp(h)` (network.py:223-224): one kernel, activations never leave the SM.
  *  x01 f32 [B,3] in [0,1]^3 (grid.py:156 mapping already applied), or NULL to read the encoding from enc_in [B,32];
- *  enc_out f32 [B,32] or NULL: the encoding, saved for the backward (bit-identical to sanerf_grid_encode_forward);
+ *  enc_out f32 [ceil(B/128)*128, 32] or NULL: the encoding, saved for the backward (values bit-identical to
+ *  sanerf_grid_encode_forward).  The three saved activations are private to this pair of kernels and are stored
+ *  TILE-CHUNK-MAJOR: element (b, k) of a W-wide matrix at float offset (((b/128)*(W/4) + k/4)*128 + b%128)*4 + k%4,
+ *  so that a warp touches 512 contiguous bytes per instruction in both kernels;
  *  precision 0: fp32 parity (every product as a 3-term tf32 split, fp32 accumulate), 1: one tf32 pass.
- *  h1_out / h2_out f32 [B,64] or both NULL: the post-ReLU activations of layers 1 and 2, saved for the backward.
+ *  h1_out / h2_out f32 [ceil(B/128)*128, 64] or both NULL: the post-ReLU activations of layers 1 and 2 (same layout).
  * Backward: from enc [B,32], h1, h2 [B,64] and g_out [B,16] produces g_enc [B,32] (feed it to
  * sanerf_grid_encode_backward, layout [B,L*C]) and ACCUMULATES the weight gradients into g_w1 / g_w2 / g_w3
  * (caller zero-fills).  Data gradients: A operand in tensor memory x transposed weight; weight gradients: MN-major

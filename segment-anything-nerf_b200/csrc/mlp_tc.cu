@@ -37,6 +37,13 @@ constexpr uint32_t kFwdSmem = oH + 2 * kH;
 constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, kTmemCols = 256;
 }  // namespace head
 
+// float offset of the 4-element chunk c of sample b in a "tile-chunk-major" [B, W] matrix: [tile][chunk][row][4].
+// The saved activations (enc, H1, H2) use it: a warp that writes / reads one chunk of 32 consecutive samples touches
+// 512 contiguous bytes, whether it works sample-per-thread (forward epilogue) or any-lane (backward staging).
+__host__ __device__ __forceinline__ size_t tcm_off(uint32_t b, uint32_t chunk, uint32_t chunks_per_row) {
+    return (((size_t)(b >> 7) * chunks_per_row + chunk) * 128u + (b & 127u)) * 4u;
+}
+
 struct HeadFwdParams {
     const float* x01;        // [B,3] in [0,1]^3, or NULL: take the encoding from `enc_in`
     const float* table;      // [rows,2] fp32
@@ -85,22 +92,24 @@ __device__ __forceinline__ void stage_weight(const float* __restrict__ w, uint8_
     }
 }
 
-// D[128, N] = A[128, K] . B[N, K]^T over chunk-major K-major operands; one thread issues
+// D[128, N] = A[128, K] . B[N, K]^T over chunk-major K-major operands; one thread issues.  a_* / b_* are the LOW
+// descriptor halves of the hi / lo planes (umma::desc_lo); the high halves are compile-time constants.
 template <uint32_t N, uint32_t K, uint32_t B_ROWS>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                            bool split) {
     constexpr uint32_t idesc = umma::idesc_tf32(128, N, 0, 0);
-    constexpr uint32_t a_lbo = head::kTile * 16u, b_lbo = B_ROWS * 16u;
+    constexpr uint32_t a_step = (2u * head::kTile * 16u) >> 4, b_step = (2u * B_ROWS * 16u) >> 4;   // 8 K elements = 2 chunks
+    constexpr uint32_t hi = umma::desc_hi(128u, umma::kLayoutNone);
     uint32_t acc = 0;
 #pragma unroll
     for (uint32_t ks = 0; ks < K / 8; ++ks) {
-        const uint32_t ao = ks * 2u * a_lbo, bo = ks * 2u * b_lbo;
+        const uint32_t ao = ks * a_step, bo = ks * b_step;
         if (split) {
-            umma::mma_tf32(tmem_d, umma::smem_desc(a_lo + ao, a_lbo, 128u), umma::smem_desc(b_hi + bo, b_lbo, 128u), idesc, acc);
-            umma::mma_tf32(tmem_d, umma::smem_desc(a_hi + ao, a_lbo, 128u), umma::smem_desc(b_lo + bo, b_lbo, 128u), idesc, 1u);
+            umma::mma_tf32_ss2(tmem_d, a_lo + ao, hi, b_hi + bo, hi, idesc, acc);
+            umma::mma_tf32_ss2(tmem_d, a_hi + ao, hi, b_lo + bo, hi, idesc, 1u);
             acc = 1;
         }
-        umma::mma_tf32(tmem_d, umma::smem_desc(a_hi + ao, a_lbo, 128u), umma::smem_desc(b_hi + bo, b_lbo, 128u), idesc, acc);
+        umma::mma_tf32_ss2(tmem_d, a_hi + ao, hi, b_hi + bo, hi, idesc, acc);
         acc = 1;
     }
 }
@@ -113,9 +122,9 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // TMEM accumulator (64 columns of this thread's lane) -> ReLU -> hi/lo planes of the chunk-major H tile
-// `save` = this sample's row of the [B,64] activation kept for the backward (or NULL)
+// `save` = the tile-chunk-major [B,64] activation kept for the backward (or NULL): chunk c of sample b at tcm_off(b, c, 16)
 __device__ __forceinline__ void relu_to_smem(uint32_t tmem_lane_col, uint8_t* h_hi, uint8_t* h_lo, uint32_t row, bool split,
-                                             float* save) {
+                                             float* save, uint32_t b) {
 #pragma unroll
     for (uint32_t c0 = 0; c0 < head::kHid; c0 += 16) {
         float v[16];
@@ -125,7 +134,8 @@ __device__ __forceinline__ void relu_to_smem(uint32_t tmem_lane_col, uint8_t* h_
 #pragma unroll
         for (uint32_t j = 0; j < 16; j += 4) {
             put_chunk(h_hi, h_lo, head::kTile, row, (c0 + j) >> 2, v[j], v[j + 1], v[j + 2], v[j + 3], split);
-            if (save != nullptr) *reinterpret_cast<float4*>(save + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (save != nullptr)
+                *reinterpret_cast<float4*>(save + tcm_off(b, (c0 + j) >> 2, 16)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
     }
 }
@@ -211,10 +221,9 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
                     enc[2 * q] = a0;
                     enc[2 * q + 1] = a1;
                 }
-                if (p.enc_out != nullptr && live) {
-                    float4* dst = reinterpret_cast<float4*>(p.enc_out + (size_t)b * kIn + lg * 8);
-                    dst[0] = make_float4(enc[0], enc[1], enc[2], enc[3]);
-                    dst[1] = make_float4(enc[4], enc[5], enc[6], enc[7]);
+                if (p.enc_out != nullptr && live) {          // tile-chunk-major: 32 consecutive samples = 512 contiguous bytes
+                    *reinterpret_cast<float4*>(p.enc_out + tcm_off(b, lg * 2, 8)) = make_float4(enc[0], enc[1], enc[2], enc[3]);
+                    *reinterpret_cast<float4*>(p.enc_out + tcm_off(b, lg * 2 + 1, 8)) = make_float4(enc[4], enc[5], enc[6], enc[7]);
                 }
             } else {
                 float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
@@ -236,45 +245,57 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
     } else {
         // ===================== MLP warps: thread t <-> TMEM lane t <-> sample row t of the tile =====================
         const uint32_t lane_base = umma::tmem_addr(tmem, warp * 32, 0);
-        const uint32_t sW1 = umma::smem_u32(smem + oW1), sW2 = umma::smem_u32(smem + oW2), sW3 = umma::smem_u32(smem + oW3);
-        const uint32_t sH = umma::smem_u32(smem + oH);
+        // low descriptor halves (K-major: LBO = rows * 16 = next 4-element K chunk)
+        const uint32_t dW1h = umma::desc_lo(umma::smem_u32(smem + oW1), kHid * 16u), dW1l = umma::desc_lo(umma::smem_u32(smem + oW1 + kW1), kHid * 16u);
+        const uint32_t dW2h = umma::desc_lo(umma::smem_u32(smem + oW2), kHid * 16u), dW2l = umma::desc_lo(umma::smem_u32(smem + oW2 + kW2), kHid * 16u);
+        const uint32_t dW3h = umma::desc_lo(umma::smem_u32(smem + oW3), kOut * 16u), dW3l = umma::desc_lo(umma::smem_u32(smem + oW3 + kW3), kOut * 16u);
+        const uint32_t dHh = umma::desc_lo(umma::smem_u32(smem + oH), kTile * 16u), dHl = umma::desc_lo(umma::smem_u32(smem + oH + kH), kTile * 16u);
         uint8_t* h_hi = smem + oH;
         uint8_t* h_lo = h_hi + kH;
         uint32_t mma_phase = 0;
         for (uint32_t it = 0, tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
             const uint32_t slot = it & 1u;
-            if (tid == 0) {
+            if (warp == 0) {              // warp-uniform branch + elected lane: the issue loop stays on the uniform datapath
                 umma::mbar_wait(umma::smem_u32(&s_full[slot]), (it >> 1) & 1u);
-                umma::fence_after_sync();
-                const uint32_t sA = umma::smem_u32(smem + oA1 + slot * 2 * kA1);
-                issue_gemm<kHid, kIn, kHid>(tmem + cD1, sA, sA + kA1, sW1, sW1 + kW1, split);
-                umma::commit(umma::smem_u32(&s_empty[slot]));     // A slot free once layer 1 has consumed it
-                umma::commit(umma::smem_u32(&s_mma));
+                if (umma::elect_one()) {
+                    umma::fence_after_sync();
+                    const uint32_t dAh = umma::desc_lo(umma::smem_u32(smem + oA1 + slot * 2 * kA1), kTile * 16u);
+                    issue_gemm<kHid, kIn, kHid>(tmem + cD1, dAh, dAh + (kA1 >> 4), dW1h, dW1l, split);
+                    umma::commit(umma::smem_u32(&s_empty[slot]));     // A slot free once layer 1 has consumed it
+                    umma::commit(umma::smem_u32(&s_mma));
+                }
+                __syncwarp();
             }
             umma::mbar_wait(umma::smem_u32(&s_mma), mma_phase); mma_phase ^= 1u;
             umma::fence_after_sync();
             const uint32_t b = tile * kTile + tid;
             const bool keep = (p.h1_out != nullptr) && b < p.B;
-            relu_to_smem(lane_base + cD1, h_hi, h_lo, tid, split, keep ? p.h1_out + (size_t)b * kHid : nullptr);
+            relu_to_smem(lane_base + cD1, h_hi, h_lo, tid, split, keep ? p.h1_out : nullptr, b);
             umma::fence_proxy_async();
             umma::fence_before_sync();
             named_bar_sync(1, kMlpWarps * 32);
-            if (tid == 0) {
-                umma::fence_after_sync();
-                issue_gemm<kHid, kHid, kHid>(tmem + cD2, sH, sH + kH, sW2, sW2 + kW2, split);
-                umma::commit(umma::smem_u32(&s_mma));
+            if (warp == 0) {
+                if (umma::elect_one()) {
+                    umma::fence_after_sync();
+                    issue_gemm<kHid, kHid, kHid>(tmem + cD2, dHh, dHl, dW2h, dW2l, split);
+                    umma::commit(umma::smem_u32(&s_mma));
+                }
+                __syncwarp();
             }
             umma::mbar_wait(umma::smem_u32(&s_mma), mma_phase); mma_phase ^= 1u;
             umma::fence_after_sync();
             relu_to_smem(lane_base + cD2, h_hi, h_lo, tid, split,    // layer 2 has completed: H may be overwritten
-                         keep ? p.h2_out + (size_t)b * kHid : nullptr);
+                         keep ? p.h2_out : nullptr, b);
             umma::fence_proxy_async();
             umma::fence_before_sync();
             named_bar_sync(1, kMlpWarps * 32);
-            if (tid == 0) {
-                umma::fence_after_sync();
-                issue_gemm<kOut, kHid, kOut>(tmem + cD3, sH, sH + kH, sW3, sW3 + kW3, split);
-                umma::commit(umma::smem_u32(&s_mma));
+            if (warp == 0) {
+                if (umma::elect_one()) {
+                    umma::fence_after_sync();
+                    issue_gemm<kOut, kHid, kOut>(tmem + cD3, dHh, dHl, dW3h, dW3l, split);
+                    umma::commit(umma::smem_u32(&s_mma));
+                }
+                __syncwarp();
             }
             umma::mbar_wait(umma::smem_u32(&s_mma), mma_phase); mma_phase ^= 1u;
             umma::fence_after_sync();
@@ -309,9 +330,9 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
 //     thread writes its own sample's row with 16-byte stores.
 //   * the three weight gradients accumulate in tensor memory (M = 64 accumulators) over all tiles of the persistent
 //     CTA and are added to HBM once per CTA.
-// Warps 0-3 own the TMEM lanes (thread t <-> sample t of the tile: masks, splits, epilogues); warps 4-7 prefetch the
-// NEXT tile's H1 / H2 / g_out rows into registers while the current tile computes and dump them into shared / tensor
-// memory at the tile boundary.
+// 16 symmetric worker warps: each prefetches its share of the NEXT tile's rows into registers (coalesced,
+// tile-chunk-major saved activations) while the current tile computes, stages them at the tile boundary, and runs the
+// epilogue of one 16-column group of its TMEM lane quadrant; one elected lane of the last warp issues the MMAs.
 namespace head {
 constexpr uint32_t kMn64 = kTile * 128u * 2u;      // one plane of a 64-wide MN-major tile (two 32-wide blocks)
 constexpr uint32_t kMn32 = kTile * 128u;           // one plane of a 32-wide (or padded 16-wide) MN-major tile
@@ -326,7 +347,7 @@ static_assert(oBufA % 1024 == 0 && oBufB % 1024 == 0 && oBufG % 1024 == 0, "swiz
 static_assert(kBwdSmem <= 227 * 1024, "backward tiles exceed shared memory");
 // TMEM columns: A-operand staging (hi, lo), data-gradient accumulator, weight-gradient accumulators (M = 64)
 constexpr uint32_t cAhi = 0, cAlo = 64, cDG = 128, cW2 = 192, cW1 = 256, cW3 = 288, kBwdTmemCols = 512;
-constexpr uint32_t kBwdThreads = 256;
+constexpr uint32_t kBwdThreads = 512;
 }  // namespace head
 
 struct HeadBwdParams {
@@ -390,41 +411,45 @@ __device__ __forceinline__ void put_tmem16(uint32_t lane_base, uint32_t col, con
     if (split) umma::tmem_st16(lane_base + head::cAlo + col, lo);
 }
 
-// D[128, N] = A[tmem: 128 lanes x K columns] . Wt[N, K]^T ; Wt = transposed weight tile (K-major, WT_ROWS = N rows)
+// D[128, N] = A[tmem: 128 lanes x K columns] . Wt[N, K]^T ; Wt = transposed weight tile (K-major, N rows); b_* are low
+// descriptor halves
 template <uint32_t N, uint32_t K>
 __device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t b_hi,
                                               uint32_t b_lo, bool split) {
     constexpr uint32_t idesc = umma::idesc_tf32(128, N, 0, 0);
-    constexpr uint32_t b_lbo = N * 16u;
+    constexpr uint32_t b_step = (2u * N * 16u) >> 4;
+    constexpr uint32_t hi = umma::desc_hi(128u, umma::kLayoutNone);
     uint32_t acc = 0;
 #pragma unroll
     for (uint32_t ks = 0; ks < K / 8; ++ks) {
-        const uint32_t bo = ks * 2u * b_lbo;
+        const uint32_t bo = ks * b_step;
         if (split) {
-            umma::mma_tf32_ts(tmem_d, tmem_a_lo + ks * 8u, umma::smem_desc(b_hi + bo, b_lbo, 128u), idesc, acc);
-            umma::mma_tf32_ts(tmem_d, tmem_a_hi + ks * 8u, umma::smem_desc(b_lo + bo, b_lbo, 128u), idesc, 1u);
+            umma::mma_tf32_ts2(tmem_d, tmem_a_lo + ks * 8u, b_hi + bo, hi, idesc, acc);
+            umma::mma_tf32_ts2(tmem_d, tmem_a_hi + ks * 8u, b_lo + bo, hi, idesc, 1u);
             acc = 1;
         }
-        umma::mma_tf32_ts(tmem_d, tmem_a_hi + ks * 8u, umma::smem_desc(b_hi + bo, b_lbo, 128u), idesc, acc);
+        umma::mma_tf32_ts2(tmem_d, tmem_a_hi + ks * 8u, b_hi + bo, hi, idesc, acc);
         acc = 1;
     }
 }
 
-// D[64, N] (+)= At^T . Bt : MN-major swizzled tiles whose 128 rows are the contraction index
+// D[64, N] (+)= At^T . Bt : MN-major swizzled tiles whose 128 rows are the contraction index (low descriptor halves)
 template <uint32_t N>
 __device__ __forceinline__ void issue_gemm_mn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                               bool split, uint32_t acc) {
     constexpr uint32_t idesc = umma::idesc_tf32(64, N, 1, 1);
     using namespace head;
+    constexpr uint32_t hi = umma::desc_hi(kMnSbo, umma::kLayoutMn32);
+    constexpr uint32_t step = (2u * kMnSbo) >> 4;                 // 8 contraction rows = two 512-byte atoms
 #pragma unroll
     for (uint32_t ks = 0; ks < kTile / 8; ++ks) {
-        const uint32_t o = ks * 2u * kMnSbo;
+        const uint32_t o = ks * step;
         if (split) {
-            umma::mma_tf32(tmem_d, umma::smem_desc_mn32(a_lo + o, kMnLbo, kMnSbo), umma::smem_desc_mn32(b_hi + o, kMnLbo, kMnSbo), idesc, acc);
-            umma::mma_tf32(tmem_d, umma::smem_desc_mn32(a_hi + o, kMnLbo, kMnSbo), umma::smem_desc_mn32(b_lo + o, kMnLbo, kMnSbo), idesc, 1u);
+            umma::mma_tf32_ss2(tmem_d, a_lo + o, hi, b_hi + o, hi, idesc, acc);
+            umma::mma_tf32_ss2(tmem_d, a_hi + o, hi, b_lo + o, hi, idesc, 1u);
             acc = 1;
         }
-        umma::mma_tf32(tmem_d, umma::smem_desc_mn32(a_hi + o, kMnLbo, kMnSbo), umma::smem_desc_mn32(b_hi + o, kMnLbo, kMnSbo), idesc, acc);
+        umma::mma_tf32_ss2(tmem_d, a_hi + o, hi, b_hi + o, hi, idesc, acc);
         acc = 1;
     }
 }
@@ -435,16 +460,31 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
     return v;
 }
 
+// Phase timestamps of CTA 0 (diagnostics; compiled in only with -DSANERF_HEAD_TRACE): [thread 0][tile 0..3][11]
+#ifdef SANERF_HEAD_TRACE
+__device__ long long g_head_trace[2 * 4 * 11];
+#define HEAD_TRACE(slot)                                                                                   \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && it < 4 && (tid == 0 || tid == 128))                                         \
+            g_head_trace[((tid == 0 ? 0 : 1) * 4 + it) * 11 + (slot)] = clock64();                          \
+    } while (0)
+#else
+#define HEAD_TRACE(slot) do {} while (0)
+#endif
+
+// 16 symmetric worker warps.  Warp w serves TMEM lane quadrant q = w & 3 (tile rows 32 q .. 32 q + 31) and, in the
+// epilogues, the 16 accumulator columns 16 (w >> 2) ..; in the staging phases it moves the 8 tile rows 8 w .. 8 w + 7.
+// Every phase therefore runs with four warps per scheduler instead of one.
 __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(const HeadBwdParams p, const uint32_t tiles) {
     using namespace head;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mma;
-    __shared__ __align__(8) uint64_t s_mask[2][kTile];
+    __shared__ __align__(16) uint8_t s_mask[2][kTile][16];     // ReLU sign patterns of H1 / H2: one nibble per 4-feature chunk
     __shared__ uint32_t s_tmem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool split = (p.precision == 0);
-    const bool owner = warp < 4;
-    const uint32_t row = tid & (kTile - 1);                 // sample row of the tile this thread serves
+    const uint32_t q = warp & 3u, cg = warp >> 2;           // TMEM lane quadrant, 16-column group
+    const uint32_t row = q * 32u + lane;                    // tile row of this thread's TMEM lane
     uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
 
     if (warp == 0) umma::tmem_alloc<kBwdTmemCols>(umma::smem_u32(&s_tmem));
@@ -460,9 +500,14 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    const uint32_t lane_base = umma::tmem_addr(tmem, (warp & 3u) * 32u, 0);
-    const uint32_t sT3 = umma::smem_u32(smem + oT3), sT2 = umma::smem_u32(smem + oT2), sT1 = umma::smem_u32(smem + oT1);
-    const uint32_t sA = umma::smem_u32(smem + oBufA), sB = umma::smem_u32(smem + oBufB), sG = umma::smem_u32(smem + oBufG);
+    const uint32_t lane_base = umma::tmem_addr(tmem, q * 32u, 0);
+    // low descriptor halves: transposed weights K-major (LBO = rows * 16), tiles MN-major (LBO = next 32-wide block)
+    const uint32_t dT3h = umma::desc_lo(umma::smem_u32(smem + oT3), kHid * 16u), dT3l = dT3h + (kW3 >> 4);
+    const uint32_t dT2h = umma::desc_lo(umma::smem_u32(smem + oT2), kHid * 16u), dT2l = dT2h + (kW2 >> 4);
+    const uint32_t dT1h = umma::desc_lo(umma::smem_u32(smem + oT1), kIn * 16u), dT1l = dT1h + (kW1 >> 4);
+    const uint32_t dA = umma::desc_lo(umma::smem_u32(smem + oBufA), kMnLbo), dB = umma::desc_lo(umma::smem_u32(smem + oBufB), kMnLbo);
+    const uint32_t dG = umma::desc_lo(umma::smem_u32(smem + oBufG), kMnLbo);
+    const bool issuer = (warp == kBwdThreads / 32 - 1);
     uint8_t* bufA = smem + oBufA;
     uint8_t* bufB = smem + oBufB;
     uint8_t* bufG = smem + oBufG;
@@ -480,158 +525,175 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         __syncthreads();
     };
 
-    // loader registers: the next tile's H2, H1 and g_out rows
-    float4 rh2[16], rh1[16], rg[4];
-    auto prefetch = [&](uint32_t tile) {
-        const uint32_t b = tile * kTile + row;
-        if (tile < tiles && b < p.B) {
-            const float* ph2 = p.h2 + (size_t)b * kHid;
-            const float* ph1 = p.h1 + (size_t)b * kHid;
-            const float* pg = p.g_out + (size_t)b * kOut;
+    // ---- staging registers of this thread: 4 chunks of H2, 4 of H1, 2 of enc, 1 of g_out (any-lane pieces of the tile)
+    // plus, in the warps with cg == 0, this lane's own g_out row for the TMEM A planes.  Loaded one tile ahead.
+    float4 rh2[4], rh1[4], re[2], rg, rgrow[4];
+    // tile-chunk-major pieces: one instruction = one chunk of 32 consecutive rows (512 contiguous bytes)
+    const uint32_t h_c = warp;                                             // H1 / H2: chunk = warp, rows 32 i + lane
+    const uint32_t e_c = warp >> 1, e_row = (warp & 1u) * 64u + lane;      // enc: chunk = warp / 2, rows e_row + 32 i
+    const uint32_t g_row = warp * 8u + (lane >> 2), g_c = lane & 3u;       // g_out (row-major): 8 rows per instruction
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld_tcm = [&](const float* base, uint32_t chunks, uint32_t tile, uint32_t r, uint32_t c) -> float4 {
+        const uint32_t bb = tile * kTile + r;
+        return (tile < tiles && bb < p.B) ? ldg_nc_f4(base + tcm_off(bb, c, chunks)) : zero4;
+    };
+    auto ld_row = [&](const float* base, uint32_t width, uint32_t tile, uint32_t r, uint32_t c) -> float4 {
+        const uint32_t bb = tile * kTile + r;
+        return (tile < tiles && bb < p.B) ? ldg_nc_f4(base + (size_t)bb * width + 4u * c) : zero4;
+    };
+    auto put_mask = [&](uint32_t layer, uint32_t r, uint32_t c, const float4& v) {
+        s_mask[layer][r][c] = (uint8_t)((v.x > 0.f) | ((v.y > 0.f) << 1) | ((v.z > 0.f) << 2) | ((v.w > 0.f) << 3));
+    };
+    auto load_h2_g = [&](uint32_t tile) {
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) rg[j] = ldg_nc_f4(pg + 4 * j);
+        for (uint32_t i = 0; i < 4; ++i) rh2[i] = ld_tcm(p.h2, 16, tile, 32 * i + lane, h_c);
+        rg = ld_row(p.g_out, kOut, tile, g_row, g_c);
+        if (cg == 0) {
 #pragma unroll
-            for (uint32_t j = 0; j < 16; ++j) rh2[j] = ldg_nc_f4(ph2 + 4 * j);
-#pragma unroll
-            for (uint32_t j = 0; j < 16; ++j) rh1[j] = ldg_nc_f4(ph1 + 4 * j);
-        } else {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) rg[j] = z;
-#pragma unroll
-            for (uint32_t j = 0; j < 16; ++j) { rh2[j] = z; rh1[j] = z; }
+            for (uint32_t j = 0; j < 4; ++j) rgrow[j] = ld_row(p.g_out, kOut, tile, row, j);
         }
     };
-    if (!owner) prefetch(blockIdx.x);
+    auto load_h1 = [&](uint32_t tile) {
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) rh1[i] = ld_tcm(p.h1, 16, tile, 32 * i + lane, h_c);
+    };
+    auto load_enc = [&](uint32_t tile) {
+#pragma unroll
+        for (uint32_t i = 0; i < 2; ++i) re[i] = ld_tcm(p.enc, 8, tile, e_row + 32 * i, e_c);
+    };
+    // masked data gradient: accumulator columns 16 cg .. of this thread's row -> TMEM A planes + MN-major tile
+    auto masked_epilogue = [&](uint32_t layer) {
+        const uint32_t c0 = cg * 16u;
+        const uint32_t nib = *reinterpret_cast<const uint32_t*>(&s_mask[layer][row][cg * 4u]);      // 4 chunks = 16 columns
+        const uint32_t bits = (nib & 0xfu) | ((nib >> 4) & 0xf0u) | ((nib >> 8) & 0xf00u) | ((nib >> 12) & 0xf000u);
+        float v[16];
+        umma::tmem_ld16(lane_base + cDG + c0, v);
+#pragma unroll
+        for (uint32_t j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.0f;
+        put_tmem16(lane_base, c0, v, split);
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
+    };
+
+    load_h2_g(blockIdx.x);
+    load_h1(blockIdx.x);
+    load_enc(blockIdx.x);
 
     for (uint32_t it = 0, tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
         const uint32_t first = (it == 0) ? 0u : 1u;
-        const uint32_t b = tile * kTile + row;
-        if (owner) {
-            // this tile's encoding row (kept in the otherwise unused rh1 registers): consumed after step 4, so the load
-            // latency is hidden
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t next = tile + gridDim.x;
+        HEAD_TRACE(0);
+        // ---- stage what step 3 needs: H2 -> bufB (+ sign mask), G3 -> bufG and TMEM A planes
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) rh1[j] = (b < p.B) ? ldg_nc_f4(p.enc + (size_t)b * kIn + 4 * j) : z;
-        } else {
-            // ---- dump the prefetched rows: H2 -> bufB, H1 -> bufA, G3 -> bufG + TMEM A planes; sign masks -> shared
-            uint64_t m1 = 0, m2 = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < 16; ++j) {
-                m2 |= (uint64_t)((rh2[j].x > 0.f) | ((rh2[j].y > 0.f) << 1) | ((rh2[j].z > 0.f) << 2) | ((rh2[j].w > 0.f) << 3)) << (4 * j);
-                m1 |= (uint64_t)((rh1[j].x > 0.f) | ((rh1[j].y > 0.f) << 1) | ((rh1[j].z > 0.f) << 2) | ((rh1[j].w > 0.f) << 3)) << (4 * j);
-                put_mn(bufB, bufB + kMn64, row, 4 * j, rh2[j].x, rh2[j].y, rh2[j].z, rh2[j].w, split);
-                put_mn(bufA, bufA + kMn64, row, 4 * j, rh1[j].x, rh1[j].y, rh1[j].z, rh1[j].w, split);
-            }
-            s_mask[0][row] = m1;
-            s_mask[1][row] = m2;
+        for (uint32_t i = 0; i < 4; ++i) {
+            put_mask(1, 32 * i + lane, h_c, rh2[i]);
+            put_mn(bufB, bufB + kMn64, 32 * i + lane, h_c * 4u, rh2[i].x, rh2[i].y, rh2[i].z, rh2[i].w, split);
+        }
+        put_mn(bufG, bufG + kMn32, g_row, g_c * 4u, rg.x, rg.y, rg.z, rg.w, split);
+        if (cg == 0) {
             float g16[16];
 #pragma unroll
             for (uint32_t j = 0; j < 4; ++j) {
-                put_mn(bufG, bufG + kMn32, row, 4 * j, rg[j].x, rg[j].y, rg[j].z, rg[j].w, split);
-                g16[4 * j] = rg[j].x; g16[4 * j + 1] = rg[j].y; g16[4 * j + 2] = rg[j].z; g16[4 * j + 3] = rg[j].w;
+                g16[4 * j] = rgrow[j].x; g16[4 * j + 1] = rgrow[j].y; g16[4 * j + 2] = rgrow[j].z; g16[4 * j + 3] = rgrow[j].w;
             }
             put_tmem16(lane_base, 0, g16, split);
         }
+        HEAD_TRACE(1);
         publish();
-        if (!owner) prefetch(tile + gridDim.x);
+        HEAD_TRACE(2);
         // ---- 3
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm_ts<kHid, kOut>(tmem + cDG, tmem + cAhi, tmem + cAlo, sT3, sT3 + kW3, split);
-            issue_gemm_mn<kOut>(tmem + cW3, sB, sB + kMn64, sG, sG + kMn32, split, first);
-            umma::commit(umma::smem_u32(&s_mma));
-        }
-        mma_done();
-        if (owner) {
-            const uint64_t mask2 = s_mask[1][row];
-#pragma unroll
-            for (uint32_t c0 = 0; c0 < kHid; c0 += 16) {
-                float v[16];
-                umma::tmem_ld16(lane_base + cDG + c0, v);
-#pragma unroll
-                for (uint32_t j = 0; j < 16; ++j) v[j] = ((mask2 >> (c0 + j)) & 1ull) ? v[j] : 0.0f;
-                put_tmem16(lane_base, c0, v, split);
-#pragma unroll
-                for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
+        if (issuer) {
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                issue_gemm_ts<kHid, kOut>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT3h, dT3l, split);
+                issue_gemm_mn<kOut>(tmem + cW3, dB, dB + (kMn64 >> 4), dG, dG + (kMn32 >> 4), split, first);
+                umma::commit(umma::smem_u32(&s_mma));
             }
+            __syncwarp();
         }
+        // H1 -> bufA is needed by step 4 only: written while step 3 runs on the tensor core; the freed registers are
+        // refilled with the next tile's rows
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            put_mask(0, 32 * i + lane, h_c, rh1[i]);
+            put_mn(bufA, bufA + kMn64, 32 * i + lane, h_c * 4u, rh1[i].x, rh1[i].y, rh1[i].z, rh1[i].w, split);
+        }
+        load_h2_g(next);
+        mma_done();
+        HEAD_TRACE(3);
+        masked_epilogue(1);                                  // G2 = DG2 * [H2 > 0]
+        HEAD_TRACE(4);
         publish();
+        HEAD_TRACE(5);
         // ---- 4
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm_ts<kHid, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, sT2, sT2 + kW2, split);
-            issue_gemm_mn<kHid>(tmem + cW2, sB, sB + kMn64, sA, sA + kMn64, split, first);
-            umma::commit(umma::smem_u32(&s_mma));
-        }
-        mma_done();
-        if (owner) {
-            const uint64_t mask1 = s_mask[0][row];
-#pragma unroll
-            for (uint32_t c0 = 0; c0 < kHid; c0 += 16) {
-                float v[16];
-                umma::tmem_ld16(lane_base + cDG + c0, v);
-#pragma unroll
-                for (uint32_t j = 0; j < 16; ++j) v[j] = ((mask1 >> (c0 + j)) & 1ull) ? v[j] : 0.0f;
-                put_tmem16(lane_base, c0, v, split);
-#pragma unroll
-                for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
+        if (issuer) {
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                issue_gemm_ts<kHid, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT2h, dT2l, split);
+                issue_gemm_mn<kHid>(tmem + cW2, dB, dB + (kMn64 >> 4), dA, dA + (kMn64 >> 4), split, first);
+                umma::commit(umma::smem_u32(&s_mma));
             }
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) put_mn(bufA, bufA + kMn32, row, 4 * j, rh1[j].x, rh1[j].y, rh1[j].z, rh1[j].w, split);
+            __syncwarp();
         }
+        load_h1(next);
+        mma_done();
+        HEAD_TRACE(6);
+        masked_epilogue(0);                                  // G1 = DG1 * [H1 > 0]; step 4 has released bufA and bufB
+#pragma unroll
+        for (uint32_t i = 0; i < 2; ++i)
+            put_mn(bufA, bufA + kMn32, e_row + 32 * i, e_c * 4u, re[i].x, re[i].y, re[i].z, re[i].w, split);
+        HEAD_TRACE(7);
         publish();
+        HEAD_TRACE(8);
         // ---- 5
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm_ts<kIn, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, sT1, sT1 + kW1, split);
-            issue_gemm_mn<kIn>(tmem + cW1, sB, sB + kMn64, sA, sA + kMn32, split, first);
-            umma::commit(umma::smem_u32(&s_mma));
+        if (issuer) {
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                issue_gemm_ts<kIn, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT1h, dT1l, split);
+                issue_gemm_mn<kIn>(tmem + cW1, dB, dB + (kMn64 >> 4), dA, dA + (kMn32 >> 4), split, first);
+                umma::commit(umma::smem_u32(&s_mma));
+            }
+            __syncwarp();
         }
+        load_enc(next);
         mma_done();
-        if (owner) {
+        HEAD_TRACE(9);
+        if (cg < 2) {                                        // g_enc [B,32] row-major: 64 contiguous bytes per thread
+            const uint32_t b = tile * kTile + row;
+            float v[16];
+            umma::tmem_ld16(lane_base + cDG + cg * 16u, v);
+            if (b < p.B) {
+                float4* dst = reinterpret_cast<float4*>(p.g_enc + (size_t)b * kIn + cg * 16u);
 #pragma unroll
-            for (uint32_t c0 = 0; c0 < kIn; c0 += 16) {
-                float v[16];
-                umma::tmem_ld16(lane_base + cDG + c0, v);
-                if (b < p.B) {
-                    float4* dst = reinterpret_cast<float4*>(p.g_enc + (size_t)b * kIn + c0);
-#pragma unroll
-                    for (uint32_t j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
+                for (uint32_t j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
         }
-        // the next tile's dump (other warps) may start at once: every MMA that read bufA / bufB / bufG / the A planes has
-        // completed; this tile's reads of cDG are ordered before the next MMAs by the fence in the next publish()
+        HEAD_TRACE(10);
+        // the next tile's staging may start at once: every MMA that read bufA / bufB / bufG / the A planes has completed;
+        // this tile's reads of cDG are ordered before the next MMAs by the fence in the next publish()
     }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
 
-    // ---- weight gradients: M = 64 accumulators, row (16 w + l) lives in TMEM lane (32 w + l), l < 16
-    if (owner) {
-        const uint32_t wrow = warp * 16 + lane;
+    // ---- weight gradients: M = 64 accumulators, row (16 q + l) lives in TMEM lane (32 q + l), l < 16
+    {
+        const uint32_t wrow = q * 16 + lane;
         const bool owns = lane < 16;
+        float v[16];
+        umma::tmem_ld16(lane_base + cW2 + cg * 16u, v);      // dW2[out=wrow][in = 16 cg ..]
+        if (owns) {
 #pragma unroll
-        for (uint32_t c0 = 0; c0 < kIn; c0 += 16) {          // dW1[out=wrow][in=c]
-            float v[16];
-            umma::tmem_ld16(lane_base + cW1 + c0, v);
+            for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w2 + wrow * kHid + cg * 16u + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (cg < 2) {                                        // dW1[out=wrow][in = 16 cg ..]
+            umma::tmem_ld16(lane_base + cW1 + cg * 16u, v);
             if (owns) {
 #pragma unroll
-                for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w1 + wrow * kIn + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w1 + wrow * kIn + cg * 16u + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
         }
-#pragma unroll
-        for (uint32_t c0 = 0; c0 < kHid; c0 += 16) {         // dW2[out=wrow][in=c]
-            float v[16];
-            umma::tmem_ld16(lane_base + cW2 + c0, v);
-            if (owns) {
-#pragma unroll
-                for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w2 + wrow * kHid + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-        }
-        {                                                    // dW3^T[in=wrow][out=c] -> g_w3[out][in]
-            float v[16];
+        if (cg == 2) {                                       // dW3^T[in=wrow][out=c] -> g_w3[out][in]
             umma::tmem_ld16(lane_base + cW3, v);
             if (owns) {
 #pragma unroll
@@ -669,6 +731,12 @@ extern "C" int sanerf_field_head_forward(const float* x01, const float* table, c
     head_forward_kernel<<<blocks, head::kThreads, head::kFwdSmem, static_cast<cudaStream_t>(stream)>>>(p, tiles);
     return check_launch("head_forward_kernel");
 }
+
+#ifdef SANERF_HEAD_TRACE
+extern "C" __attribute__((visibility("default"))) int sanerf_debug_head_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_head_trace, sizeof(long long) * 2 * 4 * 11) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int sanerf_field_head_backward(const float* enc, const float* h1, const float* h2, const float* g_out,
                                           const float* w1, const float* w2, const float* w3, uint32_t B, float* g_enc,

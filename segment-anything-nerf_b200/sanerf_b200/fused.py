@@ -127,6 +127,26 @@ def prop_density(x01, encoder, mlp):
 PRECISION_IDS = {"fp32": 0, "tf32": 1}
 
 
+# The activations the field-head forward keeps for its backward (encoding, H1, H2) are "tile-chunk-major":
+# [tile of 128 samples][4-element chunk][sample][4], so that both kernels touch 512 contiguous bytes per warp
+# instruction.  They are private to the two kernels; these helpers exist for tests and diagnostics.
+def tcm_rows(B):
+    return (B + 127) // 128 * 128
+
+
+def tcm_to_rows(t, B, W):
+    tiles = t.numel() // (128 * W)
+    return t.view(tiles, W // 4, 128, 4).permute(0, 2, 1, 3).reshape(tiles * 128, W)[:B]
+
+
+def rows_to_tcm(x):
+    B, W = x.shape
+    Bp = tcm_rows(B)
+    pad = x.new_zeros(Bp, W)
+    pad[:B] = x
+    return pad.view(Bp // 128, 128, W // 4, 4).permute(0, 2, 1, 3).contiguous().view(Bp, W)
+
+
 class _FieldHead(Function):
     """out [.., 16] = grid_mlp(grid(x)) in ONE tcgen05 kernel; backward = one tcgen05 kernel (data + weight
     gradients of the MLP) + the hash-grid scatter."""
@@ -138,9 +158,10 @@ class _FieldHead(Function):
         dev = x01.device
         need_grad = any(ctx.needs_input_grad[1:6])
         out = torch.empty(*x01.shape[:-1], 16, device=dev, dtype=torch.float32)
-        enc = torch.empty(B, 32, device=dev, dtype=torch.float32) if need_grad else None
-        h1 = torch.empty(B, 64, device=dev, dtype=torch.float32) if need_grad else None
-        h2 = torch.empty(B, 64, device=dev, dtype=torch.float32) if need_grad else None
+        Bp = tcm_rows(B)                       # saved activations are tile-chunk-major: whole 128-sample tiles
+        enc = torch.empty(Bp, 32, device=dev, dtype=torch.float32) if need_grad else None
+        h1 = torch.empty(Bp, 64, device=dev, dtype=torch.float32) if need_grad else None
+        h2 = torch.empty(Bp, 64, device=dev, dtype=torch.float32) if need_grad else None
         w1, w2, w3 = w1.contiguous(), w2.contiguous(), w3.contiguous()
         lib = _lib.load()
         with torch.cuda.device(dev), _lib.stats.span("field_head_forward", B=B):

@@ -71,8 +71,9 @@ class FusedRGBStep:
         B = N * self.steps[2]
         self.head = torch.empty(B, 16, **f32)
         self.g_head = torch.empty(B, 16, **f32)
-        self.enc, self.g_enc = torch.empty(B, 32, **f32), torch.empty(B, 32, **f32)
-        self.h1, self.h2 = torch.empty(B, 64, **f32), torch.empty(B, 64, **f32)
+        Bp = (B + 127) // 128 * 128             # saved activations are tile-chunk-major (fused.tcm_rows)
+        self.enc, self.g_enc = torch.empty(Bp, 32, **f32), torch.empty(B, 32, **f32)
+        self.h1, self.h2 = torch.empty(Bp, 64, **f32), torch.empty(Bp, 64, **f32)
         self.geo_sum, self.g_geo_sum = torch.empty(N, 15, **f32), torch.empty(N, 15, **f32)
         self.g_ws = torch.empty(N, **f32)
         self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)

@@ -74,19 +74,23 @@ def _head_setup(B, seed=0, table_scale=1.0):
 def _head_call(x01, enc, w1, w2, w3, precision, enc_in=None, want_enc=True, want_hidden=False):
     import numpy as np
     lib = _lib.load()
+    from sanerf_b200.fused import tcm_rows, tcm_to_rows
     B = x01.shape[0] if x01 is not None else enc_in.shape[0]
+    Bp = tcm_rows(B)                           # saved activations: tile-chunk-major, whole tiles
     out = torch.full((B, 16), float("nan"), device="cuda")
-    enc_out = torch.full((B, 32), float("nan"), device="cuda") if want_enc else None
-    h1 = torch.full((B, 64), float("nan"), device="cuda") if want_hidden else None
-    h2 = torch.full((B, 64), float("nan"), device="cuda") if want_hidden else None
+    enc_out = torch.full((Bp, 32), float("nan"), device="cuda") if want_enc else None
+    h1 = torch.full((Bp, 64), float("nan"), device="cuda") if want_hidden else None
+    h2 = torch.full((Bp, 64), float("nan"), device="cuda") if want_hidden else None
     rc = lib.sanerf_field_head_forward(_lib.ptr(x01), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
                                        float(np.log2(enc.per_level_scale)), int(enc.base_resolution), _lib.ptr(enc_in),
                                        w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, _lib.ptr(enc_out), _lib.ptr(h1),
                                        _lib.ptr(h2), out.data_ptr(), precision, _lib.current_stream(out.device))
     _lib.check(rc, "field_head_forward")
     torch.cuda.synchronize()
+    if want_enc:
+        enc_out = tcm_to_rows(enc_out, B, 32)
     if want_hidden:
-        return out, enc_out, h1, h2
+        return out, enc_out, h1, h2          # h1 / h2 stay in the kernels' private layout
     return out, enc_out
 
 
@@ -126,6 +130,9 @@ def test_field_head_backward_matches_autograd(cuda, B):
     W1, W2, W3 = (w.detach().double() for w in (w1, w2, w3))
     h1_ref = torch.relu(e.double() @ W1.t())
     h2_ref = torch.relu(h1_ref @ W2.t())
+    from sanerf_b200.fused import rows_to_tcm, tcm_to_rows
+    h1_tcm, h2_tcm, e_tcm = h1, h2, rows_to_tcm(e)
+    h1, h2 = tcm_to_rows(h1_tcm, B, 64), tcm_to_rows(h2_tcm, B, 64)
     assert ((h1.double() - h1_ref).abs().max() / h1_ref.abs().max()).item() < 2e-6
     assert ((h2.double() - h2_ref).abs().max() / h2_ref.abs().max()).item() < 3e-6
     # fp64 backward THROUGH THE SAME ReLU sign pattern (a pre-activation within rounding of zero may legitimately
@@ -137,7 +144,7 @@ def test_field_head_backward_matches_autograd(cuda, B):
     for precision, tol_e, tol_w in ((0, 5e-6, 1e-5), (1, 5e-3, 5e-3)):
         g_enc = torch.full((B, 32), float("nan"), device="cuda")
         gw = [torch.zeros_like(w) for w in (w1, w2, w3)]
-        rc = lib.sanerf_field_head_backward(e.data_ptr(), h1.data_ptr(), h2.data_ptr(), g_out.data_ptr(), w1.data_ptr(),
+        rc = lib.sanerf_field_head_backward(e_tcm.data_ptr(), h1_tcm.data_ptr(), h2_tcm.data_ptr(), g_out.data_ptr(), w1.data_ptr(),
                                             w2.data_ptr(), w3.data_ptr(), B, g_enc.data_ptr(), gw[0].data_ptr(),
                                             gw[1].data_ptr(), gw[2].data_ptr(), precision, _lib.current_stream(e.device))
         _lib.check(rc, "field_head_backward")

@@ -13,7 +13,8 @@ e64 = e.double().requires_grad_(True)
 ws = [w.double().requires_grad_(True) for w in (w1, w2, w3)]
 h1r = torch.relu(e64 @ ws[0].t()); h2r = torch.relu(h1r @ ws[1].t()); o = h2r @ ws[2].t()
 (o * g_out.double()).sum().backward()
-h1 = h1r.detach().float().contiguous(); h2 = h2r.detach().float().contiguous()
+from sanerf_b200.fused import rows_to_tcm
+h1 = rows_to_tcm(h1r.detach().float().contiguous()); h2 = rows_to_tcm(h2r.detach().float().contiguous()); e_rows = e; e = rows_to_tcm(e)
 for prec in (0, 1):
     g_enc = torch.full((B, 32), float("nan"), device="cuda")
     gw = [torch.zeros_like(w) for w in (w1, w2, w3)]

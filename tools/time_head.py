@@ -12,7 +12,8 @@ torch.manual_seed(0)
 enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19, desired_resolution=4096).cuda()
 w1 = (torch.randn(64, 32) / 32 ** 0.5).cuda(); w2 = (torch.randn(64, 64) / 8).cuda(); w3 = (torch.randn(16, 64) / 8).cuda()
 x01 = torch.rand(B, 3, device="cuda")
-out = torch.empty(B, 16, device="cuda"); e = torch.empty(B, 32, device="cuda"); h1 = torch.empty(B, 64, device="cuda"); h2 = torch.empty(B, 64, device="cuda")
+out = torch.empty(B, 16, device="cuda"); Bp = (B + 127) // 128 * 128
+e = torch.empty(Bp, 32, device="cuda"); h1 = torch.empty(Bp, 64, device="cuda"); h2 = torch.empty(Bp, 64, device="cuda")
 g_out = torch.randn(B, 16, device="cuda"); g_enc = torch.empty(B, 32, device="cuda")
 gw = [torch.zeros_like(w) for w in (w1, w2, w3)]
 flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
