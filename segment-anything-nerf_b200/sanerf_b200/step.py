@@ -8,7 +8,8 @@ underneath), but without autograd, without torch glue kernels and without per-la
   level 2:    sample -> field head (gather + 3-layer MLP on tcgen05) -> trunc_exp -> composite of the 15 geometry channels
               -> view head (SH, view MLP, sigmoid, background, MSE; forward AND backward in one kernel)
   losses:     proposal loss (2 levels) and distortion loss, each returning its gradient, pre-multiplied by lambda
-  backward:   composite -> trunc_exp -> field head (tcgen05) -> hash-grid scatter; composite -> proposal density (x2)
+  backward:   composite -> trunc_exp -> field head (tcgen05) -> hash-grid scatter
+              || (forked stream / parallel graph branch) proposal losses -> composite -> proposal density (x2)
   update:     [NCCL all-reduce of the flat gradient bucket when world_size > 1] -> fused Adam (clears the gradient)
 
 Every gradient kernel accumulates straight into the views of ``FusedAdam.flat_grad`` (pre-zeroed by the optimizer
@@ -79,6 +80,7 @@ class FusedRGBStep:
         self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)
         self.image = torch.empty(N, 3, **f32)
         self.loss = torch.zeros(1, **f32)
+        self.side_stream = torch.cuda.Stream(dev)
         self.graphs = {}
         self.eager_runs = {}
         self.global_step = 0
@@ -155,6 +157,42 @@ class FusedRGBStep:
                                               L["weights"].data_ptr(), L["ws"].data_ptr(), L["depth"].data_ptr(),
                                               self.geo_sum.data_ptr(), self.n_alive.data_ptr(), st)
         check(rc, "composite_forward")
+        # ---------------- fork: the proposal branch (proposal losses -> composite backward -> proposal-density backward of
+        # both levels) depends only on the three weight tensors and shares nothing with the final-level chain below except
+        # the loss scalar (atomic adds), so it runs on a second stream / as a parallel branch of the captured graph
+        main = torch.cuda.current_stream(self.dev)
+        if lam_p > 0:
+            side = self.side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                st2 = _lib.current_stream(self.dev)
+                for li in (0, 1):
+                    P = self.lv[li]
+                    with span("proposal_loss", N=N, Tp=P["T"]):
+                        rc = lib.sanerf_proposal_loss(L["bins"].data_ptr(), L["weights"].data_ptr(), T, P["bins"].data_ptr(),
+                                                      P["weights"].data_ptr(), P["T"], N, lam_p, self.loss.data_ptr(),
+                                                      P["g_weights"].data_ptr(), st2)
+                    check(rc, "proposal_loss")
+                for li in (1, 0):
+                    P = self.lv[li]
+                    Tp = P["T"]
+                    enc, mlp = m.prop_encoders[li], m.prop_mlp[li]
+                    with span("composite_backward", N=N, T=Tp, C=0):
+                        rc = lib.sanerf_composite_backward(P["sigma"].data_ptr(), P["deltas"].data_ptr(), P["t_mid"].data_ptr(),
+                                                           None, 0, None, N, Tp, 0, self.opaque, 0.0, P["weights"].data_ptr(),
+                                                           P["g_weights"].data_ptr(), None, None, None, P["g_sigma"].data_ptr(),
+                                                           None, 0, st2)
+                    check(rc, "composite_backward")
+                    with span("prop_density_backward", B=N * Tp, L=enc.num_levels):
+                        rc = lib.sanerf_prop_density_backward(P["x01"].data_ptr(), enc.embeddings.data_ptr(),
+                                                              enc.offsets.data_ptr(), mlp.net[0].weight.data_ptr(),
+                                                              mlp.net[1].weight.data_ptr(), N * Tp, enc.num_levels,
+                                                              float(np.log2(enc.per_level_scale)), int(enc.base_resolution),
+                                                              P["enc"].data_ptr(), P["g_sigma"].data_ptr(),
+                                                              enc.embeddings.grad.data_ptr(), mlp.net[0].weight.grad.data_ptr(),
+                                                              mlp.net[1].weight.grad.data_ptr(), st2)
+                    check(rc, "prop_density_backward")
+        # ---------------- final level: view head + photometric loss (forward and backward), distortion loss
         v1, v2, v3 = (l.weight for l in m.view_mlp.net)
         with span("view_head", N=N):
             rc = lib.sanerf_view_head(self.geo_sum.data_ptr(), L["ws"].data_ptr(), d, self.gt.data_ptr(), v1.data_ptr(),
@@ -162,15 +200,6 @@ class FusedRGBStep:
                                       self.g_geo_sum.data_ptr(), self.g_ws.data_ptr(), v1.grad.data_ptr(), v2.grad.data_ptr(),
                                       v3.grad.data_ptr(), st)
         check(rc, "view_head")
-        # ---------------- sampling regularisers: loss + d loss / d weights, pre-multiplied by lambda
-        if lam_p > 0:
-            for li in (0, 1):
-                P = self.lv[li]
-                with span("proposal_loss", N=N, Tp=P["T"]):
-                    rc = lib.sanerf_proposal_loss(L["bins"].data_ptr(), L["weights"].data_ptr(), T, P["bins"].data_ptr(),
-                                                  P["weights"].data_ptr(), P["T"], N, lam_p, self.loss.data_ptr(),
-                                                  P["g_weights"].data_ptr(), st)
-                check(rc, "proposal_loss")
         have_gw2 = lam_d > 0
         if have_gw2:
             with span("distortion_loss", N=N, T=T):
@@ -198,26 +227,8 @@ class FusedRGBStep:
                                                  g.offsets.data_ptr(), g.embeddings.grad.data_ptr(), B, 3, 2, 16, 16, S, H, None,
                                                  None, 0, 0, 0, _lib.SANERF_F32, _lib.LAYOUT_BLC, st)
         check(rc, "grid_encode_backward")
-        # ---------------- backward: proposal levels (their only gradient source is the proposal loss)
         if lam_p > 0:
-            for li in (1, 0):
-                P = self.lv[li]
-                Tp = P["T"]
-                enc, mlp = m.prop_encoders[li], m.prop_mlp[li]
-                with span("composite_backward", N=N, T=Tp, C=0):
-                    rc = lib.sanerf_composite_backward(P["sigma"].data_ptr(), P["deltas"].data_ptr(), P["t_mid"].data_ptr(), None, 0,
-                                                       None, N, Tp, 0, self.opaque, 0.0, P["weights"].data_ptr(),
-                                                       P["g_weights"].data_ptr(), None, None, None, P["g_sigma"].data_ptr(), None,
-                                                       0, st)
-                check(rc, "composite_backward")
-                with span("prop_density_backward", B=N * Tp, L=enc.num_levels):
-                    rc = lib.sanerf_prop_density_backward(P["x01"].data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
-                                                          mlp.net[0].weight.data_ptr(), mlp.net[1].weight.data_ptr(), N * Tp,
-                                                          enc.num_levels, float(np.log2(enc.per_level_scale)),
-                                                          int(enc.base_resolution), P["enc"].data_ptr(), P["g_sigma"].data_ptr(),
-                                                          enc.embeddings.grad.data_ptr(), mlp.net[0].weight.grad.data_ptr(),
-                                                          mlp.net[1].weight.grad.data_ptr(), st)
-                check(rc, "prop_density_backward")
+            main.wait_stream(self.side_stream)            # join
 
     def _update(self):
         if self.world_size > 1:
