@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 9
+#define SANERF_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -176,6 +176,21 @@ SANERF_API int sanerf_composite_backward(const float* sigmas, const float* delta
                               const float* g_weights_sum, const float* g_depth, const float* g_out,
                               float* grad_sigmas, float* grad_feats, uint32_t grad_feat_stride,
                               void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Final-level density activation + compositing of the field head's [N*T, 16] output in one kernel per direction:
+ * column 0 = density logit -> sigma = exp(.) (activation.py:5-18), columns 1..15 = geometry feature composited with the
+ * weights of renderer.py:309-338.  Dense rays only (T samples each).  sigma (out, [N*T]) and n_alive may be NULL.
+ * Backward: incoming g_weights [N*T], g_weights_sum [N], g_depth [N], g_out [N,15], g_sigma_direct [N*T] (any may be
+ * NULL = zero); writes the whole 16-wide gradient row g_head [N*T,16] (column 0 through trunc_exp's clamped derivative).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_head_composite_forward(const float* head, const float* deltas, const float* ts, uint32_t N,
+                                  uint32_t T, int last_sample_opaque, float t_thresh, float* sigma, float* weights,
+                                  float* weights_sum, float* depth, float* out, int32_t* n_alive, void* stream);
+SANERF_API int sanerf_head_composite_backward(const float* head, const float* deltas, const float* ts, uint32_t N,
+                                   uint32_t T, int last_sample_opaque, float t_thresh, const float* g_weights,
+                                   const float* g_weights_sum, const float* g_depth, const float* g_out,
+                                   const float* g_sigma_direct, float* g_head, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Proposal sampling chain, one kernel per level (nerf/renderer.py:122-139 near/far, :250-253 spacing,

@@ -237,6 +237,17 @@ class _HeadComposite(Function):
         n_alive = torch.empty(N, device=dev, dtype=torch.int32)
         lib = _lib.load()
         st = _stream(f)
+        ctx.save_for_backward(f, sigma, deltas, ts, weights)
+        ctx.meta = (N, T, W, bool(last_sample_opaque), float(t_thresh))
+        ctx.mark_non_differentiable(n_alive)
+        if W == 16:        # the reference's head (1 logit + 15 features): one kernel, a lane owns a sample's whole row
+            with torch.cuda.device(dev), _lib.stats.span("head_composite_forward", N=N, T=T):
+                rc = lib.sanerf_head_composite_forward(f.data_ptr(), deltas.data_ptr(), ts.data_ptr(), N, T,
+                                                       int(bool(last_sample_opaque)), float(t_thresh), sigma.data_ptr(),
+                                                       weights.data_ptr(), weights_sum.data_ptr(), depth.data_ptr(),
+                                                       out.data_ptr(), n_alive.data_ptr(), st)
+            _lib.check(rc, "head_composite_forward")
+            return sigma, weights, weights_sum, depth, out, n_alive
         with torch.cuda.device(dev):
             with _lib.stats.span("trunc_exp_forward", n=N * T):
                 rc = lib.sanerf_trunc_exp_forward(f.data_ptr(), sigma.data_ptr(), N * T, W, 0, st)
@@ -247,9 +258,6 @@ class _HeadComposite(Function):
                                                   float(t_thresh), weights.data_ptr(), weights_sum.data_ptr(),
                                                   depth.data_ptr(), out.data_ptr(), n_alive.data_ptr(), st)
             _lib.check(rc, "composite_forward")
-        ctx.save_for_backward(f, sigma, deltas, ts, weights)
-        ctx.meta = (N, T, W, bool(last_sample_opaque), float(t_thresh))
-        ctx.mark_non_differentiable(n_alive)
         return sigma, weights, weights_sum, depth, out, n_alive
 
     @staticmethod
@@ -261,9 +269,17 @@ class _HeadComposite(Function):
         cont = lambda t: None if t is None else t.contiguous()  # noqa: E731
         g_weights, g_weights_sum, g_depth, g_out = cont(g_weights), cont(g_weights_sum), cont(g_depth), cont(g_out)
         grad_f = torch.empty_like(f)
-        grad_sigma = torch.empty(N, T, device=dev)
         lib = _lib.load()
         st = _stream(f)
+        if W == 16:
+            with torch.cuda.device(dev), _lib.stats.span("head_composite_backward", N=N, T=T):
+                rc = lib.sanerf_head_composite_backward(f.data_ptr(), deltas.data_ptr(), ts.data_ptr(), N, T, int(opaque),
+                                                        t_thresh, _lib.ptr(g_weights), _lib.ptr(g_weights_sum),
+                                                        _lib.ptr(g_depth), _lib.ptr(g_out), _lib.ptr(cont(g_sigma_direct)),
+                                                        grad_f.data_ptr(), st)
+            _lib.check(rc, "head_composite_backward")
+            return grad_f, None, None, None, None
+        grad_sigma = torch.empty(N, T, device=dev)
         with torch.cuda.device(dev):
             with _lib.stats.span("composite_backward", N=N, T=T, C=C):
                 rc = lib.sanerf_composite_backward(sigma.data_ptr(), deltas.data_ptr(), ts.data_ptr(), f.data_ptr() + 4,

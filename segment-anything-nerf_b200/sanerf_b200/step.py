@@ -5,10 +5,10 @@ Same computation as ``RGBTrainer.loss(...).backward(); optimizer.step()`` (the r
 underneath), but without autograd, without torch glue kernels and without per-launch CPU work:
 
   level 0/1:  sample -> proposal density (encode + MLP + trunc_exp, one kernel) -> weights (composite, C = 0)
-  level 2:    sample -> field head (gather + 3-layer MLP on tcgen05) -> trunc_exp -> composite of the 15 geometry channels
+  level 2:    sample -> field head (gather + 3-layer MLP on tcgen05) -> trunc_exp + composite of the 15 geometry channels
               -> view head (SH, view MLP, sigmoid, background, MSE; forward AND backward in one kernel)
   losses:     proposal loss (2 levels) and distortion loss, each returning its gradient, pre-multiplied by lambda
-  backward:   composite -> trunc_exp -> field head (tcgen05) -> hash-grid scatter
+  backward:   composite + trunc_exp -> field head (tcgen05) -> hash-grid scatter
               || (forked stream / parallel graph branch) proposal losses -> composite -> proposal density (x2)
   update:     [NCCL all-reduce of the flat gradient bucket when world_size > 1] -> fused Adam (clears the gradient)
 
@@ -148,15 +148,12 @@ class FusedRGBStep:
                                                w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, self.enc.data_ptr(),
                                                self.h1.data_ptr(), self.h2.data_ptr(), self.head.data_ptr(), self.precision, st)
         check(rc, "field_head_forward")
-        with span("trunc_exp_forward", n=B):
-            rc = lib.sanerf_trunc_exp_forward(self.head.data_ptr(), L["sigma"].data_ptr(), B, 16, 0, st)
-        check(rc, "trunc_exp_forward")
-        with span("composite_forward", N=N, T=T, C=15):
-            rc = lib.sanerf_composite_forward(L["sigma"].data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(),
-                                              self.head.data_ptr() + 4, 16, None, N, T, 15, self.opaque, float(m.t_thresh),
-                                              L["weights"].data_ptr(), L["ws"].data_ptr(), L["depth"].data_ptr(),
-                                              self.geo_sum.data_ptr(), self.n_alive.data_ptr(), st)
-        check(rc, "composite_forward")
+        with span("head_composite_forward", N=N, T=T):
+            rc = lib.sanerf_head_composite_forward(self.head.data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), N, T,
+                                                   self.opaque, float(m.t_thresh), None, L["weights"].data_ptr(),
+                                                   L["ws"].data_ptr(), L["depth"].data_ptr(), self.geo_sum.data_ptr(),
+                                                   self.n_alive.data_ptr(), st)
+        check(rc, "head_composite_forward")
         # ---------------- fork: the proposal branch (proposal losses -> composite backward -> proposal-density backward of
         # both levels) depends only on the three weight tensors and shares nothing with the final-level chain below except
         # the loss scalar (atomic adds), so it runs on a second stream / as a parallel branch of the captured graph
@@ -207,16 +204,12 @@ class FusedRGBStep:
                                                 L["g_weights"].data_ptr(), st)
             check(rc, "distortion_loss")
         # ---------------- backward: final level
-        with span("composite_backward", N=N, T=T, C=15):
-            rc = lib.sanerf_composite_backward(L["sigma"].data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(),
-                                               self.head.data_ptr() + 4, 16, None, N, T, 15, self.opaque, float(m.t_thresh),
-                                               L["weights"].data_ptr(), L["g_weights"].data_ptr() if have_gw2 else None,
-                                               self.g_ws.data_ptr(), None, self.g_geo_sum.data_ptr(), L["g_sigma"].data_ptr(),
-                                               self.g_head.data_ptr() + 4, 16, st)
-        check(rc, "composite_backward")
-        with span("trunc_exp_backward", n=B):
-            rc = lib.sanerf_trunc_exp_backward(L["g_sigma"].data_ptr(), self.head.data_ptr(), self.g_head.data_ptr(), B, 16, 0, st)
-        check(rc, "trunc_exp_backward")
+        with span("head_composite_backward", N=N, T=T):
+            rc = lib.sanerf_head_composite_backward(self.head.data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), N, T,
+                                                    self.opaque, float(m.t_thresh),
+                                                    L["g_weights"].data_ptr() if have_gw2 else None, self.g_ws.data_ptr(),
+                                                    None, self.g_geo_sum.data_ptr(), None, self.g_head.data_ptr(), st)
+        check(rc, "head_composite_backward")
         with span("field_head_backward", B=B):
             rc = lib.sanerf_field_head_backward(self.enc.data_ptr(), self.h1.data_ptr(), self.h2.data_ptr(), self.g_head.data_ptr(),
                                                 w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, self.g_enc.data_ptr(),

@@ -140,23 +140,26 @@ def test_prop_density_forward_backward(cuda):
     torch.testing.assert_close(sig.detach().cpu(), exp.detach(), rtol=1e-3, atol=1e-6)
 
 
-def test_head_composite_equals_separate_ops(cuda):
+@pytest.mark.parametrize("T,t_thresh", [(32, 0.0), (70, 0.0), (32, 1e-2), (9, 0.0)])
+def test_head_composite_equals_separate_ops(cuda, T, t_thresh):
+    """W = 16 runs the fused lane-per-sample kernels (csrc/head_composite.cu); trunc_exp + composite are the checker."""
     from activation import trunc_exp
-    N, T = 200, 32
+    N = 200
     g = torch.Generator(device="cuda").manual_seed(1)
     f = torch.randn(N, T, 16, device="cuda", generator=g).requires_grad_(True)
     bins = torch.sort(torch.rand(N, T + 1, device="cuda", generator=g), -1).values * 5 + 0.2
     deltas, ts = bins[:, 1:] - bins[:, :-1], (bins[:, 1:] + bins[:, :-1]) / 2
-    sig, w, ws, dp, out, alive = fused.head_composite(f, deltas, ts, True, 0.0)
+    sig, w, ws, dp, out, alive = fused.head_composite(f, deltas, ts, True, t_thresh)
     f2 = f.detach().clone().requires_grad_(True)
     sig2 = trunc_exp(f2[..., 0])
-    w2, ws2, dp2, out2, _ = composite(sig2, deltas, ts, f2[..., 1:].contiguous())
+    w2, ws2, dp2, out2, alive2 = composite(sig2, deltas, ts, f2[..., 1:].contiguous(), t_thresh=t_thresh)
+    assert torch.equal(alive, alive2)
     for a, b in ((sig, sig2), (w, w2), (ws, ws2), (dp, dp2), (out, out2)):
-        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
     go, gw = torch.randn(N, 15, device="cuda", generator=g), torch.randn(N, T, device="cuda", generator=g)
     ((out * go).sum() + (w * gw).sum() + dp.sum() + (sig * 0.1).sum()).backward()
     ((out2 * go).sum() + (w2 * gw).sum() + dp2.sum() + (sig2 * 0.1).sum()).backward()
-    torch.testing.assert_close(f.grad, f2.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(f.grad, f2.grad, rtol=1e-4, atol=1e-5)   # suffix = total - prefix vs a reverse scan
 
 
 def test_losses_vs_oracle(cuda):
