@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 10
+#define SANERF_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -278,7 +278,10 @@ SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
  *  h1_out / h2_out f32 [ceil(B/128)*128, 64] or both NULL: the post-ReLU activations of layers 1 and 2 (same layout).
  * Backward: from enc [B,32], h1, h2 [B,64] and g_out [B,16] produces g_enc [B,32] (feed it to
  * sanerf_grid_encode_backward, layout [B,L*C]) and ACCUMULATES the weight gradients into g_w1 / g_w2 / g_w3
- * (caller zero-fills).  Data gradients: A operand in tensor memory x transposed weight; weight gradients: MN-major
+ * (caller zero-fills).  With x01 / offsets / g_table given (x01 != NULL) the hash-grid scatter of
+ * sanerf_grid_encode_backward is FUSED into the kernel's last epilogue: the gradient of the encoding goes from tensor
+ * memory straight into red.global.add.v2.f32 on g_table [rows,2] (warp-aggregated; g_enc may then be NULL and is not
+ * written).  Data gradients: A operand in tensor memory x transposed weight; weight gradients: MN-major
  * operands in the 128-byte-swizzle / 32-byte-atom layout, accumulated in tensor memory over the CTA's tiles.
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_field_head_forward(const float* x01, const float* table, const int32_t* offsets, float S,
@@ -287,6 +290,7 @@ SANERF_API int sanerf_field_head_forward(const float* x01, const float* table, c
                               void* stream);
 SANERF_API int sanerf_field_head_backward(const float* enc, const float* h1, const float* h2, const float* g_out,
                                const float* w1, const float* w2, const float* w3, uint32_t B, float* g_enc,
+                               const float* x01, const int32_t* offsets, float S, uint32_t H, float* g_table,
                                float* g_w1, float* g_w2, float* g_w3, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -81,12 +81,32 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams 
             if (!contributes) key[0] = 0xffffffffu - lane;       // a key no cell has: its own (skipped) run
             const bool head = warp_run_reduce<(1u << D) * CH, D>(v, key, lane);
             if (head && contributes) {
+                if constexpr (CH == 2) {
+                    // The two corners along the first dimension are adjacent rows whenever the lower one is even
+                    // (dense levels: stride 1; hashed levels: prime 1, so x ^ h and (x + 1) ^ h differ in bit 0 only):
+                    // then both fit ONE 16-byte-aligned slot and go out as one red.global.add.v4.f32 - the scatter is
+                    // bound by the number of reduction requests an SM can inject, not by their payload.
 #pragma unroll
-                for (uint32_t k = 0; k < (1u << D); ++k) {
-                    float upd[CH];
+                    for (uint32_t k = 0; k < (1u << D); k += 2) {
+                        const uint32_t r0 = corner_row<D>(geo, cell, k), r1 = corner_row<D>(geo, cell, k + 1);
+                        if ((r0 ^ r1) == 1u) {
+                            const bool lo_first = r0 < r1;
+                            float* dst = reinterpret_cast<float*>(slice) + (size_t)(lo_first ? r0 : r1) * 2;
+                            red_add_v4_f32(dst, lo_first ? v[2 * k] : v[2 * k + 2], lo_first ? v[2 * k + 1] : v[2 * k + 3],
+                                           lo_first ? v[2 * k + 2] : v[2 * k], lo_first ? v[2 * k + 3] : v[2 * k + 1]);
+                        } else {
+                            red_add_v2_f32(reinterpret_cast<float*>(slice) + (size_t)r0 * 2, v[2 * k], v[2 * k + 1]);
+                            red_add_v2_f32(reinterpret_cast<float*>(slice) + (size_t)r1 * 2, v[2 * k + 2], v[2 * k + 3]);
+                        }
+                    }
+                } else {
 #pragma unroll
-                    for (uint32_t c = 0; c < CH; ++c) upd[c] = v[k * CH + c];
-                    RowIO<T, CH>::red(slice + (size_t)corner_row<D>(geo, cell, k) * C, upd);
+                    for (uint32_t k = 0; k < (1u << D); ++k) {
+                        float upd[CH];
+#pragma unroll
+                        for (uint32_t c = 0; c < CH; ++c) upd[c] = v[k * CH + c];
+                        RowIO<T, CH>::red(slice + (size_t)corner_row<D>(geo, cell, k) * C, upd);
+                    }
                 }
             }
         } else {

@@ -346,7 +346,8 @@ constexpr uint32_t kBwdSmem = oBufG + 2 * kMn32 + 1024;     // + slack to align 
 static_assert(oBufA % 1024 == 0 && oBufB % 1024 == 0 && oBufG % 1024 == 0, "swizzled tiles need aligned bases");
 static_assert(kBwdSmem <= 227 * 1024, "backward tiles exceed shared memory");
 // TMEM columns: A-operand staging (hi, lo), data-gradient accumulator, weight-gradient accumulators (M = 64)
-constexpr uint32_t cAhi = 0, cAlo = 64, cDG = 128, cW2 = 192, cW1 = 256, cW3 = 288, kBwdTmemCols = 512;
+constexpr uint32_t cAhi = 0, cAlo = 64, cDG = 128, cW2 = 192, cW1 = 256, cW3 = 288, cDGE = 304 /* two 32-column buffers */,
+                   kBwdTmemCols = 512;
 constexpr uint32_t kBwdThreads = 512;
 }  // namespace head
 
@@ -358,7 +359,13 @@ struct HeadBwdParams {
     const float* w1;
     const float* w2;
     const float* w3;
-    float* g_enc;         // [B,32]
+    float* g_enc;         // [B,32] or NULL
+    // fused hash-grid scatter (all NULL / 0: g_enc is written instead)
+    const float* x01;        // [B,3]
+    const int32_t* offsets;  // [17]
+    float* g_table;          // [rows,2] accumulated
+    float S;
+    uint32_t H;
     float* g_w1;          // [64,32] accumulated
     float* g_w2;          // [64,64]
     float* g_w3;          // [16,64]
@@ -472,6 +479,37 @@ __device__ long long g_head_trace[2 * 4 * 11];
 #define HEAD_TRACE(slot) do {} while (0)
 #endif
 
+// Hash-grid scatter of ONE level for this thread's sample, fused into the backward (replaces the matching slice of
+// sanerf_grid_encode_backward): the two gradient values come straight from tensor memory, consecutive lanes that share
+// a cell are merged first (grid_common.cuh: warp_run_reduce), the run heads issue the eight red.global.add.v2.f32.
+__device__ __noinline__ void scatter_level(const float* __restrict__ x01, float* __restrict__ g_table, const LevelGeom<3> geo,
+                                           uint32_t base_row, uint32_t taddr, uint32_t b, uint32_t B, uint32_t lane) {
+    float g0, g1;
+    umma::tmem_ld2(taddr, g0, g1);
+    float x[3] = {0.5f, 0.5f, 0.5f};
+    const bool live = b < B;
+    if (live) {
+#pragma unroll
+        for (uint32_t d = 0; d < 3; ++d) x[d] = __ldg(x01 + (size_t)b * 3 + d);
+    }
+    const bool contributes = live && !out_of_range<3>(x) && (g0 != 0.0f || g1 != 0.0f);
+    const Cell<3> cell = locate<3>(geo, x, false, 0u);
+    float v[16];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) {
+        const float w = contributes ? corner_weight<3>(cell, k) : 0.0f;
+        v[2 * k] = w * g0;
+        v[2 * k + 1] = w * g1;
+    }
+    const uint32_t key[3] = {contributes ? cell.lo[0] : 0xffffffffu - lane, cell.lo[1], cell.lo[2]};
+    const bool head_lane = warp_run_reduce<16, 3>(v, key, lane);
+    if (head_lane && contributes) {
+        float* slice = g_table + (size_t)base_row * 2;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) red_add_v2_f32(slice + (size_t)corner_row<3>(geo, cell, k) * 2, v[2 * k], v[2 * k + 1]);
+    }
+}
+
 // 16 symmetric worker warps.  Warp w serves TMEM lane quadrant q = w & 3 (tile rows 32 q .. 32 q + 31) and, in the
 // epilogues, the 16 accumulator columns 16 (w >> 2) ..; in the staging phases it moves the 8 tile rows 8 w .. 8 w + 7.
 // Every phase therefore runs with four warps per scheduler instead of one.
@@ -481,9 +519,16 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
     __shared__ __align__(8) uint64_t s_mma;
     __shared__ __align__(16) uint8_t s_mask[2][kTile][16];     // ReLU sign patterns of H1 / H2: one nibble per 4-feature chunk
     __shared__ uint32_t s_tmem;
+    __shared__ LevelGeom<3> s_geo[kLevels];
+    __shared__ uint32_t s_base[kLevels];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool split = (p.precision == 0);
     const uint32_t q = warp & 3u, cg = warp >> 2;           // TMEM lane quadrant, 16-column group
+    const bool scatter = (p.x01 != nullptr);
+    if (scatter && tid >= 64 && tid < 64 + kLevels) {
+        s_geo[tid - 64] = level_geometry<3>(p.offsets, tid - 64, p.S, p.H, 0u);
+        s_base[tid - 64] = (uint32_t)__ldg(p.offsets + (tid - 64));
+    }
     const uint32_t row = q * 32u + lane;                    // tile row of this thread's TMEM lane
     uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -575,6 +620,15 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
     };
 
+    // One level (of the four this warp serves: 4 cg + lq) of the PREVIOUS tile's scatter.  Spread over the tile's four
+    // tensor-core waits: the L2 reduction rate (~0.7 per clock and SM), not the issue rate, bounds the scatter, so the
+    // reductions have to drain while the tensor core and the other phases are busy, not in one burst.
+    auto scatter_slot = [&](uint32_t prev_it, uint32_t prev_tile, uint32_t lq) {
+        const uint32_t level = cg * 4u + lq;
+        scatter_level(p.x01, p.g_table, s_geo[level], s_base[level],
+                      lane_base + cDGE + (prev_it & 1u) * 32u + cg * 8u + lq * 2u, prev_tile * kTile + row, p.B, lane);
+    };
+
     load_h2_g(blockIdx.x);
     load_h1(blockIdx.x);
     load_enc(blockIdx.x);
@@ -619,6 +673,7 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
             put_mn(bufA, bufA + kMn64, 32 * i + lane, h_c * 4u, rh1[i].x, rh1[i].y, rh1[i].z, rh1[i].w, split);
         }
         load_h2_g(next);
+        if (scatter && it > 0) scatter_slot(it - 1, tile - gridDim.x, 0);
         mma_done();
         HEAD_TRACE(3);
         masked_epilogue(1);                                  // G2 = DG2 * [H2 > 0]
@@ -636,6 +691,7 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
             __syncwarp();
         }
         load_h1(next);
+        if (scatter && it > 0) { scatter_slot(it - 1, tile - gridDim.x, 1); scatter_slot(it - 1, tile - gridDim.x, 2); }
         mma_done();
         HEAD_TRACE(6);
         masked_epilogue(0);                                  // G1 = DG1 * [H1 > 0]; step 4 has released bufA and bufB
@@ -649,16 +705,19 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         if (issuer) {
             if (umma::elect_one()) {
                 umma::fence_after_sync();
-                issue_gemm_ts<kIn, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT1h, dT1l, split);
+                issue_gemm_ts<kIn, kHid>(tmem + (scatter ? cDGE + (it & 1u) * 32u : cDG), tmem + cAhi, tmem + cAlo, dT1h, dT1l, split);
                 issue_gemm_mn<kIn>(tmem + cW1, dB, dB + (kMn64 >> 4), dA, dA + (kMn32 >> 4), split, first);
                 umma::commit(umma::smem_u32(&s_mma));
             }
             __syncwarp();
         }
         load_enc(next);
+        if (scatter && it > 0) scatter_slot(it - 1, tile - gridDim.x, 3);
         mma_done();
         HEAD_TRACE(9);
-        if (cg < 2) {                                        // g_enc [B,32] row-major: 64 contiguous bytes per thread
+        if (scatter) {
+            // the gradient of the encoding stays in tensor memory (buffer it & 1); it is scattered during the next tile
+        } else if (cg < 2) {                                 // g_enc [B,32] row-major: 64 contiguous bytes per thread
             const uint32_t b = tile * kTile + row;
             float v[16];
             umma::tmem_ld16(lane_base + cDG + cg * 16u, v);
@@ -671,6 +730,14 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         HEAD_TRACE(10);
         // the next tile's staging may start at once: every MMA that read bufA / bufB / bufG / the A planes has completed;
         // this tile's reads of cDG are ordered before the next MMAs by the fence in the next publish()
+    }
+    if (scatter) {                                        // the last tile's scatter
+        const uint32_t n_it = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        if (n_it > 0) {
+            const uint32_t last_tile = blockIdx.x + (n_it - 1) * gridDim.x;
+#pragma unroll 1
+            for (uint32_t lq = 0; lq < 4; ++lq) scatter_slot(n_it - 1, last_tile, lq);
+        }
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -740,13 +807,19 @@ extern "C" __attribute__((visibility("default"))) int sanerf_debug_head_trace(lo
 
 extern "C" int sanerf_field_head_backward(const float* enc, const float* h1, const float* h2, const float* g_out,
                                           const float* w1, const float* w2, const float* w3, uint32_t B, float* g_enc,
+                                          const float* x01, const int32_t* offsets, float S, uint32_t H, float* g_table,
                                           float* g_w1, float* g_w2, float* g_w3, int precision, void* stream) {
     if (B == 0) return SANERF_OK;
+    if (x01 != nullptr) {
+        SANERF_REQUIRE_PTR(offsets); SANERF_REQUIRE_PTR(g_table);
+    } else {
+        SANERF_REQUIRE_PTR(g_enc);
+    }
     SANERF_REQUIRE_PTR(enc); SANERF_REQUIRE_PTR(h1); SANERF_REQUIRE_PTR(h2); SANERF_REQUIRE_PTR(g_out);
     SANERF_REQUIRE_PTR(w1); SANERF_REQUIRE_PTR(w2); SANERF_REQUIRE_PTR(w3);
-    SANERF_REQUIRE_PTR(g_enc); SANERF_REQUIRE_PTR(g_w1); SANERF_REQUIRE_PTR(g_w2); SANERF_REQUIRE_PTR(g_w3);
+    SANERF_REQUIRE_PTR(g_w1); SANERF_REQUIRE_PTR(g_w2); SANERF_REQUIRE_PTR(g_w3);
     if (precision != 0 && precision != 1) return fail(SANERF_ERR_INVALID_ARG, "field_head: precision 0 (3xTF32) or 1 (TF32)");
-    HeadBwdParams p{enc, h1, h2, g_out, w1, w2, w3, g_enc, g_w1, g_w2, g_w3, B, precision};
+    HeadBwdParams p{enc, h1, h2, g_out, w1, w2, w3, g_enc, x01, offsets, g_table, S, H, g_w1, g_w2, g_w3, B, precision};
     const uint32_t tiles = div_up(B, head::kTile);
     const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     cudaError_t e = cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kBwdSmem);

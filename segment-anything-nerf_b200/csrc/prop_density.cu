@@ -142,6 +142,11 @@ __global__ void __launch_bounds__(kPropThreads, 2) prop_backward_kernel(const Pr
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint32_t b = tile * kPropThreads + tid;
         const bool live = b < p.B;
+        // Most proposal samples receive no gradient at all (the proposal loss only pushes where the final level's
+        // weight exceeds the proposal's bound): a warp whose 32 incoming gradients are all zero contributes nothing to
+        // the table, to dW1 or to dW2 and skips the tile outright.
+        const float gs = live ? __ldg(g_sigma + b) : 0.0f;
+        if (__ballot_sync(0xffffffffu, gs != 0.0f) == 0u) continue;
         float x[3] = {0.5f, 0.5f, 0.5f};
         if (live) {
 #pragma unroll
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(kPropThreads, 2) prop_backward_kernel(const Pr
             for (uint32_t i = 0; i < IN; ++i) u[i] = __fmaf_rn(gate, wj[i], u[i]);
         }
         // trunc_exp backward (activation.py:16)
-        const float dpre = live ? __ldg(g_sigma + b) * expf(fminf(fmaxf(pre, -15.0f), 15.0f)) : 0.0f;
+        const float dpre = gs * expf(fminf(fmaxf(pre, -15.0f), 15.0f));
         float denc[IN];
 #pragma unroll
         for (uint32_t i = 0; i < IN; ++i) denc[i] = dpre * u[i];

@@ -155,6 +155,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// TMEM -> registers: 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// TMEM -> registers: 2 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    a = __uint_as_float(r0);
+    b = __uint_as_float(r1);
+}
+
 // registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns (no wait: call tmem_st_wait() before the
 // data is consumed by an MMA or another warp)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {

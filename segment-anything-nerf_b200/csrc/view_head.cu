@@ -183,6 +183,170 @@ __global__ void __launch_bounds__(vh::kRays) view_head_kernel(const ViewHeadPara
     }
 }
 
+
+// ---- training variant: forward + loss + full backward, 32 rays per 256-thread block ---------------------------------
+// The per-ray chains above are ~6 k dependent instructions; with 8192 rays a thread-per-ray kernel leaves the GPU
+// almost empty.  Here every layer is a [32 rays x 32 units] tile product computed by the whole block from shared
+// memory: thread (ray = lane, unit group = warp) produces 4 outputs per layer, activations are exchanged through
+// padded shared tiles, and the weight gradients are dot products over the block's 32 rays (one atomic per entry).
+namespace vt {
+using namespace vh;
+constexpr int kR = 32, kThreads = 256, kP = 33;           // rays per block, threads, tile pitch (conflict-free both ways)
+constexpr int oW1 = 0, oW2 = oW1 + kW1, oW3 = oW2 + kW2, oF = oW3 + kW3, oH1 = oF + kR * kP, oH2 = oH1 + kR * kP,
+              oG1 = oH2 + kR * kP, oG2 = oG1 + kR * kP, oGF = oG2 + kR * kP, oG3 = oGF + kR * kP, oSH = oG3 + kR * 4,
+              oMisc = oSH + kR * 17, kFloats = oMisc + kR * 2 + 8;
+constexpr size_t kSmem = (size_t)kFloats * sizeof(float);
+}  // namespace vt
+
+__global__ void __launch_bounds__(vt::kThreads) view_head_train_kernel(const ViewHeadParams p) {
+    using namespace vt;
+    extern __shared__ float smem[];
+    float *sW1 = smem + oW1, *sW2 = smem + oW2, *sW3 = smem + oW3, *sF = smem + oF, *sH1 = smem + oH1, *sH2 = smem + oH2;
+    float *sG1 = smem + oG1, *sG2 = smem + oG2, *sGF = smem + oGF, *sG3 = smem + oG3, *sSH = smem + oSH;
+    float *sWs = smem + oMisc, *sGws = sWs + kR, *sLoss = sGws + kR;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < kW1; i += kThreads) sW1[i] = __ldg(p.w1 + i);
+    for (int i = t; i < kW2; i += kThreads) sW2[i] = __ldg(p.w2 + i);
+    for (int i = t; i < kW3; i += kThreads) sW3[i] = __ldg(p.w3 + i);
+    const uint32_t r0 = blockIdx.x * kR;
+    const uint32_t r = r0 + lane;
+    const bool live = r < p.N;
+    if (t == 0) sLoss[0] = 0.0f;
+    // ---- inputs: geometry sums spread over the block, SH by warp 0
+    for (int e = t; e < kR * kGeo; e += kThreads) {
+        const int rr = e / kGeo, i = e - rr * kGeo;
+        sF[rr * kP + i] = (r0 + rr < p.N) ? __ldg(p.geo_sum + (size_t)(r0 + rr) * kGeo + i) : 0.0f;
+    }
+    if (warp == 0) {
+        float sh[kSh], ws = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kSh; ++i) sh[i] = 0.0f;
+        if (live) {
+            ws = __ldg(p.weights_sum + r);
+            float x = __ldg(p.rays_d + (size_t)r * 3), y = __ldg(p.rays_d + (size_t)r * 3 + 1), z = __ldg(p.rays_d + (size_t)r * 3 + 2);
+            const float n = sqrtf(x * x + y * y + z * z);
+            x /= n; y /= n; z /= n;
+            sh_eval<4, false>(x, y, z, sh, nullptr);
+        }
+        sWs[lane] = ws;
+        sGws[lane] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kSh; ++i) { sSH[lane * 17 + i] = sh[i]; sF[lane * kP + kGeo + i] = ws * sh[i]; }
+    }
+    __syncthreads();
+    // ---- layer 1 / 2: thread (ray = lane, units 4 warp .. 4 warp + 3)
+    {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < kIn; ++i) {
+            const float f = sF[lane * kP + i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = __fmaf_rn(sW1[(warp * 4 + q) * kIn + i], f, a[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sH1[lane * kP + warp * 4 + q] = fmaxf(a[q], 0.0f);
+    }
+    __syncthreads();
+    {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < kHid; ++j) {
+            const float h = sH1[lane * kP + j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = __fmaf_rn(sW2[(warp * 4 + q) * kHid + j], h, a[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sH2[lane * kP + warp * 4 + q] = fmaxf(a[q], 0.0f);
+    }
+    __syncthreads();
+    // ---- output, loss, d loss / d pre-sigmoid: warps 0..2 <-> channels
+    const float inv = p.loss_weight / (3.0f * (float)p.N);       // mean over [N,3]
+    if (warp < kOut) {
+        float a = 0.0f;
+        for (int k = 0; k < kHid; ++k) a = __fmaf_rn(sW3[warp * kHid + k], sH2[lane * kP + k], a);
+        const float rgb = 1.0f / (1.0f + expf(-a));
+        const float img = rgb + (1.0f - sWs[lane]) * p.bg;
+        float diff = 0.0f;
+        if (live) {
+            p.image[(size_t)r * kOut + warp] = img;
+            diff = img - __ldg(p.gt + (size_t)r * kOut + warp);
+        }
+        const float gi = 2.0f * diff * inv;
+        sG3[lane * 4 + warp] = gi * rgb * (1.0f - rgb);
+        atomicAdd(sGws + lane, -gi * p.bg);
+        const float l = warp_sum(diff * diff);
+        if (lane == 0) atomicAdd(sLoss, l);
+    }
+    __syncthreads();
+    if (t == 0) atomicAdd(p.loss, sLoss[0] * inv);
+    // ---- backward through the three layers
+    {
+        const float g0 = sG3[lane * 4], g1 = sG3[lane * 4 + 1], g2 = sG3[lane * 4 + 2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = warp * 4 + q;
+            const float a = __fmaf_rn(sW3[2 * kHid + k], g2, __fmaf_rn(sW3[kHid + k], g1, sW3[k] * g0));
+            sG2[lane * kP + k] = (sH2[lane * kP + k] > 0.0f) ? a : 0.0f;
+        }
+    }
+    __syncthreads();
+    {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < kHid; ++k) {
+            const float g = sG2[lane * kP + k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = __fmaf_rn(sW2[k * kHid + warp * 4 + q], g, a[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sG1[lane * kP + warp * 4 + q] = (sH1[lane * kP + warp * 4 + q] > 0.0f) ? a[q] : 0.0f;
+    }
+    __syncthreads();
+    {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < kHid; ++j) {
+            const float g = sG1[lane * kP + j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = warp * 4 + q;
+                if (i < kIn) a[q] = __fmaf_rn(sW1[j * kIn + i], g, a[q]);
+            }
+        }
+        float gws = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = warp * 4 + q;
+            if (i < kGeo) {
+                if (live) p.g_geo_sum[(size_t)r * kGeo + i] = a[q];
+            } else if (i < kIn) {
+                gws = __fmaf_rn(a[q], sSH[lane * 17 + (i - kGeo)], gws);
+            }
+        }
+        if (warp * 4 + 3 >= kGeo) atomicAdd(sGws + lane, gws);
+    }
+    __syncthreads();
+    if (warp == 0 && live) p.g_weights_sum[r] = sGws[lane];
+    // ---- weight gradients: dot products over the block's rays
+    auto dot = [&](const float* a, const float* b) {
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int q = 0; q < kR; ++q) acc = __fmaf_rn(a[q * kP], b[q * kP], acc);
+        return acc;
+    };
+    for (int e = t; e < kW1; e += kThreads) {           // dW1[j][i] = sum_r g1[r][j] f[r][i]
+        const int j = e / kIn, i = e - j * kIn;
+        red_add_f32(p.g_w1 + e, dot(sG1 + j, sF + i));
+    }
+    for (int e = t; e < kW2; e += kThreads) {           // dW2[k][j] = sum_r g2[r][k] h1[r][j]
+        const int k = e / kHid, j = e - k * kHid;
+        red_add_f32(p.g_w2 + e, dot(sG2 + k, sH1 + j));
+    }
+    if (t < kW3) {                                      // dW3[c][k] = sum_r g3[r][c] h2[r][k]
+        const int c = t / kHid, k = t - c * kHid;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int q = 0; q < kR; ++q) acc = __fmaf_rn(sG3[q * 4 + c], sH2[q * kP + k], acc);
+        red_add_f32(p.g_w3 + t, acc);
+    }
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -204,9 +368,8 @@ extern "C" int sanerf_view_head(const float* geo_sum, const float* weights_sum, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t blocks = div_up(N, (uint32_t)vh::kRays);
     if (train) {
-        cudaError_t e = cudaFuncSetAttribute(view_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vh::kSmemBwd);
-        if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "view_head: %s", cudaGetErrorString(e));
-        view_head_kernel<true><<<blocks, vh::kRays, vh::kSmemBwd, st>>>(p);
+        view_head_train_kernel<<<div_up(N, (uint32_t)vt::kR), vt::kThreads, vt::kSmem, st>>>(p);
+        return check_launch("view_head_train_kernel");
     }
     else view_head_kernel<false><<<blocks, vh::kRays, vh::kSmemFwd, st>>>(p);
     return check_launch("view_head_kernel");

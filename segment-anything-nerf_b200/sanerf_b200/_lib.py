@@ -16,7 +16,7 @@ _HEADER = os.path.join(os.path.dirname(_PKG_DIR), "include", "sanerf_b200.h")
 
 SANERF_F32, SANERF_F16 = 0, 1
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 c_void_p, c_int, c_u32, c_u64, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                           ctypes.c_uint64, ctypes.c_float)
@@ -71,7 +71,8 @@ _SIGNATURES = {
     "sanerf_field_head_forward": [c_void_p, c_void_p, c_void_p, c_float, c_u32, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "sanerf_field_head_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+                                   c_void_p, c_void_p, c_void_p, c_float, c_u32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_void_p],
     "sanerf_umma_selftest": [c_int, c_u32, c_u32, c_u32, c_void_p, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"sanerf_last_error": ctypes.c_char_p, "sanerf_status_string": ctypes.c_char_p}
@@ -147,7 +148,7 @@ class _Span:
     def __enter__(self):
         st = self.stats
         st.count += 1
-        if st.watch and st.watch[0] == self.name and (st.watch[1] is None or st.watch[1](self.info)):
+        if st.watch and st.watch[0] in (self.name, "*") and (st.watch[1] is None or st.watch[1](self.info)):
             import torch
 
             self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -157,7 +158,7 @@ class _Span:
     def __exit__(self, *exc):
         if self.ev is not None:
             self.ev[1].record()
-            self.stats.spans.append((self.ev[0], self.ev[1], self.info))
+            self.stats.spans.append((self.ev[0], self.ev[1], dict(self.info, name=self.name)))
         return False
 
 

@@ -180,15 +180,16 @@ class _FieldHead(Function):
         B, S, H, precision = ctx.meta
         dev = x01.device
         g_out = g_out.contiguous()
-        g_enc = torch.empty(B, 32, device=dev, dtype=torch.float32)
         g_w1, g_w2, g_w3 = torch.zeros_like(w1), torch.zeros_like(w2), torch.zeros_like(w3)
         lib = _lib.load()
         st = _stream(x01)
+        g_enc = torch.empty(B, 32, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             with _lib.stats.span("field_head_backward", B=B):
                 rc = lib.sanerf_field_head_backward(enc.data_ptr(), h1.data_ptr(), h2.data_ptr(), g_out.data_ptr(),
-                                                    w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, g_enc.data_ptr(),
-                                                    g_w1.data_ptr(), g_w2.data_ptr(), g_w3.data_ptr(), precision, st)
+                                                    w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, g_enc.data_ptr(), None,
+                                                    None, 0.0, 0, None, g_w1.data_ptr(), g_w2.data_ptr(), g_w3.data_ptr(),
+                                                    precision, st)
             _lib.check(rc, "field_head_backward")
             g_table = None
             if ctx.needs_input_grad[1]:
@@ -383,7 +384,9 @@ class FusedAdam:
         self.exp_avg = torch.zeros(total, device=dev)
         self.exp_avg_sq = torch.zeros(total, device=dev)
         off = 0
+        self.ranges = {}                                    # id(param) -> (start, stop) in the flat buffers
         for p, n in zip(self.params, sizes):
+            self.ranges[id(p)] = (off, off + n)
             view = self.flat_param[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
@@ -391,22 +394,36 @@ class FusedAdam:
             off += n
         self.lr, self.betas, self.eps, self.decay_iters = float(lr), betas, float(eps), float(decay_iters)
         self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
-        self.dyn = torch.zeros(4, device=dev)
+        self.dyn = torch.tensor([self.lr, 1.0, 1.0, 0.0], device=dev)     # {lr_t, 1-b1^t, 1-b2^t}: neutral before step 1
 
     def zero_grad(self):
         self.flat_grad.zero_()
 
-    def step(self, grad_scale=1.0, zero_grad=True):
+    def schedule(self):
+        """Advance the device-side step counter and learning-rate / bias-correction terms (one tiny kernel)."""
         lib = _lib.load()
         dev = self.flat_param.device
-        st = _lib.current_stream(dev)
-        with torch.cuda.device(dev):
-            with _lib.stats.span("adam_schedule"):
-                rc = lib.sanerf_adam_schedule(self.step_count.data_ptr(), self.dyn.data_ptr(), self.lr, self.betas[0],
-                                              self.betas[1], self.decay_iters, st)
-            _lib.check(rc, "adam_schedule")
-            with _lib.stats.span("adam_step", n=self.flat_param.numel()):
-                rc = lib.sanerf_adam_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
-                                          self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.dyn.data_ptr(),
-                                          self.betas[0], self.betas[1], self.eps, float(grad_scale), int(zero_grad), st)
-            _lib.check(rc, "adam_step")
+        with torch.cuda.device(dev), _lib.stats.span("adam_schedule"):
+            rc = lib.sanerf_adam_schedule(self.step_count.data_ptr(), self.dyn.data_ptr(), self.lr, self.betas[0],
+                                          self.betas[1], self.decay_iters, _lib.current_stream(dev))
+        _lib.check(rc, "adam_schedule")
+
+    def apply(self, start=0, stop=None, grad_scale=1.0, zero_grad=True):
+        """Adam update of the flat range [start, stop) with the terms of the LAST ``schedule()`` (multiples of 4)."""
+        stop = self.flat_param.numel() if stop is None else stop
+        n = stop - start
+        if n <= 0:
+            return
+        lib = _lib.load()
+        dev = self.flat_param.device
+        off = 4 * start
+        with torch.cuda.device(dev), _lib.stats.span("adam_step", n=n):
+            rc = lib.sanerf_adam_step(self.flat_param.data_ptr() + off, self.flat_grad.data_ptr() + off,
+                                      self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off, n, self.dyn.data_ptr(),
+                                      self.betas[0], self.betas[1], self.eps, float(grad_scale), int(zero_grad),
+                                      _lib.current_stream(dev))
+        _lib.check(rc, "adam_step")
+
+    def step(self, grad_scale=1.0, zero_grad=True):
+        self.schedule()
+        self.apply(0, None, grad_scale, zero_grad)

@@ -10,7 +10,9 @@ underneath), but without autograd, without torch glue kernels and without per-la
   losses:     proposal loss (2 levels) and distortion loss, each returning its gradient, pre-multiplied by lambda
   backward:   composite + trunc_exp -> field head (tcgen05) -> hash-grid scatter
               || (forked stream / parallel graph branch) proposal losses -> composite -> proposal density (x2)
-  update:     [NCCL all-reduce of the flat gradient bucket when world_size > 1] -> fused Adam (clears the gradient)
+  update:     [NCCL all-reduce when world_size > 1] -> fused Adam (clears the gradient): MLPs and proposal tables at the
+              end of the step; the main hash table (89 % of the parameters) at the START of the next step, on a second
+              stream, hidden behind jitter + the two proposal levels (which do not read it).  ``flush()`` applies it.
 
 Every gradient kernel accumulates straight into the views of ``FusedAdam.flat_grad`` (pre-zeroed by the optimizer
 kernel), so there is no ``zeros_like`` + add per parameter.  ``tests/test_gpu_step.py`` checks loss and every gradient
@@ -81,6 +83,8 @@ class FusedRGBStep:
         self.image = torch.empty(N, 3, **f32)
         self.loss = torch.zeros(1, **f32)
         self.side_stream = torch.cuda.Stream(dev)
+        self.update_stream = torch.cuda.Stream(dev)
+        self.pending_main = False
         self.graphs = {}
         self.eager_runs = {}
         self.global_step = 0
@@ -91,7 +95,12 @@ class FusedRGBStep:
 
     # ------------------------------------------------------------------------------------------------------
     def _launch(self, update_proposal):
-        """Enqueue the whole step on the current stream (eagerly, or under CUDA-graph capture)."""
+        """Enqueue forward + backward on the current stream (eagerly, or under CUDA-graph capture)."""
+        self._launch_front(update_proposal)
+        self._launch_back(update_proposal)
+
+    def _launch_front(self, update_proposal):
+        """Jitter + the two proposal levels + the final level's sample positions: nothing here touches the main table."""
         m, lib, N = self.model, _lib.load(), self.N
         st = _lib.current_stream(self.dev)
         span, check, ptr = _lib.stats.span, _lib.check, _lib.ptr
@@ -137,6 +146,14 @@ class FusedRGBStep:
                                                       None, N, T, 0, self.opaque, 0.0, L["weights"].data_ptr(), L["ws"].data_ptr(),
                                                       L["depth"].data_ptr(), None, None, st)
                 check(rc, "composite_forward")
+    def _launch_back(self, update_proposal):
+        """Final level forward, losses, backward of everything."""
+        m, lib, N = self.model, _lib.load(), self.N
+        st = _lib.current_stream(self.dev)
+        span, check = _lib.stats.span, _lib.check
+        lam_p = float(m.opt.lambda_proposal) if update_proposal else 0.0
+        lam_d = float(m.opt.lambda_distort)
+        d = self.rays_d.data_ptr()
         # ---------------- forward: final level
         L = self.lv[2]
         T, B = L["T"], N * L["T"]
@@ -212,8 +229,9 @@ class FusedRGBStep:
         check(rc, "head_composite_backward")
         with span("field_head_backward", B=B):
             rc = lib.sanerf_field_head_backward(self.enc.data_ptr(), self.h1.data_ptr(), self.h2.data_ptr(), self.g_head.data_ptr(),
-                                                w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, self.g_enc.data_ptr(),
-                                                w1.grad.data_ptr(), w2.grad.data_ptr(), w3.grad.data_ptr(), self.precision, st)
+                                                w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, self.g_enc.data_ptr(), None, None,
+                                                0.0, 0, None, w1.grad.data_ptr(), w2.grad.data_ptr(), w3.grad.data_ptr(),
+                                                self.precision, st)
         check(rc, "field_head_backward")
         with span("grid_encode_backward", B=B, L=16, C=2, D=3, half=False):
             rc = lib.sanerf_grid_encode_backward(self.g_enc.data_ptr(), L["x01"].data_ptr(), g.embeddings.data_ptr(),
@@ -223,28 +241,70 @@ class FusedRGBStep:
         if lam_p > 0:
             main.wait_stream(self.side_stream)            # join
 
-    def _update(self):
+    # ---- optimizer.  The main hash table is 89 % of the parameters and nothing before the final level's field head reads
+    # it, so its Adam update (and, multi-GPU, the all-reduce of its gradient) is DEFERRED to the start of the next step,
+    # where it runs on a second stream concurrently with jitter + both proposal levels.  Everything else (MLPs, proposal
+    # tables) is updated at the end of the step.  ``flush()`` applies a pending main-table update (call it before
+    # reading the parameters: checkpoints, evaluation, tests).
+    def _main_range(self):
+        return self.optimizer.ranges[id(self.model.grid.embeddings)]
+
+    def _update_main(self):
+        a, b = self._main_range()
         if self.world_size > 1:
-            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
-        self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
+            dist.all_reduce(self.optimizer.flat_grad[a:b], op=dist.ReduceOp.SUM)
+        self.optimizer.apply(a, b, grad_scale=1.0 / self.world_size, zero_grad=True)
+
+    def _update_rest(self):
+        a, b = self._main_range()
+        n = self.optimizer.flat_param.numel()
+        assert a == 0, "the main table is expected to lead the flat parameter buffer"
+        if self.world_size > 1:
+            dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
+        self.optimizer.schedule()
+        self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
+
+    def flush(self):
+        if self.pending_main:
+            with torch.cuda.device(self.dev):
+                self._update_main()
+            self.pending_main = False
 
     def gradients_only(self, rays_o, rays_d, gt, update_proposal=True):
         """Forward + backward without the optimizer update (tests): gradients are left in the flat bucket."""
+        self.flush()
         self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.gt.copy_(gt)
         with torch.cuda.device(self.dev):
             self._launch(update_proposal)
         return self.loss[0]
 
-    def _graph(self, update_proposal):
+    def _whole_step(self, update_proposal):
+        """Single-GPU step on the current stream: deferred main-table update || front, then back, then the small update."""
+        main = torch.cuda.current_stream(self.dev)
+        upd = self.update_stream
+        upd.wait_stream(main)
+        with torch.cuda.stream(upd):
+            self._update_main()                            # previous step's gradient (zero before the first step)
+        self._launch_front(update_proposal)
+        main.wait_stream(upd)
+        self._launch_back(update_proposal)
+        self._update_rest()
+
+    def _graphs(self, update_proposal):
         key = bool(update_proposal)
         if key not in self.graphs:
-            graph_whole = self.world_size == 1          # the NCCL exchange stays outside the graph
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._launch(update_proposal)
-                if graph_whole:
-                    self._update()
-            self.graphs[key] = (g, graph_whole)
+            if self.world_size == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._whole_step(update_proposal)
+                self.graphs[key] = (g,)
+            else:                                          # NCCL stays outside the graphs
+                gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gf):
+                    self._launch_front(update_proposal)
+                with torch.cuda.graph(gb):
+                    self._launch_back(update_proposal)
+                self.graphs[key] = (gf, gb)
         return self.graphs[key]
 
     def __call__(self, rays_o, rays_d, gt):
@@ -257,13 +317,29 @@ class FusedRGBStep:
         self.gt.copy_(gt, non_blocking=True)
         with torch.cuda.device(self.dev):
             key = bool(update_proposal)
-            if self.use_graph and self.eager_runs.get(key, 0) >= 1:      # first step of each variant runs eagerly (warm-up)
-                g, whole = self._graph(update_proposal)
-                g.replay()
-                if not whole:
-                    self._update()
-            else:
+            graphed = self.use_graph and self.eager_runs.get(key, 0) >= 1   # first step of each variant runs eagerly (warm-up)
+            if not graphed:
                 self.eager_runs[key] = self.eager_runs.get(key, 0) + 1
-                self._launch(update_proposal)
-                self._update()
+            if self.world_size == 1:
+                if graphed:
+                    self._graphs(update_proposal)[0].replay()
+                else:
+                    self._whole_step(update_proposal)
+            else:
+                main = torch.cuda.current_stream(self.dev)
+                upd = self.update_stream
+                upd.wait_stream(main)
+                with torch.cuda.stream(upd):
+                    self._update_main()                    # all-reduce + Adam of the main table, hidden behind the front
+                if graphed:
+                    gf, gb = self._graphs(update_proposal)
+                    gf.replay()
+                    main.wait_stream(upd)
+                    gb.replay()
+                else:
+                    self._launch_front(update_proposal)
+                    main.wait_stream(upd)
+                    self._launch_back(update_proposal)
+                self._update_rest()
+            self.pending_main = True
         return self.loss[0]

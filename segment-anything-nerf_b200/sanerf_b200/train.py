@@ -68,12 +68,23 @@ class RGBTrainer:
                 self._plans[n_rays] = None
         return self._plans[n_rays]
 
+    def flush(self):
+        """Apply the main-table update the hand-scheduled step defers to the start of the next step (call before
+        reading parameters: checkpoint, evaluation, switching ray counts)."""
+        for plan in self._plans.values():
+            if plan is not None:
+                plan.flush()
+
     def step(self, rays_o, rays_d, gt_rgb):
         plan = self.plan(rays_o.shape[0])
+        for other in self._plans.values():                # a pending update of another ray count's plan comes first
+            if other is not None and other is not plan:
+                other.flush()
         if plan is not None:
             plan.global_step = self.global_step
             self.global_step += 1
             return plan(rays_o, rays_d, gt_rgb)
+        self.flush()
         self.global_step += 1
         update_proposal = self.global_step <= 3000 or self.global_step % 5 == 0   # nerf/utils.py:910-911
         dev = self.optimizer.flat_param.device

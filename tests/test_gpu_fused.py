@@ -228,3 +228,47 @@ def test_fused_renderer_equals_generic_renderer(cuda):
     from tests.test_gpu_render import assert_grad_close
     for n in ga:
         assert_grad_close(n, ga[n], gb[n].cpu())
+
+
+@pytest.mark.parametrize("N", [8192, 77])
+def test_view_head_kernel_matches_autograd(cuda, N):
+    """Fused deferred-shading head (SH + view MLP + sigmoid + background + MSE, forward and backward) vs torch."""
+    from shencoder import SHEncoder
+    from sanerf_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(11)
+    geo = torch.randn(N, 15, device="cuda", generator=g).requires_grad_(True)
+    ws = torch.rand(N, device="cuda", generator=g).requires_grad_(True)
+    d = torch.randn(N, 3, device="cuda", generator=g) * 3
+    gt = torch.rand(N, 3, device="cuda", generator=g)
+    w1 = (torch.randn(32, 31, device="cuda", generator=g) / 31 ** 0.5).requires_grad_(True)
+    w2 = (torch.randn(32, 32, device="cuda", generator=g) / 32 ** 0.5).requires_grad_(True)
+    w3 = (torch.randn(3, 32, device="cuda", generator=g) / 32 ** 0.5).requires_grad_(True)
+    sh = SHEncoder(degree=4)(d)
+    f = torch.cat([geo, ws.unsqueeze(-1) * sh], dim=-1)
+    rgb = torch.sigmoid(torch.relu(torch.relu(f @ w1.t()) @ w2.t()) @ w3.t())
+    image_ref = rgb + (1 - ws).unsqueeze(-1) * 1.0
+    loss_ref = 0.7 * torch.nn.functional.mse_loss(image_ref, gt)
+    loss_ref.backward()
+
+    lib = _lib.load()
+    image, loss = torch.empty(N, 3, device="cuda"), torch.zeros(1, device="cuda")
+    g_geo, g_ws = torch.empty(N, 15, device="cuda"), torch.empty(N, device="cuda")
+    gw = [torch.zeros_like(w) for w in (w1, w2, w3)]
+    rc = lib.sanerf_view_head(geo.data_ptr(), ws.data_ptr(), d.data_ptr(), gt.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                              w3.data_ptr(), 1.0, 0.7, N, image.data_ptr(), loss.data_ptr(), g_geo.data_ptr(), g_ws.data_ptr(),
+                              gw[0].data_ptr(), gw[1].data_ptr(), gw[2].data_ptr(), _lib.current_stream(geo.device))
+    _lib.check(rc, "view_head")
+    torch.testing.assert_close(image, image_ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(loss[0], loss_ref.detach(), rtol=1e-5, atol=1e-8)
+    scale = lambda t: t.abs().max().item()  # noqa: E731
+    torch.testing.assert_close(g_geo, geo.grad, rtol=1e-4, atol=1e-5 * scale(geo.grad))
+    torch.testing.assert_close(g_ws, ws.grad, rtol=1e-4, atol=1e-5 * scale(ws.grad))
+    for got, ref in zip(gw, (w1, w2, w3)):
+        torch.testing.assert_close(got, ref.grad, rtol=1e-4, atol=2e-5 * scale(ref.grad))
+    # forward only (inference): same image, nothing else touched
+    image2 = torch.empty(N, 3, device="cuda")
+    rc = lib.sanerf_view_head(geo.data_ptr(), ws.data_ptr(), d.data_ptr(), None, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(),
+                              1.0, 1.0, N, image2.data_ptr(), None, None, None, None, None, None,
+                              _lib.current_stream(geo.device))
+    _lib.check(rc, "view_head")
+    torch.testing.assert_close(image2, image_ref.detach(), rtol=1e-5, atol=1e-6)

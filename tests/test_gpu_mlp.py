@@ -145,7 +145,7 @@ def test_field_head_backward_matches_autograd(cuda, B):
         g_enc = torch.full((B, 32), float("nan"), device="cuda")
         gw = [torch.zeros_like(w) for w in (w1, w2, w3)]
         rc = lib.sanerf_field_head_backward(e_tcm.data_ptr(), h1_tcm.data_ptr(), h2_tcm.data_ptr(), g_out.data_ptr(), w1.data_ptr(),
-                                            w2.data_ptr(), w3.data_ptr(), B, g_enc.data_ptr(), gw[0].data_ptr(),
+                                            w2.data_ptr(), w3.data_ptr(), B, g_enc.data_ptr(), None, None, 0.0, 0, None, gw[0].data_ptr(),
                                             gw[1].data_ptr(), gw[2].data_ptr(), precision, _lib.current_stream(e.device))
         _lib.check(rc, "field_head_backward")
         torch.cuda.synchronize()
@@ -174,3 +174,44 @@ def test_field_head_autograd_equals_unfused(cuda):
     g_new = torch.autograd.grad(out, params, go)
     for a, b in zip(g_new, g_ref):
         assert ((a - b).norm() / b.norm()).item() < 1e-4
+
+
+def test_field_head_backward_fused_scatter_equals_separate_kernel(cuda):
+    """Optional mode of the backward kernel: the hash-grid scatter runs inside it (gradient of the encoding taken from
+    tensor memory) instead of sanerf_grid_encode_backward on a [B,32] buffer."""
+    import numpy as np
+    from sanerf_b200.fused import rows_to_tcm
+    B = 128 * 148 * 2 + 37
+    enc, w1, w2, w3, x01 = _head_setup(B, seed=6)
+    # ray-like ordering so that the warp aggregation actually merges lanes
+    x01 = (torch.rand(B // 32 + 1, 1, 3, device="cuda") + torch.linspace(0, 0.05, 32, device="cuda").view(1, 32, 1)).reshape(-1, 3)[:B]
+    x01 = x01.clamp(0, 1).contiguous()
+    x01[::97] = 1.5
+    lib = _lib.load()
+    _, enc_rows, h1, h2 = _head_call(x01, enc, w1.detach(), w2.detach(), w3.detach(), 0, want_hidden=True)
+    e_tcm = rows_to_tcm(enc_rows.contiguous())
+    g_out = torch.randn(B, 16, device="cuda")
+    S, H = float(np.log2(enc.per_level_scale)), int(enc.base_resolution)
+    st = _lib.current_stream(x01.device)
+    g_enc = torch.empty(B, 32, device="cuda")
+    gw_a = [torch.zeros_like(w) for w in (w1, w2, w3)]
+    rc = lib.sanerf_field_head_backward(e_tcm.data_ptr(), h1.data_ptr(), h2.data_ptr(), g_out.data_ptr(), w1.data_ptr(),
+                                        w2.data_ptr(), w3.data_ptr(), B, g_enc.data_ptr(), None, None, 0.0, 0, None,
+                                        gw_a[0].data_ptr(), gw_a[1].data_ptr(), gw_a[2].data_ptr(), 0, st)
+    _lib.check(rc, "field_head_backward")
+    gt_a = torch.zeros_like(enc.embeddings)
+    rc = lib.sanerf_grid_encode_backward(g_enc.data_ptr(), x01.data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
+                                         gt_a.data_ptr(), B, 3, 2, 16, 16, S, H, None, None, 0, 0, 0, _lib.SANERF_F32,
+                                         _lib.LAYOUT_BLC, st)
+    _lib.check(rc, "grid_encode_backward")
+    gt_b = torch.zeros_like(enc.embeddings)
+    gw_b = [torch.zeros_like(w) for w in (w1, w2, w3)]
+    rc = lib.sanerf_field_head_backward(e_tcm.data_ptr(), h1.data_ptr(), h2.data_ptr(), g_out.data_ptr(), w1.data_ptr(),
+                                        w2.data_ptr(), w3.data_ptr(), B, None, x01.data_ptr(), enc.offsets.data_ptr(), S, H,
+                                        gt_b.data_ptr(), gw_b[0].data_ptr(), gw_b[1].data_ptr(), gw_b[2].data_ptr(), 0, st)
+    _lib.check(rc, "field_head_backward")
+    torch.cuda.synchronize()
+    assert ((gt_a - gt_b).norm() / gt_a.norm()).item() < 1e-5          # same contributions, different summation order
+    torch.testing.assert_close(gt_b, gt_a, rtol=1e-3, atol=1e-5 * gt_a.abs().max().item())
+    for a, b in zip(gw_a, gw_b):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5 * a.abs().max().item())

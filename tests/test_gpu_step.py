@@ -62,6 +62,7 @@ def test_fused_step_graph_replay_equals_eager(cuda):
         la, lb = pa(o, d, gt).clone(), pb(o, d, gt).clone()
         assert torch.isfinite(la)
         torch.testing.assert_close(la, lb, rtol=2e-4, atol=1e-6)
+    pa.flush(); pb.flush()          # the main-table update of the last step is deferred to the next one
     assert True in pa.graphs and int(ta.optimizer.step_count) == 4
     for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
@@ -74,3 +75,9 @@ def test_trainer_uses_fused_step_and_learns(cuda):
     gt = gt * 0 + torch.tensor([0.2, 0.5, 0.8], device="cuda")
     losses = [float(trainer.step(o, d, gt)) for _ in range(30)]
     assert losses[-1] < 0.5 * losses[0], losses
+    before = model.grid.embeddings.detach().clone()
+    trainer.flush()                 # applies the deferred main-table update exactly once
+    assert not torch.equal(before, model.grid.embeddings)
+    after = model.grid.embeddings.detach().clone()
+    trainer.flush()
+    assert torch.equal(after, model.grid.embeddings)

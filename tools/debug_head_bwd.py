@@ -19,7 +19,7 @@ for prec in (0, 1):
     g_enc = torch.full((B, 32), float("nan"), device="cuda")
     gw = [torch.zeros_like(w) for w in (w1, w2, w3)]
     rc = lib.sanerf_field_head_backward(e.data_ptr(), h1.data_ptr(), h2.data_ptr(), g_out.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B,
-                                        g_enc.data_ptr(), gw[0].data_ptr(), gw[1].data_ptr(), gw[2].data_ptr(), prec, _lib.current_stream(e.device))
+                                        g_enc.data_ptr(), None, None, 0.0, 0, None, gw[0].data_ptr(), gw[1].data_ptr(), gw[2].data_ptr(), prec, _lib.current_stream(e.device))
     _lib.check(rc, "bwd"); torch.cuda.synchronize()
     err = (g_enc.double() - e64.grad).abs().max(dim=1).values / e64.grad.abs().max()
     tiles = (B + 127) // 128

@@ -27,7 +27,7 @@ def fwd(prec, train):
     _lib.check(rc, "fwd")
 def bwd(prec):
     rc = lib.sanerf_field_head_backward(e.data_ptr(), h1.data_ptr(), h2.data_ptr(), g_out.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B,
-                                        g_enc.data_ptr(), gw[0].data_ptr(), gw[1].data_ptr(), gw[2].data_ptr(), prec, st)
+                                        g_enc.data_ptr(), None, None, 0.0, 0, None, gw[0].data_ptr(), gw[1].data_ptr(), gw[2].data_ptr(), prec, st)
     _lib.check(rc, "bwd")
 def timeit(fn, n=10):
     ts = []
