@@ -182,27 +182,40 @@ def cpu_baseline_sample(budget_s=20.0):
 
 
 # ----------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of one head_forward_kernel launch inside the training step
+# (ncu --set full, profiles/r1_head_forward_ncu.md); the 50 MB table is L2-resident, so this is far below the
+# algorithmic bytes
+HEAD_FWD_TRAFFIC = None
+
+
 def algorithmic_bytes_encode(B, L, C, D=3, table_bytes=4, out_bytes=4):
     """per sample 4*D + L*2^D*C*s_p + L*C*s_o."""
     return B * (4 * D + L * (1 << D) * C * table_bytes + L * C * out_bytes)
 
 
-# name -> (C-ABI entry watched, predicate on the launch info, algorithmic bytes per launch (SURVEY §8 d4), description)
+# name -> (C-ABI entry watched, predicate on the launch info, algorithmic bytes per launch (SURVEY §8 d4), description,
+#          DRAM traffic per launch from the committed `ncu --set full` capture (profiles/), or None)
+B_FINAL = N_RAYS * NUM_STEPS[2]
 ROOFLINE_KERNELS = {
-    "main_backward": ("grid_encode_backward", lambda i: i.get("L") == 16 and i.get("B") == N_RAYS * NUM_STEPS[2],
-                      algorithmic_bytes_encode(N_RAYS * NUM_STEPS[2], 16, 2),
-                      "grid_backward_kernel<float,3,2,4,2> (main grid L16 F2 T2^19, B=262144): 1164 B/sample"),
-    "main_forward": ("grid_encode_forward", lambda i: i.get("L") == 16 and i.get("B") == N_RAYS * NUM_STEPS[2],
-                     algorithmic_bytes_encode(N_RAYS * NUM_STEPS[2], 16, 2),
-                     "grid_forward_kernel<float,3,2,4,2> (main grid L16 F2 T2^19, B=262144): 1164 B/sample"),
+    "head_forward": ("field_head_forward", lambda i: i.get("B") == B_FINAL,
+                     B_FINAL * (12 + 16 * 8 * 8 + 64 + 640),
+                     "head_forward_kernel (final level: hash-grid gather L16 F2 T2^19 + 32-64-64-16 MLP on tcgen05, "
+                     "B=262144): 12 B in + 1024 B gathered + 64 B out + 640 B saved activations per sample",
+                     HEAD_FWD_TRAFFIC),
+    "head_backward": ("field_head_backward", lambda i: i.get("B") == B_FINAL, B_FINAL * (640 + 64 + 128),
+                      "head_backward_kernel (MLP data + weight gradients on tcgen05, B=262144): 640 B saved activations "
+                      "+ 64 B in + 128 B out per sample", None),
+    "main_backward": ("grid_encode_backward", lambda i: i.get("L") == 16 and i.get("B") == B_FINAL,
+                      algorithmic_bytes_encode(B_FINAL, 16, 2),
+                      "grid_backward_kernel<float,3,2,4,2> (main grid L16 F2 T2^19, B=262144): 1164 B/sample", None),
     "prop0_forward": ("prop_density_forward", lambda i: i.get("B") == N_RAYS * NUM_STEPS[0],
-                      N_RAYS * NUM_STEPS[0] * (12 + 5 * 8 * 8 + 4),
+                      N_RAYS * NUM_STEPS[0] * (12 + 5 * 8 * 8 + 4 + 40),
                       "prop_forward_kernel<5> (proposal level 0: encode L5 F2 + MLP + trunc_exp fused, B=1048576): "
-                      "12 B in + 320 B gathered + 4 B out per sample"),
+                      "12 B in + 320 B gathered + 4 B out + 40 B saved per sample", None),
     "prop0_backward": ("prop_density_backward", lambda i: i.get("B") == N_RAYS * NUM_STEPS[0],
-                       N_RAYS * NUM_STEPS[0] * (12 + 4 + 2 * 5 * 8 * 8),
-                       "prop_backward_kernel<5> (proposal level 0 backward: recompute + scatter, B=1048576): "
-                       "16 B in + 320 B gathered + 320 B reduced per sample"),
+                       N_RAYS * NUM_STEPS[0] * (12 + 4 + 40 + 5 * 8 * 8),
+                       "prop_backward_kernel<5> (proposal level 0 backward: MLP recompute + warp-aggregated scatter, "
+                       "B=1048576): 56 B in + 320 B reduced per sample", None),
 }
 
 
@@ -268,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
     # dominant kernel of the step, picked from the ncu launch list (profiles/): see ROOFLINE_KERNELS.  Kernels inside a
     # graph cannot be bracketed by events, so the SAME step is replayed eagerly (same buffers, same kernels, same L2
     # flush) right after the timed region with CUDA events around the watched launches on the launching stream.
-    watch_name, pred, alg_bytes, watch_desc = ROOFLINE_KERNELS[args.roofline_kernel]
+    watch_name, pred, alg_bytes, watch_desc, traffic = ROOFLINE_KERNELS[args.roofline_kernel]
     plan = trainer.plan(N_RAYS)
     if plan is not None:
         plan.use_graph = False
@@ -298,7 +311,7 @@ def run_ours(args, rank, world, local_rank):
         achieved = alg / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": watch_desc,
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                    "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
                     "avg_launch_ms": avg_ms, "launches_timed": len(spans),
                     "timing": "CUDA events around the kernel's launches in an eager replay of the same step after the "
                               "timed region (the timed region itself replays a CUDA graph)"}
@@ -332,7 +345,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
-    ap.add_argument("--roofline-kernel", default="prop0_backward", choices=sorted(ROOFLINE_KERNELS))
+    ap.add_argument("--roofline-kernel", default="head_forward", choices=sorted(ROOFLINE_KERNELS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 

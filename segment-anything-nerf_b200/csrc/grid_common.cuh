@@ -159,6 +159,25 @@ __device__ __forceinline__ bool warp_run_reduce(float (&v)[NV], const uint32_t (
     return head;
 }
 
+// Pair-merged gather for fp32 tables with two features per row: the two corners along the first dimension are adjacent
+// rows whenever the lower one is even (dense levels: stride 1; hashed levels: prime 1, so x ^ h and (x + 1) ^ h differ in
+// bit 0 only); both then sit in ONE aligned 16-byte slot and come back from one 128-bit load.  Random 8-byte gathers are
+// bound by L1 wavefronts (one 128-byte line per lane and instruction), so every merged pair saves a quarter of a level's
+// cost.  `slice` = first row of the level (levels start at multiples of 8 rows, grid.py:130, so slots stay aligned).
+// Values and their use order are unchanged: results stay bit-identical.
+__device__ __forceinline__ void gather_pair_f2(const float* __restrict__ slice, uint32_t r0, uint32_t r1, float2& v0,
+                                               float2& v1) {
+    if ((r0 ^ r1) == 1u) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(slice + (size_t)(r0 & ~1u) * 2));
+        const bool lower = (r0 & 1u) == 0u;
+        v0 = lower ? make_float2(t.x, t.y) : make_float2(t.z, t.w);
+        v1 = lower ? make_float2(t.z, t.w) : make_float2(t.x, t.y);
+    } else {
+        v0 = __ldg(reinterpret_cast<const float2*>(slice + (size_t)r0 * 2));
+        v1 = __ldg(reinterpret_cast<const float2*>(slice + (size_t)r1 * 2));
+    }
+}
+
 // Inclusive range test of the reference (gridencoder.cu:109): NaN passes.
 template <uint32_t D>
 __device__ __forceinline__ bool out_of_range(const float (&x)[D]) {

@@ -203,9 +203,14 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
 #pragma unroll
                     for (uint32_t d = 0; d < 3; ++d) frac[q][d] = cell.f[d];
 #pragma unroll
-                    for (uint32_t k = 0; k < 8; ++k)
-                        val[q][k] = zero ? make_float2(0.0f, 0.0f)
-                                         : __ldg(reinterpret_cast<const float2*>(table + (base + corner_row<3>(geo, cell, k)) * 2));
+                    for (uint32_t k = 0; k < 8; k += 2) {
+                        if (zero) {
+                            val[q][k] = val[q][k + 1] = make_float2(0.0f, 0.0f);
+                        } else {
+                            gather_pair_f2(table + base * 2, corner_row<3>(geo, cell, k), corner_row<3>(geo, cell, k + 1),
+                                           val[q][k], val[q][k + 1]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (uint32_t q = 0; q < kLevelsPerThread; ++q) {

@@ -41,7 +41,8 @@ __device__ __forceinline__ void prop_encode(const PropParams& p, const float (&x
 #pragma unroll
             for (uint32_t d = 0; d < 3; ++d) frac[l][d] = cell.f[d];
 #pragma unroll
-            for (uint32_t k = 0; k < 8; ++k)
+            for (uint32_t k = 0; k < 8; ++k)   // plain 8-byte gathers: these 3 MB tables hit L1/L2; the kernel is issue-bound and
+                                               // the pair-merged form (grid_common.cuh: gather_pair_f2) costs it 30 %
                 val[l][k] = __ldg(reinterpret_cast<const float2*>(table + (base + corner_row<3>(geo, cell, k)) * 2));
         } else {
 #pragma unroll
