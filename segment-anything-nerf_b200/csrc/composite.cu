@@ -113,15 +113,31 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_forward_kernel(
             if constexpr (KC > 0) {
                 const uint32_t cnt = min(32u, n - base);
                 const float* rows = a.feats + (start + base) * a.fs;
-#pragma unroll 4
-                for (uint32_t j = 0; j < cnt; ++j) {
-                    const float wj = __shfl_sync(kFull, s.w, j);
-                    if (wj == 0.0f) continue;  // terminated / transparent sample: row never read
-                    const float* row = rows + (size_t)j * a.fs;
+                // rows are fetched in batches of U independent loads per lane before the first FMA (memory-level
+                // parallelism: a ray is a strictly sequential sum); the summation order is unchanged
+                constexpr int U = (KC <= 2) ? 8 : (KC <= 4) ? 4 : 2;
+                for (uint32_t j0 = 0; j0 < cnt; j0 += U) {
+                    float wj[U], v[U][KC];
 #pragma unroll
-                    for (int q = 0; q < KC; ++q) {
-                        const uint32_t c = lane + 32u * q;
-                        if (c < C) acc[q] = __fmaf_rn(wj, __ldg(row + c), acc[q]);
+                    for (int u = 0; u < U; ++u) {
+                        wj[u] = __shfl_sync(kFull, s.w, (j0 + u) & 31u);
+                        if (j0 + u >= cnt) wj[u] = 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float* row = rows + (size_t)(j0 + u) * a.fs;
+#pragma unroll
+                        for (int q = 0; q < KC; ++q) {
+                            const uint32_t c = lane + 32u * q;
+                            // terminated / transparent sample (w = 0): row never read
+                            v[u][q] = (wj[u] != 0.0f && c < C) ? __ldg(row + c) : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (wj[u] == 0.0f) continue;
+#pragma unroll
+                        for (int q = 0; q < KC; ++q) acc[q] = __fmaf_rn(wj[u], v[u][q], acc[q]);
                     }
                 }
             } else {
@@ -223,22 +239,34 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_backward_kernel(
                 const float* rows = a.feats + (start + base) * a.fs;
                 float* grows = grad_feats ? grad_feats + (start + base) * a.gfs : nullptr;
                 float part[32];
+                // batches of U rows: all loads of a batch are issued before its FMAs and stores (the stores may alias
+                // the loads as far as the compiler knows, so without batching every row is a full memory round trip)
+                constexpr uint32_t U = (KC <= 2) ? 8 : (KC <= 4) ? 4 : 1;      // KC = 8 is register-bound already
 #pragma unroll
-                for (uint32_t j = 0; j < 32; ++j) {
-                    float p = 0.0f;
-                    if (j < cnt) {
-                        const float wj = __shfl_sync(kFull, s.w, j);
-                        const float* row = rows + (size_t)j * a.fs;
+                for (uint32_t j0 = 0; j0 < 32; j0 += U) {
+                    float v[U][KC];
+#pragma unroll
+                    for (uint32_t u = 0; u < U; ++u) {
+                        const float* row = rows + (size_t)(j0 + u) * a.fs;
 #pragma unroll
                         for (int q = 0; q < KC; ++q) {
                             const uint32_t c = lane + 32u * q;
-                            if (c < C) {
-                                p = __fmaf_rn(go[q], __ldg(row + c), p);
-                                if (grows) grows[(size_t)j * a.gfs + c] = wj * go[q];
-                            }
+                            v[u][q] = (j0 + u < cnt && c < C) ? __ldg(row + c) : 0.0f;
                         }
                     }
-                    part[j] = p;
+#pragma unroll
+                    for (uint32_t u = 0; u < U; ++u) {
+                        const uint32_t j = j0 + u;
+                        const float wj = __shfl_sync(kFull, s.w, j);
+                        float p = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < KC; ++q) {
+                            const uint32_t c = lane + 32u * q;
+                            p = __fmaf_rn(go[q], v[u][q], p);
+                            if (grows && j < cnt && c < C) grows[(size_t)j * a.gfs + c] = wj * go[q];
+                        }
+                        part[j] = p;
+                    }
                 }
                 dot = butterfly_transpose_sum(part, lane);
             } else {
