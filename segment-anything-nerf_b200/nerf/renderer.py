@@ -274,6 +274,9 @@ class NeRFRenderer(nn.Module):
         if bg_color is None:
             bg_color = 1
         common = dict(cam_near_far=cam_near_far, contract=self.opt.contract, bound=float(self.bound))
+        # the reference evaluates the SAM branch (s_grid, 128-channel compositing, samvit_mlp) for every ray of every call
+        # and drops the result unless return_feats > 0 (renderer.py:302-303, 367-389); skipping it then changes nothing
+        want_sam = self.opt.with_sam and (return_feats > 0 or self.training)
         all_bins, all_weights = [], []
         bins = weights = None
         last = len(steps) - 1
@@ -294,7 +297,7 @@ class NeRFRenderer(nn.Module):
                     head, deltas, t_mid, opaque_last, self.t_thresh)
                 sh = self.view_encoder(rays_d)                                    # once per ray
                 f_image = torch.cat([geo_sum, weights_sum.unsqueeze(-1) * sh], dim=-1)   # = sum_i w_i [geo_i, sh]
-                if self.opt.with_sam:
+                if want_sam:
                     features = self.features_unit(x01)                            # [N,T,128]
             if self.training:
                 all_bins.append(bins)
@@ -311,7 +314,7 @@ class NeRFRenderer(nn.Module):
                 results["distort_loss"] = fused.distort_loss(bins, weights)
         image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
         results.update(weights_sum=weights_sum, depth=depth, image=image, n_alive=n_alive)
-        if self.opt.with_sam:
+        if want_sam:
             f_sam = composite(sigmas, deltas, t_mid, features, last_sample_opaque=opaque_last,
                               t_thresh=self.t_thresh)[3]
             if self.opt.sam_use_view_direction:

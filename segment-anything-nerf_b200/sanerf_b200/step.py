@@ -104,10 +104,8 @@ class FusedRGBStep:
         m, lib, N = self.model, _lib.load(), self.N
         st = _lib.current_stream(self.dev)
         span, check, ptr = _lib.stats.span, _lib.check, _lib.ptr
-        aabb = m.aabb_train
+        aabb = m.aabb_train if m.training else m.aabb_infer
         bound, contract, min_near = float(m.bound), int(bool(m.opt.contract)), float(m.min_near)
-        lam_p = float(m.opt.lambda_proposal) if update_proposal else 0.0
-        lam_d = float(m.opt.lambda_distort)
         self.loss.zero_()
         if self.perturb:
             self.noise_flat.uniform_()
@@ -343,3 +341,96 @@ class FusedRGBStep:
                 self._update_rest()
             self.pending_main = True
         return self.loss[0]
+
+
+class FusedRGBFrame(FusedRGBStep):
+    """Forward-only sibling of ``FusedRGBStep`` for inference: rays [N,3] -> image [N,3], depth [N], weights_sum [N] in
+    12 launches (3 samplers, 2 proposal densities + 2 compositings, field head on tcgen05 without saved activations,
+    fused trunc_exp + compositing, fused SH + view MLP + sigmoid + background), replayed as one CUDA graph.  It is what
+    the interactive frame (nerf/utils.py:1647-1712 ``test_gui``, renderer.py:185-219 staged ``render``) reduces to for
+    the RGB pass; a SAM model's feature branch is not touched (its outputs are not part of an RGB frame)."""
+
+    def __init__(self, model, n_rays, use_graph=True, bg_color=1.0):
+        opt = model.opt
+        if opt.with_mask or opt.sum_after_mlp:
+            raise UnsupportedConfig("FusedRGBFrame covers deferred shading without mask heads")
+        if not field_head_supported(model.grid, model.grid_mlp):
+            raise UnsupportedConfig("FusedRGBFrame needs the reference's main grid + grid_mlp shapes")
+        for enc, mlp in zip(model.prop_encoders, model.prop_mlp):
+            if not prop_density_supported(enc, mlp):
+                raise UnsupportedConfig("FusedRGBFrame needs the reference's proposal network shapes")
+        vw = [l.weight for l in model.view_mlp.net]
+        if [tuple(w.shape) for w in vw] != [(32, 31), (32, 32), (3, 32)] or any(l.bias is not None for l in model.view_mlp.net):
+            raise UnsupportedConfig("FusedRGBFrame needs the reference's view_mlp (31 -> 32 -> 32 -> 3, no bias)")
+        self.model, self.world_size = model, 1
+        self.N, self.steps = int(n_rays), [int(t) for t in opt.num_steps]
+        if len(self.steps) != 3:
+            raise UnsupportedConfig("FusedRGBFrame expects two proposal levels and one final level")
+        self.perturb, self.bg = False, float(bg_color)
+        self.precision = PRECISION_IDS[model.mlp_precision]
+        self.opaque = int(opt.background == "last_sample")
+        self.use_graph = bool(use_graph)
+        dev = self.dev = next(model.parameters()).device
+        N = self.N
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.rays_o, self.rays_d = torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32)
+        self.noise = [None] * 3
+        self.lv = []
+        for t in self.steps:
+            self.lv.append(dict(T=t, bins=torch.empty(N, t + 1, **f32), t_mid=torch.empty(N, t, **f32),
+                                deltas=torch.empty(N, t, **f32), x01=torch.empty(N, t, 3, **f32),
+                                sigma=torch.empty(N, t, **f32), weights=torch.empty(N, t, **f32), enc=None,
+                                ws=torch.empty(N, **f32), depth=torch.empty(N, **f32)))
+        self.head = torch.empty(N * self.steps[2], 16, **f32)
+        self.geo_sum = torch.empty(N, 15, **f32)
+        self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)
+        self.image = torch.empty(N, 3, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.graph = None
+        self.eager_runs = 0
+
+    def _launch_render(self):
+        m, lib, N = self.model, _lib.load(), self.N
+        self._launch_front(False)
+        st = _lib.current_stream(self.dev)
+        span, check = _lib.stats.span, _lib.check
+        L = self.lv[2]
+        T, B = L["T"], N * L["T"]
+        g = m.grid
+        w1, w2, w3 = (l.weight for l in m.grid_mlp.net)
+        with span("field_head_forward", B=B):
+            rc = lib.sanerf_field_head_forward(L["x01"].data_ptr(), g.embeddings.data_ptr(), g.offsets.data_ptr(),
+                                               float(np.log2(g.per_level_scale)), int(g.base_resolution), None, w1.data_ptr(),
+                                               w2.data_ptr(), w3.data_ptr(), B, None, None, None, self.head.data_ptr(),
+                                               self.precision, st)
+        check(rc, "field_head_forward")
+        with span("head_composite_forward", N=N, T=T):
+            rc = lib.sanerf_head_composite_forward(self.head.data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), N, T,
+                                                   self.opaque, float(m.t_thresh), None, L["weights"].data_ptr(),
+                                                   L["ws"].data_ptr(), L["depth"].data_ptr(), self.geo_sum.data_ptr(),
+                                                   self.n_alive.data_ptr(), st)
+        check(rc, "head_composite_forward")
+        v1, v2, v3 = (l.weight for l in m.view_mlp.net)
+        with span("view_head", N=N):
+            rc = lib.sanerf_view_head(self.geo_sum.data_ptr(), L["ws"].data_ptr(), self.rays_d.data_ptr(), None, v1.data_ptr(),
+                                      v2.data_ptr(), v3.data_ptr(), self.bg, 1.0, N, self.image.data_ptr(), None, None, None,
+                                      None, None, None, st)
+        check(rc, "view_head")
+
+    @torch.no_grad()
+    def __call__(self, rays_o, rays_d):
+        """Returns views of static buffers (image [N,3], depth [N], weights_sum [N], n_alive [N]): copy before the next call."""
+        self.rays_o.copy_(rays_o, non_blocking=True)
+        self.rays_d.copy_(rays_d, non_blocking=True)
+        with torch.cuda.device(self.dev):
+            if self.use_graph and self.eager_runs >= 1:
+                if self.graph is None:
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph):
+                        self._launch_render()
+                self.graph.replay()
+            else:
+                self.eager_runs += 1
+                self._launch_render()
+        L = self.lv[2]
+        return {"image": self.image, "depth": L["depth"], "weights_sum": L["ws"], "n_alive": self.n_alive}

@@ -128,12 +128,29 @@ class SAMTrainer:
         return loss.detach()
 
 
+_FRAME_PLANS = {}
+
+
 @torch.no_grad()
-def render_frame(model, rays_o, rays_d, feat_rays_o=None, feat_rays_d=None, h=64, w=64):
-    """Interactive frame (nerf/utils.py:1647-1712): staged full-resolution RGB + depth, plus the low-resolution
-    256-d SAM feature map when feature rays are given."""
+def render_frame(model, rays_o, rays_d, feat_rays_o=None, feat_rays_d=None, h=64, w=64, fused=True):
+    """Interactive frame (nerf/utils.py:1647-1712): full-resolution RGB + depth, plus the low-resolution 256-d SAM
+    feature map when feature rays are given.  The RGB pass is ONE CUDA-graph replay of the hand-scheduled forward
+    (``FusedRGBFrame``) when the model has the reference's shapes, else the staged renderer (renderer.py:185-219)."""
     model.eval()
-    out = model.render(rays_o, rays_d, staged=True, bg_color=1, perturb=False)
+    plan = None
+    if fused and rays_o.is_cuda and getattr(model, "tc_head", False):
+        from .step import FusedRGBFrame, UnsupportedConfig
+        key = (id(model), rays_o.shape[0])
+        if key not in _FRAME_PLANS:
+            try:
+                _FRAME_PLANS[key] = FusedRGBFrame(model, rays_o.shape[0])
+            except UnsupportedConfig:
+                _FRAME_PLANS[key] = None
+        plan = _FRAME_PLANS[key]
+    if plan is not None:
+        out = plan(rays_o, rays_d)
+    else:
+        out = model.render(rays_o, rays_d, staged=True, bg_color=1, perturb=False)
     res = {"image": out["image"], "depth": out["depth"]}
     if feat_rays_o is not None:
         f = model.render(feat_rays_o, feat_rays_d, staged=False, bg_color=1, perturb=False, return_feats=1, H=h, W=w)

@@ -81,3 +81,32 @@ def test_trainer_uses_fused_step_and_learns(cuda):
     after = model.grid.embeddings.detach().clone()
     trainer.flush()
     assert torch.equal(after, model.grid.embeddings)
+
+
+@pytest.mark.parametrize("with_sam", [False, True])
+def test_fused_frame_equals_staged_render(cuda, with_sam):
+    """Forward-only hand-scheduled frame (one CUDA graph) == the renderer's staged evaluation, RGB / depth / weights_sum."""
+    from nerf.network import NeRFNetwork
+    from sanerf_b200.step import FusedRGBFrame
+    from sanerf_b200.train import default_opt, render_frame
+    torch.manual_seed(2)
+    model = NeRFNetwork(default_opt(with_sam=with_sam, max_ray_batch=300)).cuda().eval()
+    with torch.no_grad():
+        for enc in [model.grid, *model.prop_encoders]:
+            enc.embeddings.uniform_(-0.5, 0.5)
+    g = torch.Generator().manual_seed(9)
+    o = (torch.rand(1000, 3, generator=g) - 0.5).cuda()
+    d = (torch.randn(1000, 3, generator=g)).cuda()                      # un-normalised, as get_rays produces them
+    with torch.no_grad():
+        ref = model.render(o, d, staged=True, bg_color=1, perturb=False)
+    plan = FusedRGBFrame(model, 1000)
+    for _ in range(3):                                                   # eager, capture, replay
+        out = plan(o, d)
+        torch.testing.assert_close(out["image"], ref["image"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(out["depth"], ref["depth"], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(out["weights_sum"], ref["weights_sum"], rtol=1e-5, atol=1e-6)
+    assert plan.graph is not None
+    res = render_frame(model, o, d, o[:64] if with_sam else None, d[:64] if with_sam else None, 8, 8)
+    torch.testing.assert_close(res["image"], ref["image"], rtol=1e-5, atol=1e-6)
+    if with_sam:
+        assert res["samvit"].shape == (8, 8, 256)
