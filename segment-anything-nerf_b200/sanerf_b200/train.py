@@ -101,10 +101,12 @@ class SAMTrainer:
     """Stage-2 step on frozen stage-1 parameters: render the [h,w] low-resolution rays' 256-d feature map and
     regress a target feature map (nerf/utils.py:1095-1106; the ViT-H target is replaced by a given tensor)."""
 
-    def __init__(self, model, lr=1e-2, iters=5000, world_size=1):
+    def __init__(self, model, lr=1e-2, iters=5000, world_size=1, use_graph=True):
         assert model.opt.with_sam
         self.model = model.train()
         self.world_size = world_size
+        self.use_graph = bool(use_graph)
+        self._graphs = {}                                 # (n_rays, h, w, target shape) -> captured step
         trainable = set()
         for m in (model.s_grid, model.samvit_mlp):
             trainable.update(id(p) for p in m.parameters())
@@ -113,8 +115,7 @@ class SAMTrainer:
         self.optimizer = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=lr, eps=1e-15,
                                    decay_iters=iters)
 
-    def step(self, rays_o, rays_d, target, h, w):
-        """target: [1, 256, H_t, W_t]; prediction is bilinearly resized to it (nerf/utils.py:1100-1106)."""
+    def _forward_backward(self, rays_o, rays_d, target, h, w):
         out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=False, update_proposal=False,
                                 return_feats=1, H=h, W=w)
         pred = out["samvit"].permute(2, 0, 1).unsqueeze(0)
@@ -122,10 +123,42 @@ class SAMTrainer:
             pred = F.interpolate(pred, target.shape[-2:], mode="bilinear")
         loss = F.mse_loss(pred, target)
         loss.backward()
-        if self.world_size > 1:
-            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
-        self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
         return loss.detach()
+
+    def step(self, rays_o, rays_d, target, h, w):
+        """target: [1, 256, H_t, W_t]; prediction is bilinearly resized to it (nerf/utils.py:1100-1106).
+
+        The step is autograd-driven (the 163 -> 256 x 5 SkipConnMLP + LayerNorm run on cuBLAS); after one eager call
+        per input shape it is captured into a CUDA graph and replayed (static input buffers), which removes the
+        ~150 host-side launches that otherwise dominate this 4096-ray step."""
+        dev = self.optimizer.flat_param.device
+        key = (tuple(rays_o.shape), h, w, tuple(target.shape))
+        entry = self._graphs.get(key)
+        if not self.use_graph or self.world_size > 1 or entry is None:
+            rays_o, rays_d, target = (t.to(dev, non_blocking=True) for t in (rays_o, rays_d, target))
+            loss = self._forward_backward(rays_o, rays_d, target, h, w)
+            if self.world_size > 1:
+                dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+            self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
+            if self.use_graph and self.world_size == 1 and entry is None:
+                self._graphs[key] = "warm"                # next call with this shape captures
+            return loss
+        if entry == "warm":
+            static = [torch.empty_like(t, device=dev) for t in (rays_o, rays_d, target)]
+            for buf, src in zip(static, (rays_o, rays_d, target)):
+                buf.copy_(src)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self._forward_backward(static[0], static[1], static[2], h, w)
+                self.optimizer.step(grad_scale=1.0, zero_grad=True)
+            self._graphs[key] = (graph, static, loss)
+            graph.replay()                                # capture does not execute the work
+            return loss
+        graph, static, loss = entry
+        for buf, src in zip(static, (rays_o, rays_d, target)):
+            buf.copy_(src, non_blocking=True)
+        graph.replay()
+        return loss
 
 
 _FRAME_PLANS = {}

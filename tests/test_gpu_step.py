@@ -110,3 +110,27 @@ def test_fused_frame_equals_staged_render(cuda, with_sam):
     torch.testing.assert_close(res["image"], ref["image"], rtol=1e-5, atol=1e-6)
     if with_sam:
         assert res["samvit"].shape == (8, 8, 256)
+
+
+def test_sam_trainer_graph_replay_equals_eager(cuda):
+    """Stage-2 step (autograd + cuBLAS MLP) captured as a CUDA graph == the same step run eagerly."""
+    from nerf.network import NeRFNetwork
+    from sanerf_b200.train import SAMTrainer, default_opt
+    torch.manual_seed(4)
+    model_a = NeRFNetwork(default_opt(with_sam=True)).cuda()
+    with torch.no_grad():
+        for enc in [model_a.grid, *model_a.prop_encoders, model_a.s_grid]:
+            enc.embeddings.uniform_(-0.5, 0.5)
+    model_b = copy.deepcopy(model_a)
+    ta, tb = SAMTrainer(model_a, use_graph=True), SAMTrainer(model_b, use_graph=False)
+    g = torch.Generator().manual_seed(5)
+    o = (torch.rand(64, 3, generator=g) - 0.5).cuda()
+    d = torch.nn.functional.normalize(torch.randn(64, 3, generator=g), dim=-1).cuda()
+    target = torch.randn(1, 256, 8, 8, generator=g).cuda()
+    for i in range(5):
+        la, lb = ta.step(o, d, target, 8, 8).clone(), tb.step(o, d, target, 8, 8).clone()
+        torch.testing.assert_close(la, lb, rtol=1e-4, atol=1e-6)
+    assert any(isinstance(v, tuple) for v in ta._graphs.values()) and int(ta.optimizer.step_count) == 5
+    for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
+    assert not model_a.grid.embeddings.requires_grad and model_a.s_grid.embeddings.requires_grad
