@@ -85,6 +85,8 @@ class FusedRGBStep:
         self.side_stream = torch.cuda.Stream(dev)
         self.update_stream = torch.cuda.Stream(dev)
         self.pending_main = False
+        self._works = []
+        self._main_works = []
         self.graphs = {}
         self.eager_runs = {}
         self.global_step = 0
@@ -144,8 +146,9 @@ class FusedRGBStep:
                                                       None, N, T, 0, self.opaque, 0.0, L["weights"].data_ptr(), L["ws"].data_ptr(),
                                                       L["depth"].data_ptr(), None, None, st)
                 check(rc, "composite_forward")
-    def _launch_back(self, update_proposal):
-        """Final level forward, losses, backward of everything."""
+    def _launch_back(self, update_proposal, reduce_small=False):
+        """Final level forward, losses, backward of everything (``reduce_small``: start the all-reduces of the small
+        gradient ranges as soon as they are complete)."""
         m, lib, N = self.model, _lib.load(), self.N
         st = _lib.current_stream(self.dev)
         span, check = _lib.stats.span, _lib.check
@@ -204,6 +207,8 @@ class FusedRGBStep:
                                                               enc.embeddings.grad.data_ptr(), mlp.net[0].weight.grad.data_ptr(),
                                                               mlp.net[1].weight.grad.data_ptr(), st2)
                     check(rc, "prop_density_backward")
+                if reduce_small:                          # proposal tables + MLPs: reduced while the final-level chain runs
+                    self._reduce_async(self._prop_start(), self.optimizer.flat_param.numel())
         # ---------------- final level: view head + photometric loss (forward and backward), distortion loss
         v1, v2, v3 = (l.weight for l in m.view_mlp.net)
         with span("view_head", N=N):
@@ -236,6 +241,8 @@ class FusedRGBStep:
                                                  g.offsets.data_ptr(), g.embeddings.grad.data_ptr(), B, 3, 2, 16, 16, S, H, None,
                                                  None, 0, 0, 0, _lib.SANERF_F32, _lib.LAYOUT_BLC, st)
         check(rc, "grid_encode_backward")
+        if reduce_small:                                  # grid_mlp + view_mlp gradients are complete: tiny reduction
+            self._reduce_async(self._main_range()[1], self._prop_start())
         if lam_p > 0:
             main.wait_stream(self.side_stream)            # join
 
@@ -247,17 +254,53 @@ class FusedRGBStep:
     def _main_range(self):
         return self.optimizer.ranges[id(self.model.grid.embeddings)]
 
-    def _update_main(self):
+    def _prop_start(self):
+        """Flat offset where the proposal networks' parameters begin (they trail the buffer: nerf/network.py declares
+        grid, grid_mlp, view_mlp, prop_encoders, prop_mlp in this order)."""
+        m = self.model
+        starts = [self.optimizer.ranges[id(p)][0] for p in [*m.prop_encoders.parameters(), *m.prop_mlp.parameters()]]
+        others = [self.optimizer.ranges[id(p)][1] for p in [m.grid.embeddings, *m.grid_mlp.parameters(), *m.view_mlp.parameters()]]
+        b0 = min(starts)
+        assert max(others) <= b0, "proposal parameters are expected to trail the flat parameter buffer"
+        return b0
+
+    def _start_main_reduce(self, chunks=1):
+        """Multi-GPU: queue the all-reduce of the main table's gradient on NCCL's stream.  (Measured at 8 GPUs: queueing
+        it right after the backward, or cutting it into chunks whose Adam overlaps the next chunk's reduction, is not
+        faster than one all-reduce at the start of the next step - 59.2 vs 61.4 M rays/s.)"""
         a, b = self._main_range()
-        if self.world_size > 1:
-            dist.all_reduce(self.optimizer.flat_grad[a:b], op=dist.ReduceOp.SUM)
-        self.optimizer.apply(a, b, grad_scale=1.0 / self.world_size, zero_grad=True)
+        step = ((b - a + chunks - 1) // chunks + 3) // 4 * 4
+        cuts = [(lo, min(lo + step, b)) for lo in range(a, b, step)]
+        self._main_works = [(lo, hi, dist.all_reduce(self.optimizer.flat_grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                            for lo, hi in cuts]
+
+    def _update_main(self):
+        """Adam of the main table (after its all-reduce, multi-GPU: each chunk's update starts as soon as its own
+        reduction has landed, overlapping the next chunk's reduction)."""
+        a, b = self._main_range()
+        if self.world_size == 1:
+            self.optimizer.apply(a, b, grad_scale=1.0, zero_grad=True)
+            return
+        if not self._main_works:
+            self._start_main_reduce()
+        for lo, hi, w in self._main_works:
+            w.wait()
+            self.optimizer.apply(lo, hi, grad_scale=1.0 / self.world_size, zero_grad=True)
+        self._main_works = []
+
+    def _reduce_async(self, lo, hi):
+        if self.world_size > 1 and hi > lo:
+            self._works.append(dist.all_reduce(self.optimizer.flat_grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
 
     def _update_rest(self):
         a, b = self._main_range()
         n = self.optimizer.flat_param.numel()
         assert a == 0, "the main table is expected to lead the flat parameter buffer"
-        if self.world_size > 1:
+        if self._works:                                    # reductions of the small ranges, started inside the backward
+            for w in self._works:
+                w.wait()
+            self._works = []
+        elif self.world_size > 1:
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
         self.optimizer.schedule()
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
@@ -277,7 +320,7 @@ class FusedRGBStep:
         return self.loss[0]
 
     def _whole_step(self, update_proposal):
-        """Single-GPU step on the current stream: deferred main-table update || front, then back, then the small update."""
+        """One step on the current stream: deferred main-table update || front, then back, then the small update."""
         main = torch.cuda.current_stream(self.dev)
         upd = self.update_stream
         upd.wait_stream(main)
@@ -285,10 +328,14 @@ class FusedRGBStep:
             self._update_main()                            # previous step's gradient (zero before the first step)
         self._launch_front(update_proposal)
         main.wait_stream(upd)
-        self._launch_back(update_proposal)
+        # (starting the small ranges' all-reduces inside the backward was measured slower: NCCL's CTAs spin on SMs the
+        # persistent one-CTA-per-SM field-head kernels count on, so they stay at the end of the step)
+        self._launch_back(update_proposal, reduce_small=False)
         self._update_rest()
 
     def _graphs(self, update_proposal):
+        """Single GPU: the whole step is one graph.  Multi-GPU: the forward / backward halves are two graphs and the
+        NCCL all-reduces stay eager between them (capturing them into one graph works but measured 7 % slower at 2 GPUs)."""
         key = bool(update_proposal)
         if key not in self.graphs:
             if self.world_size == 1:
@@ -296,12 +343,12 @@ class FusedRGBStep:
                 with torch.cuda.graph(g):
                     self._whole_step(update_proposal)
                 self.graphs[key] = (g,)
-            else:                                          # NCCL stays outside the graphs
+            else:
                 gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gf):
                     self._launch_front(update_proposal)
                 with torch.cuda.graph(gb):
-                    self._launch_back(update_proposal)
+                    self._launch_back(update_proposal, reduce_small=False)
                 self.graphs[key] = (gf, gb)
         return self.graphs[key]
 
@@ -318,26 +365,19 @@ class FusedRGBStep:
             graphed = self.use_graph and self.eager_runs.get(key, 0) >= 1   # first step of each variant runs eagerly (warm-up)
             if not graphed:
                 self.eager_runs[key] = self.eager_runs.get(key, 0) + 1
-            if self.world_size == 1:
-                if graphed:
-                    self._graphs(update_proposal)[0].replay()
-                else:
-                    self._whole_step(update_proposal)
+                self._whole_step(update_proposal)
+            elif self.world_size == 1:
+                self._graphs(update_proposal)[0].replay()
             else:
                 main = torch.cuda.current_stream(self.dev)
                 upd = self.update_stream
                 upd.wait_stream(main)
                 with torch.cuda.stream(upd):
                     self._update_main()                    # all-reduce + Adam of the main table, hidden behind the front
-                if graphed:
-                    gf, gb = self._graphs(update_proposal)
-                    gf.replay()
-                    main.wait_stream(upd)
-                    gb.replay()
-                else:
-                    self._launch_front(update_proposal)
-                    main.wait_stream(upd)
-                    self._launch_back(update_proposal)
+                gf, gb = self._graphs(update_proposal)
+                gf.replay()
+                main.wait_stream(upd)
+                gb.replay()
                 self._update_rest()
             self.pending_main = True
         return self.loss[0]
