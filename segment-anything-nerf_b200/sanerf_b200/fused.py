@@ -377,7 +377,9 @@ class FusedAdam:
     def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
-        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]     # keep every view 16-byte aligned
+        # every slot is a multiple of 32 elements: views stay 16-byte aligned and any range of whole slots splits into
+        # 2 / 4 / 8 equal, 16-byte-aligned shards (reduce-scatter + sharded update + all-gather, sanerf_b200/step.py)
+        sizes = [(p.numel() + 31) // 32 * 32 for p in self.params]
         total = sum(sizes)
         self.flat_param = torch.zeros(total, device=dev)
         self.flat_grad = torch.zeros(total, device=dev)
