@@ -280,16 +280,9 @@ class FusedRGBStep:
             dist.all_reduce(opt.flat_grad[a:b], op=dist.ReduceOp.SUM)
             opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True)
             return
-        shard = (b - a) // world
-        assert shard * world == b - a and shard % 4 == 0, "flat slots are multiples of 32 elements"
-        lo, hi = a + rank * shard, a + (rank + 1) * shard
-        dist.reduce_scatter_tensor(opt.flat_grad[lo:hi], opt.flat_grad[a:b], op=dist.ReduceOp.SUM)      # in place
-        opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True)
-        if lo > a:
-            opt.flat_grad[a:lo].zero_()
-        if hi < b:
-            opt.flat_grad[hi:b].zero_()
-        dist.all_gather_into_tensor(opt.flat_param[a:b], opt.flat_param[lo:hi])                          # in place
+        from .parallel import sharded_update
+        sharded_update(opt.flat_param, opt.flat_grad, a, b,
+                       lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True), world, rank)
 
     def _reduce_async(self, lo, hi):
         if self.world_size > 1 and hi > lo:

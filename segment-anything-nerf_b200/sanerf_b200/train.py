@@ -191,22 +191,4 @@ def render_frame(model, rays_o, rays_d, feat_rays_o=None, feat_rays_d=None, h=64
     return res
 
 
-def shard_rays(n_total, rank, world_size):
-    """Contiguous [start, stop) slice of ``n_total`` rays / pixels owned by ``rank`` (tiles for inference,
-    ray shards for training); sizes differ by at most one."""
-    base, rem = divmod(n_total, world_size)
-    start = rank * base + min(rank, rem)
-    return start, start + base + (1 if rank < rem else 0)
-
-
-def gather_frame(local, n_total, rank, world_size):
-    """Inference: every rank renders its tile; one all_gather stitches [rays, C] tensors."""
-    if world_size == 1:
-        return local
-    sizes = [shard_rays(n_total, r, world_size) for r in range(world_size)]
-    longest = max(b - a for a, b in sizes)
-    pad = torch.zeros(longest, *local.shape[1:], device=local.device, dtype=local.dtype)
-    pad[:local.shape[0]] = local
-    parts = [torch.empty_like(pad) for _ in range(world_size)]
-    dist.all_gather(parts, pad)
-    return torch.cat([p[:b - a] for p, (a, b) in zip(parts, sizes)], dim=0)
+from .parallel import gather_frame, shard_rays  # noqa: E402,F401  (re-exported: sharding helpers live in parallel.py)
