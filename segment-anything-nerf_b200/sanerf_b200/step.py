@@ -84,6 +84,7 @@ class FusedRGBStep:
         self.loss = torch.zeros(1, **f32)
         self.side_stream = torch.cuda.Stream(dev)
         self.update_stream = torch.cuda.Stream(dev)
+        self.distort_done = torch.cuda.Event()
         self.pending_main = False
         self._works = []
         self.sharded_update = True
@@ -176,9 +177,19 @@ class FusedRGBStep:
         # both levels) depends only on the three weight tensors and shares nothing with the final-level chain below except
         # the loss scalar (atomic adds), so it runs on a second stream / as a parallel branch of the captured graph
         main = torch.cuda.current_stream(self.dev)
-        if lam_p > 0:
-            side = self.side_stream
+        have_gw2 = lam_d > 0
+        side = self.side_stream
+        if lam_p > 0 or have_gw2:
             side.wait_stream(main)
+        if have_gw2:                                       # distortion loss: concurrent with the view head on the main stream
+            with torch.cuda.stream(side):
+                with span("distortion_loss", N=N, T=T):
+                    rc = lib.sanerf_distortion_loss(L["bins"].data_ptr(), L["weights"].data_ptr(), T, N, lam_d,
+                                                    self.loss.data_ptr(), L["g_weights"].data_ptr(),
+                                                    _lib.current_stream(self.dev))
+                check(rc, "distortion_loss")
+                self.distort_done.record(side)
+        if lam_p > 0:
             with torch.cuda.stream(side):
                 st2 = _lib.current_stream(self.dev)
                 for li in (0, 1):
@@ -217,13 +228,9 @@ class FusedRGBStep:
                                       self.g_geo_sum.data_ptr(), self.g_ws.data_ptr(), v1.grad.data_ptr(), v2.grad.data_ptr(),
                                       v3.grad.data_ptr(), st)
         check(rc, "view_head")
-        have_gw2 = lam_d > 0
-        if have_gw2:
-            with span("distortion_loss", N=N, T=T):
-                rc = lib.sanerf_distortion_loss(L["bins"].data_ptr(), L["weights"].data_ptr(), T, N, lam_d, self.loss.data_ptr(),
-                                                L["g_weights"].data_ptr(), st)
-            check(rc, "distortion_loss")
         # ---------------- backward: final level
+        if have_gw2:
+            main.wait_event(self.distort_done)
         with span("head_composite_backward", N=N, T=T):
             rc = lib.sanerf_head_composite_backward(self.head.data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), N, T,
                                                     self.opaque, float(m.t_thresh),
@@ -243,7 +250,7 @@ class FusedRGBStep:
         check(rc, "grid_encode_backward")
         if reduce_small:                                  # grid_mlp + view_mlp gradients are complete: tiny reduction
             self._reduce_async(self._main_range()[1], self._prop_start())
-        if lam_p > 0:
+        if lam_p > 0 or have_gw2:
             main.wait_stream(self.side_stream)            # join
 
     # ---- optimizer.  The main hash table is 89 % of the parameters and nothing before the final level's field head reads
@@ -298,7 +305,6 @@ class FusedRGBStep:
             self._works = []
         elif self.world_size > 1:
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
-        self.optimizer.schedule()
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
 
     def flush(self):
@@ -322,6 +328,7 @@ class FusedRGBStep:
         upd.wait_stream(main)
         with torch.cuda.stream(upd):
             self._update_main()                            # previous step's gradient (zero before the first step)
+            self.optimizer.schedule()                      # then this step's learning rate / bias corrections
         self._launch_front(update_proposal)
         main.wait_stream(upd)
         # (starting the small ranges' all-reduces inside the backward was measured slower: NCCL's CTAs spin on SMs the
@@ -369,7 +376,8 @@ class FusedRGBStep:
                 upd = self.update_stream
                 upd.wait_stream(main)
                 with torch.cuda.stream(upd):
-                    self._update_main()                    # all-reduce + Adam of the main table, hidden behind the front
+                    self._update_main()                    # reduce-scatter + Adam shard + all-gather, hidden behind the front
+                    self.optimizer.schedule()
                 gf, gb = self._graphs(update_proposal)
                 gf.replay()
                 main.wait_stream(upd)
