@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 11
+#define SANERF_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -204,12 +204,15 @@ SANERF_API int sanerf_sample_uniform(const float* rays_o, const float* rays_d, c
                           const float* cam_near_far, uint32_t cnf_stride, const float* noise, uint32_t N,
                           uint32_t T, int contract, float bound, float* bins, float* t_mid, float* deltas,
                           float* x01, void* stream);
-/* prev_bins [N,T0+1], prev_weights [N,T0]: the previous level's edges and compositing weights */
+/* prev_bins [N,T0+1], prev_weights [N,T0]: the previous level's edges and compositing weights.  With prev_sigmas /
+ * prev_deltas [N,T0] given (prev_sigmas != NULL) the compositing of the previous level (renderer.py:309-326) is fused in:
+ * its weights are computed here, written to prev_weights_out [N,T0] and used for the resampling (prev_weights unused). */
 SANERF_API int sanerf_sample_pdf(const float* rays_o, const float* rays_d, const float* aabb, float min_near,
                       const float* cam_near_far, uint32_t cnf_stride, const float* prev_bins,
                       const float* prev_weights, uint32_t T0, const float* noise, uint32_t N, uint32_t T,
                       int contract, float bound, float* bins, float* t_mid, float* deltas, float* x01,
-                      void* stream);
+                      const float* prev_sigmas, const float* prev_deltas, int last_sample_opaque,
+                      float* prev_weights_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Proposal density, fused: hash-grid encode (D=3, F=2, L<=8, fp32) -> Linear(2L,16) -> ReLU -> Linear(16,1) ->

@@ -12,7 +12,7 @@
 //
 // Random jitter comes from a caller-provided uniform tensor (torch's generator), so parity tests
 // can share the draw with the oracle; NULL = no perturbation.
-#include "common.cuh"
+#include "composite_common.cuh"
 
 namespace sanerf {
 
@@ -119,26 +119,45 @@ __global__ void __launch_bounds__(32 * kSamplerWarps) sample_pdf_kernel(
     float min_near, const float* __restrict__ cam_near_far, uint32_t cnf_stride,
     const float* __restrict__ prev_bins, const float* __restrict__ prev_weights, uint32_t T0,
     const float* __restrict__ noise, uint32_t N, uint32_t T, int contract, float bound,
-    float* __restrict__ bins, float* __restrict__ t_mid, float* __restrict__ deltas, float* __restrict__ x01) {
+    float* __restrict__ bins, float* __restrict__ t_mid, float* __restrict__ deltas, float* __restrict__ x01,
+    const float* __restrict__ prev_sigmas, const float* __restrict__ prev_deltas, int last_opaque,
+    float* __restrict__ prev_weights_out) {
     extern __shared__ float smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kSamplerWarps + warp;
     if (r >= N) return;
-    const uint32_t per_warp = (T0 + 1u) * 2u + (T + 1u);
+    const uint32_t per_warp = (T0 + 1u) * 2u + (T + 1u) + T0;
     float* cdf = smem + (size_t)warp * per_warp;
     float* pbin = cdf + (T0 + 1u);
     float* nbin = pbin + (T0 + 1u);
+    float* wbuf = nbin + (T + 1u);                   // the previous level's weights of this ray
     const uint32_t E = T + 1u;                       // edges to draw
 
+    if (prev_sigmas != nullptr) {
+        // fused compositing of the previous level (renderer.py:309-326, the C = 0 case of csrc/composite.cu): weights
+        // from sigma and interval lengths, written out for the losses / the backward and kept here for the resampling
+        CompositeArgs a{prev_sigmas, prev_deltas, nullptr, nullptr, nullptr, N, T0, 0u, last_opaque, 0.0f, 0u, 0u};
+        float carry_x = 0.0f;
+        for (uint32_t base = 0; base < T0; base += 32) {
+            const SampleTerms st = chunk_terms(a, (size_t)r * T0, T0, base, lane, carry_x);
+            if (st.valid) {
+                wbuf[base + lane] = st.w;
+                prev_weights_out[(size_t)r * T0 + base + lane] = st.w;
+            }
+        }
+    } else {
+        for (uint32_t i = lane; i < T0; i += 32) wbuf[i] = __ldg(prev_weights + (size_t)r * T0 + i);
+    }
+    __syncwarp();
     // pdf = (w + 0.01) / sum ; cdf = min(cumsum, 1) with a leading 0
-    const float* w = prev_weights + (size_t)r * T0;
+    const float* w = wbuf;
     float total = 0.0f;
-    for (uint32_t i = lane; i < T0; i += 32) total += __ldg(w + i) + 0.01f;
+    for (uint32_t i = lane; i < T0; i += 32) total += w[i] + 0.01f;
     total = warp_sum(total);
     float carry = 0.0f;
     for (uint32_t base = 0; base < T0; base += 32) {
         const uint32_t i = base + lane;
-        float p = (i < T0) ? __fdiv_rn(__ldg(w + i) + 0.01f, total) : 0.0f;
+        float p = (i < T0) ? __fdiv_rn(w[i] + 0.01f, total) : 0.0f;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const float v = __shfl_up_sync(0xffffffffu, p, o);
@@ -203,20 +222,26 @@ extern "C" int sanerf_sample_pdf(const float* rays_o, const float* rays_d, const
                                  const float* cam_near_far, uint32_t cnf_stride, const float* prev_bins,
                                  const float* prev_weights, uint32_t T0, const float* noise, uint32_t N, uint32_t T,
                                  int contract, float bound, float* bins, float* t_mid, float* deltas, float* x01,
-                                 void* stream) {
+                                 const float* prev_sigmas, const float* prev_deltas, int last_sample_opaque,
+                                 float* prev_weights_out, void* stream) {
     if (N == 0 || T == 0) return SANERF_OK;
     SANERF_REQUIRE_PTR(rays_o); SANERF_REQUIRE_PTR(rays_d); SANERF_REQUIRE_PTR(aabb);
-    SANERF_REQUIRE_PTR(prev_bins); SANERF_REQUIRE_PTR(prev_weights);
+    SANERF_REQUIRE_PTR(prev_bins);
+    if (prev_sigmas != nullptr) {
+        SANERF_REQUIRE_PTR(prev_deltas); SANERF_REQUIRE_PTR(prev_weights_out);
+    } else {
+        SANERF_REQUIRE_PTR(prev_weights);
+    }
     SANERF_REQUIRE_PTR(bins); SANERF_REQUIRE_PTR(t_mid); SANERF_REQUIRE_PTR(deltas); SANERF_REQUIRE_PTR(x01);
     if (T0 == 0) return fail(SANERF_ERR_INVALID_ARG, "sample_pdf: previous level has no samples");
     if (!(bound > 0.0f)) return fail(SANERF_ERR_INVALID_ARG, "sample_pdf: bound must be > 0");
-    const size_t smem = (size_t)kSamplerWarps * ((T0 + 1u) * 2u + (T + 1u)) * sizeof(float);
+    const size_t smem = (size_t)kSamplerWarps * ((T0 + 1u) * 2u + (T + 1u) + T0) * sizeof(float);
     if (smem > 200 * 1024) return fail(SANERF_ERR_INVALID_ARG, "sample_pdf: T0/T too large for shared memory");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sample_pdf_kernel<<<div_up(N, (uint32_t)kSamplerWarps), 32 * kSamplerWarps, smem, st>>>(
         rays_o, rays_d, aabb, min_near, cam_near_far, cnf_stride, prev_bins, prev_weights, T0, noise, N, T, contract,
-        bound, bins, t_mid, deltas, x01);
+        bound, bins, t_mid, deltas, x01, prev_sigmas, prev_deltas, last_sample_opaque, prev_weights_out);
     return check_launch("sample_pdf_kernel");
 }

@@ -66,7 +66,7 @@ def sample_pdf(rays_o, rays_d, aabb, min_near, prev_bins, prev_weights, T, noise
         rc = lib.sanerf_sample_pdf(rays_o.data_ptr(), rays_d.data_ptr(), aabb.data_ptr(), float(min_near),
                                    _lib.ptr(cnf), stride, prev_bins.data_ptr(), prev_weights.data_ptr(), T0,
                                    _lib.ptr(noise), N, T, int(bool(contract)), float(bound), bins.data_ptr(),
-                                   t_mid.data_ptr(), deltas.data_ptr(), x01.data_ptr(), _stream(rays_o))
+                                   t_mid.data_ptr(), deltas.data_ptr(), x01.data_ptr(), None, None, 0, None, _stream(rays_o))
     _lib.check(rc, "sample_pdf")
     return bins, t_mid, deltas, x01
 

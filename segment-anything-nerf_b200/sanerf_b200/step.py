@@ -58,7 +58,7 @@ class FusedRGBStep:
         f32 = dict(device=dev, dtype=torch.float32)
         self.rays_o, self.rays_d, self.gt = (torch.zeros(N, 3, **f32) for _ in range(3))
         sizes = [N * (t + 1) for t in self.steps]
-        self.noise_flat = torch.zeros(sum(sizes), **f32)
+        self.noise_flat = torch.rand(sum(sizes), **f32)
         self.noise, off = [], 0
         for t, n in zip(self.steps, sizes):
             self.noise.append(self.noise_flat[off:off + n].view(N, t + 1))
@@ -109,9 +109,7 @@ class FusedRGBStep:
         span, check, ptr = _lib.stats.span, _lib.check, _lib.ptr
         aabb = m.aabb_train if m.training else m.aabb_infer
         bound, contract, min_near = float(m.bound), int(bool(m.opt.contract)), float(m.min_near)
-        self.loss.zero_()
-        if self.perturb:
-            self.noise_flat.uniform_()
+        self.loss.zero_()          # (the jitter of THIS step was drawn during the previous step's backward, off the critical path)
         o, d = self.rays_o.data_ptr(), self.rays_d.data_ptr()
 
         # ---------------- forward: proposal levels
@@ -125,13 +123,13 @@ class FusedRGBStep:
                                                    L["bins"].data_ptr(), L["t_mid"].data_ptr(), L["deltas"].data_ptr(),
                                                    L["x01"].data_ptr(), st)
                 check(rc, "sample_uniform")
-            else:
+            else:                  # the previous level's compositing (sigma -> weights) is fused into the resampling kernel
                 P = self.lv[li - 1]
                 with span("sample_pdf", N=N, T=T):
-                    rc = lib.sanerf_sample_pdf(o, d, aabb.data_ptr(), min_near, None, 0, P["bins"].data_ptr(),
-                                               P["weights"].data_ptr(), P["T"], noise, N, T, contract, bound,
-                                               L["bins"].data_ptr(), L["t_mid"].data_ptr(), L["deltas"].data_ptr(),
-                                               L["x01"].data_ptr(), st)
+                    rc = lib.sanerf_sample_pdf(o, d, aabb.data_ptr(), min_near, None, 0, P["bins"].data_ptr(), None, P["T"],
+                                               noise, N, T, contract, bound, L["bins"].data_ptr(), L["t_mid"].data_ptr(),
+                                               L["deltas"].data_ptr(), L["x01"].data_ptr(), P["sigma"].data_ptr(),
+                                               P["deltas"].data_ptr(), self.opaque, P["weights"].data_ptr(), st)
                 check(rc, "sample_pdf")
             if li < 2:
                 enc, mlp = m.prop_encoders[li], m.prop_mlp[li]
@@ -142,11 +140,7 @@ class FusedRGBStep:
                                                          int(enc.base_resolution), L["sigma"].data_ptr(),
                                                          L["enc"].data_ptr() if update_proposal else None, st)
                 check(rc, "prop_density_forward")
-                with span("composite_forward", N=N, T=T, C=0):
-                    rc = lib.sanerf_composite_forward(L["sigma"].data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), None, 0,
-                                                      None, N, T, 0, self.opaque, 0.0, L["weights"].data_ptr(), L["ws"].data_ptr(),
-                                                      L["depth"].data_ptr(), None, None, st)
-                check(rc, "composite_forward")
+
     def _launch_back(self, update_proposal, reduce_small=False):
         """Final level forward, losses, backward of everything (``reduce_small``: start the all-reduces of the small
         gradient ranges as soon as they are complete)."""
@@ -181,6 +175,9 @@ class FusedRGBStep:
         side = self.side_stream
         if lam_p > 0 or have_gw2:
             side.wait_stream(main)
+        if self.perturb:                                   # next step's jitter ([N, T+1] uniforms per level, reference order)
+            with torch.cuda.stream(side if (lam_p > 0 or have_gw2) else main):
+                self.noise_flat.uniform_()
         if have_gw2:                                       # distortion loss: concurrent with the view head on the main stream
             with torch.cuda.stream(side):
                 with span("distortion_loss", N=N, T=T):

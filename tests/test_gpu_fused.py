@@ -272,3 +272,30 @@ def test_view_head_kernel_matches_autograd(cuda, N):
                               _lib.current_stream(geo.device))
     _lib.check(rc, "view_head")
     torch.testing.assert_close(image2, image_ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_sample_pdf_with_fused_compositing_equals_two_kernels(cuda):
+    """sanerf_sample_pdf fed with (sigma, deltas) of the previous level == composite (C = 0) followed by sample_pdf."""
+    from sanerf_b200 import _lib
+    N, T0, T = 257, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    o = torch.rand(N, 3, device="cuda", generator=g) - 0.5
+    d = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda", generator=g), dim=-1)
+    aabb = torch.tensor([-128.0] * 3 + [128.0] * 3, device="cuda")
+    noise0, noise1 = torch.rand(N, T0 + 1, device="cuda", generator=g), torch.rand(N, T + 1, device="cuda", generator=g)
+    bins0, t0, d0, _ = fused.sample_uniform(o, d, aabb, 0.2, T0, noise0)
+    sigma0 = torch.randn(N, T0, device="cuda", generator=g).exp()
+    w0 = composite(sigma0, d0, t0, None, last_sample_opaque=True)[0]
+    ref = fused.sample_pdf(o, d, aabb, 0.2, bins0, w0, T, noise1)
+    lib = _lib.load()
+    outs = (torch.empty(N, T + 1, device="cuda"), torch.empty(N, T, device="cuda"), torch.empty(N, T, device="cuda"),
+            torch.empty(N, T, 3, device="cuda"))
+    w_out = torch.full((N, T0), float("nan"), device="cuda")
+    rc = lib.sanerf_sample_pdf(o.data_ptr(), d.data_ptr(), aabb.data_ptr(), 0.2, None, 0, bins0.data_ptr(), None, T0,
+                               noise1.data_ptr(), N, T, 1, 2.0, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                               outs[3].data_ptr(), sigma0.data_ptr(), d0.data_ptr(), 1, w_out.data_ptr(),
+                               _lib.current_stream(o.device))
+    _lib.check(rc, "sample_pdf")
+    assert torch.equal(w_out, w0)                          # same arithmetic as the compositing kernel
+    for a, b in zip(outs, ref):
+        assert torch.equal(a, b)
