@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(kPropThreads, 2) prop_backward_kernel(const Pr
 #pragma unroll 4
         for (uint32_t s = 0; s < 32; ++s) {
             const float* r = rows + s * kPropRow;
-            const float hs = r[own_j], dp = r[32];
+            const float dp = r[32];
+            if (dp == 0.0f) continue;                       // warp-uniform (broadcast read): this sample contributes nothing
+            const float hs = r[own_j];
             const float m = (hs > 0.0f) ? dp : 0.0f;
             const float4 e0 = *reinterpret_cast<const float4*>(r + 16 + own_half * 8);
             float e[8] = {e0.x, e0.y, e0.z, e0.w, 0.0f, 0.0f, 0.0f, 0.0f};
