@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 12
+#define SANERF_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -213,6 +213,16 @@ SANERF_API int sanerf_sample_pdf(const float* rays_o, const float* rays_d, const
                       int contract, float bound, float* bins, float* t_mid, float* deltas, float* x01,
                       const float* prev_sigmas, const float* prev_deltas, int last_sample_opaque,
                       float* prev_weights_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ray generation (get_rays, nerf/utils.py:145-279): pixel centres, un-normalised pinhole directions rotated by the
+ * camera-to-world pose, origin = its translation.  poses f32 row-major 4x4 with stride pose_stride floats (0: one
+ * pose for all rays, 16: one per ray); intrinsics f32 (fx, fy, cx, cy) with stride 0 or 4; inds i64 [N] flat pixel
+ * indices (row * W + col) or NULL for pixels 0..N-1; outputs rays_o, rays_d f32 [N,3].
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_generate_rays(const float* poses, uint32_t pose_stride, const float* intrinsics,
+                         uint32_t intr_stride, const int64_t* inds, uint32_t W, uint32_t N, float* rays_o,
+                         float* rays_d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Proposal density, fused: hash-grid encode (D=3, F=2, L<=8, fp32) -> Linear(2L,16) -> ReLU -> Linear(16,1) ->

@@ -245,3 +245,42 @@ extern "C" int sanerf_sample_pdf(const float* rays_o, const float* rays_d, const
         bound, bins, t_mid, deltas, x01, prev_sigmas, prev_deltas, last_sample_opaque, prev_weights_out);
     return check_launch("sample_pdf_kernel");
 }
+
+// ---- ray generation ---------------------------------------------------------------------------------------------
+// get_rays of the reference (nerf/utils.py:145-279) for the pixels `inds` (flat row * W + col; NULL = the whole image):
+// pixel centres (+0.5), pinhole directions ((i - cx) / fx, -(j - cy) / fy, -1), NOT normalised, rotated by the
+// camera-to-world pose; origin = the pose's translation.  One pose / intrinsics for all rays (stride 0) or one per ray.
+namespace sanerf {
+__global__ void __launch_bounds__(256) generate_rays_kernel(const float* __restrict__ poses, uint32_t pose_stride,
+                                                            const float* __restrict__ intrinsics, uint32_t intr_stride,
+                                                            const int64_t* __restrict__ inds, uint32_t W, uint32_t N,
+                                                            float* __restrict__ rays_o, float* __restrict__ rays_d) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int64_t pix = inds ? inds[n] : (int64_t)n;
+    const float i = (float)(pix % W) + 0.5f, j = (float)(pix / W) + 0.5f;
+    const float* P = poses + (size_t)n * pose_stride;           // row-major 4x4
+    const float* K = intrinsics + (size_t)n * intr_stride;      // fx, fy, cx, cy
+    const float xs = __fdiv_rn(i - __ldg(K + 2), __ldg(K + 0));
+    const float ys = -__fdiv_rn(j - __ldg(K + 3), __ldg(K + 1));
+    const float zs = -1.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float d = __fmaf_rn(zs, __ldg(P + 4 * k + 2), __fmaf_rn(ys, __ldg(P + 4 * k + 1), xs * __ldg(P + 4 * k)));
+        rays_d[(size_t)n * 3 + k] = d;
+        rays_o[(size_t)n * 3 + k] = __ldg(P + 4 * k + 3);
+    }
+}
+}  // namespace sanerf
+
+extern "C" int sanerf_generate_rays(const float* poses, uint32_t pose_stride, const float* intrinsics, uint32_t intr_stride,
+                                    const int64_t* inds, uint32_t W, uint32_t N, float* rays_o, float* rays_d, void* stream) {
+    if (N == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(poses); SANERF_REQUIRE_PTR(intrinsics); SANERF_REQUIRE_PTR(rays_o); SANERF_REQUIRE_PTR(rays_d);
+    if (W == 0) return sanerf::fail(SANERF_ERR_INVALID_ARG, "generate_rays: W must be > 0");
+    if ((pose_stride != 0 && pose_stride != 16) || (intr_stride != 0 && intr_stride != 4))
+        return sanerf::fail(SANERF_ERR_INVALID_ARG, "generate_rays: pose stride 0 or 16 floats, intrinsics stride 0 or 4");
+    sanerf::generate_rays_kernel<<<sanerf::div_up(N, 256u), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        poses, pose_stride, intrinsics, intr_stride, inds, W, N, rays_o, rays_d);
+    return sanerf::check_launch("generate_rays_kernel");
+}
