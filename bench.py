@@ -336,6 +336,137 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def _timed(step_fn, n_steps, dev, world, flush):
+    import torch.distributed as dist
+    evs = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(n_steps):
+        flush.fill_(float(i))                                      # evict L2 between timed iterations
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); step_fn(i); e.record()
+        evs.append((s, e))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_sam(args, rank, world, local_rank):
+    """configs[2]: stage-2 SAM feature-field training step, 4096 rays (64x64) per GPU, synthetic [1,256,64,64] target."""
+    from nerf.network import NeRFNetwork
+    from sanerf_b200 import _lib
+    from sanerf_b200.train import SAMTrainer, default_opt
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    torch.manual_seed(0)
+    model = NeRFNetwork(default_opt(with_sam=True)).to(dev)
+    trainer = SAMTrainer(model, world_size=world)
+    n = 4096
+    sets = [synthetic_rays(n, dev, 1234 + rank * 100 + i)[:2] for i in range(4)]
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
+    target = torch.randn(1, 256, 64, 64, generator=g)
+    host = [tuple(t.cpu().pin_memory() for t in s) for s in sets]
+    target_dev, target_host = target.to(dev), target.pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    last = [0.0]
+    for i in range(args.warmup):
+        trainer.step(*sets[i % 4], target_dev, 64, 64)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = _timed(lambda i: trainer.step(*sets[i % 4], target_dev, 64, 64), args.steps, dev, world, flush)
+
+    def e2e(i):
+        last[0] = trainer.step(*host[i % 4], target_host, 64, 64).item()
+    e2e_ms = _timed(e2e, args.steps, dev, world, flush)
+    clocks = sampler.stop() if rank == 0 else {}
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": "train rays/s (SAM feature fwd+bwd+Adam step)", "value": world * n * args.steps / (ms / 1e3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "configs[2]: stage-2 SAM feature-field step, 4096 rays (64x64) per GPU x (128,64,32) samples, s_grid "
+                               "L16 F8 T2^19 + samvit_mlp (163->256x5, LayerNorm), frozen stage-1 field, [1,256,64,64] target",
+                   "execution": "autograd step captured as a CUDA graph", "l2": "flushed between timed iterations",
+                   "parallelism": f"ray-sharded data parallel x{world}"},
+        "clocks": clocks,
+        "e2e": {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": 2 * n * 3 * 4 + 256 * 64 * 64 * 4, "d2h_bytes_per_step": 4, "last_loss": last[0]},
+        "gpu_launches": None, "roofline": None, "cpu_baseline": None}), flush=True)
+
+
+def run_frame(args, rank, world, local_rank):
+    """configs[3]: 512x512 RGB + depth + 64x64x256 SAM feature map; image rows are sharded over the ranks, one final gather."""
+    import numpy as np
+    from nerf.network import NeRFNetwork
+    from nerf.utils import get_rays
+    from sanerf_b200 import _lib
+    from sanerf_b200.parallel import gather_frame, shard_rays
+    from sanerf_b200.train import default_opt, render_frame
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    torch.manual_seed(0)
+    model = NeRFNetwork(default_opt(with_sam=True)).to(dev).eval()
+    H = W = 512
+    intr = np.array([0.5 * H / np.tan(np.radians(30)), 0.5 * H / np.tan(np.radians(30)), W / 2, H / 2], dtype=np.float32)
+    intr_f = intr / 8
+    pose_host = torch.eye(4).unsqueeze(0).pin_memory()
+    pose_host[0, :3, 3] = torch.tensor([0.1, 0.0, 0.4])
+    a, b = shard_rays(H * W, rank, world)
+    fa, fb = shard_rays(64 * 64, rank, world)
+    pix = torch.arange(a, b, device=dev)
+    fpix = torch.arange(fa, fb, device=dev)
+    img_host = torch.empty(H * W, 3).pin_memory()
+    feat_host = torch.empty(64, 64, 256).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def frame(pose, copy_back):
+        pose = pose.to(dev, non_blocking=True)
+        r = get_rays(pose, intr, H, W, b - a, coords=torch.stack([pix // W, pix % W], -1))
+        f = get_rays(pose, intr_f, 64, 64, fb - fa, coords=torch.stack([fpix // 64, fpix % 64], -1))
+        out = render_frame(model, r["rays_o"], r["rays_d"], f["rays_o"], f["rays_d"], fb - fa, 1)
+        image = gather_frame(out["image"], H * W, rank, world)
+        feats = gather_frame(out["samvit"].reshape(fb - fa, 256), 64 * 64, rank, world)
+        if copy_back and rank == 0:
+            img_host.copy_(image, non_blocking=True)
+            feat_host.copy_(feats.view(64, 64, 256), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    pose_dev = pose_host.to(dev)
+    for _ in range(args.warmup):
+        frame(pose_dev, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = _timed(lambda i: frame(pose_dev, False), args.steps, dev, world, flush)
+    e2e_ms = _timed(lambda i: frame(pose_host, True), args.steps, dev, world, flush)
+    clocks = sampler.stop() if rank == 0 else {}
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": "512x512 RGB + 256-d SAM feature render FPS", "value": args.steps / (ms / 1e3), "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "configs[3]: 512x512 RGB + depth (262144 rays x (128,64,32) samples) + 64x64x256 SAM feature map, "
+                               "random-init field; pose -> rays -> render -> gather",
+                   "execution": "hand-scheduled forward replayed as one CUDA graph + autograd-free feature pass",
+                   "l2": "flushed between timed frames", "parallelism": f"image rows sharded x{world}, one final all_gather"},
+        "clocks": clocks,
+        "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 3 * 4 + 64 * 64 * 256 * 4},
+        "gpu_launches": None, "roofline": None, "cpu_baseline": None}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +477,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
     ap.add_argument("--roofline-kernel", default="head_forward", choices=sorted(ROOFLINE_KERNELS))
+    ap.add_argument("--workload", default="rgb", choices=["rgb", "sam", "frame"],
+                    help="rgb = BASELINE configs[1] (the headline); sam = configs[2]; frame = configs[3]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -360,7 +493,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        {"rgb": run_ours, "sam": run_sam, "frame": run_frame}[args.workload](args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -134,31 +134,33 @@ class SAMTrainer:
         dev = self.optimizer.flat_param.device
         key = (tuple(rays_o.shape), h, w, tuple(target.shape))
         entry = self._graphs.get(key)
-        if not self.use_graph or self.world_size > 1 or entry is None:
+        if not self.use_graph or entry is None:
             rays_o, rays_d, target = (t.to(dev, non_blocking=True) for t in (rays_o, rays_d, target))
             loss = self._forward_backward(rays_o, rays_d, target, h, w)
-            if self.world_size > 1:
-                dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
-            self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
-            if self.use_graph and self.world_size == 1 and entry is None:
+            self._update()
+            if self.use_graph:
                 self._graphs[key] = "warm"                # next call with this shape captures
             return loss
         if entry == "warm":
             static = [torch.empty_like(t, device=dev) for t in (rays_o, rays_d, target)]
-            for buf, src in zip(static, (rays_o, rays_d, target)):
-                buf.copy_(src)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph):                 # forward + backward; the NCCL exchange stays outside the graph
                 loss = self._forward_backward(static[0], static[1], static[2], h, w)
-                self.optimizer.step(grad_scale=1.0, zero_grad=True)
-            self._graphs[key] = (graph, static, loss)
-            graph.replay()                                # capture does not execute the work
-            return loss
+                if self.world_size == 1:
+                    self._update()
+            entry = self._graphs[key] = (graph, static, loss)
         graph, static, loss = entry
         for buf, src in zip(static, (rays_o, rays_d, target)):
             buf.copy_(src, non_blocking=True)
         graph.replay()
+        if self.world_size > 1:
+            self._update()
         return loss
+
+    def _update(self):
+        if self.world_size > 1:
+            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+        self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
 
 
 _FRAME_PLANS = {}
