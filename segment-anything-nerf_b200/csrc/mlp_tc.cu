@@ -7,8 +7,10 @@
 //
 // Design
 //  * A tile is 128 samples = the 128 TMEM lanes.  Weights live in shared memory for the whole kernel as UMMA
-//    B operands; activations go TMEM -> registers (ReLU) -> shared memory (A operand of the next layer); nothing
-//    but the 16-wide head (and, for training, the 32-wide encoding) is written to HBM.
+//    B operands; every A operand lives in TENSOR MEMORY: the producers write the encoding there (tcgen05.st), the
+//    activations go TMEM accumulator -> registers (ReLU, hi/lo split) -> TMEM operand planes.  The unified L1 / shared
+//    data path is what the hash-grid gather is bound by (one 128-byte wavefront per lane and load), so no activation
+//    tile travels through it, and with 56 KB of shared memory the L1 keeps ~170 KB for the table.
 //  * fp32 parity: every product is evaluated as hi*hi + hi*lo + lo*hi with hi = the tf32 truncation of the operand
 //    and lo = the exact remainder ("3xTF32"), accumulated in fp32 in TMEM: error ~2^-21 relative per product.
 //    precision = 1 runs one tf32 pass on round-to-nearest operands (the 1e-2 "fp16-class" tolerance).
@@ -30,11 +32,9 @@ constexpr uint32_t kThreads = (kMlpWarps + kProducerWarps) * 32;
 constexpr uint32_t kW1 = kHid * kIn * 4, kW2 = kHid * kHid * 4, kW3 = kOut * kHid * 4;
 constexpr uint32_t kA1 = kTile * kIn * 4, kH = kTile * kHid * 4;
 constexpr uint32_t oW1 = 0, oW2 = oW1 + 2 * kW1, oW3 = oW2 + 2 * kW2;
-constexpr uint32_t oA1 = oW3 + 2 * kW3;            // 2 slots x (hi, lo)
-constexpr uint32_t oH = oA1 + 4 * kA1;             // (hi, lo)
-constexpr uint32_t kFwdSmem = oH + 2 * kH;
-// TMEM columns
-constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, kTmemCols = 256;
+constexpr uint32_t kFwdSmem = oW3 + 2 * kW3;       // forward: only the weights live in shared memory
+// forward TMEM columns: two encoding slots (hi 32 | lo 32 each), hidden activations (hi 64 | lo 64), three accumulators
+constexpr uint32_t cEnc = 0, cHhi = 128, cHlo = 192, cD1 = 256, cD2 = 320, cD3 = 384, kTmemCols = 512;
 }  // namespace head
 
 // float offset of the 4-element chunk c of sample b in a "tile-chunk-major" [B, W] matrix: [tile][chunk][row][4].
@@ -81,6 +81,50 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi_plane, uint8_t* lo_plane, 
     }
 }
 
+// 16 / 8 consecutive columns of this thread's TMEM lane <- hi / lo parts of v (A-operand planes of the next product)
+__device__ __forceinline__ void split_to_tmem16(uint32_t t_hi, uint32_t t_lo, const float (&v)[16], bool split) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        if (split) umma::split_tf32(v[j], hi[j], lo[j]);
+        else hi[j] = round_tf32(v[j]);
+    }
+    umma::tmem_st16(t_hi, hi);
+    if (split) umma::tmem_st16(t_lo, lo);
+}
+__device__ __forceinline__ void split_to_tmem8(uint32_t t_hi, uint32_t t_lo, const float (&v)[8], bool split) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) {
+        if (split) umma::split_tf32(v[j], hi[j], lo[j]);
+        else hi[j] = round_tf32(v[j]);
+    }
+    umma::tmem_st8(t_hi, hi);
+    if (split) umma::tmem_st8(t_lo, lo);
+}
+
+// D[128, N] = A[tmem: 128 lanes x K columns] . B[N, K]^T ; B = chunk-major K-major weight tile with N rows; b_* are low
+// descriptor halves (umma::desc_lo), the high halves are compile-time constants
+template <uint32_t N, uint32_t K>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t b_hi,
+                                              uint32_t b_lo, bool split) {
+    constexpr uint32_t idesc = umma::idesc_tf32(128, N, 0, 0);
+    constexpr uint32_t b_step = (2u * N * 16u) >> 4;
+    constexpr uint32_t hi = umma::desc_hi(128u, umma::kLayoutNone);
+    uint32_t acc = 0;
+#pragma unroll
+    for (uint32_t ks = 0; ks < K / 8; ++ks) {
+        const uint32_t bo = ks * b_step;
+        if (split) {
+            umma::mma_tf32_ts2(tmem_d, tmem_a_lo + ks * 8u, b_hi + bo, hi, idesc, acc);
+            umma::mma_tf32_ts2(tmem_d, tmem_a_hi + ks * 8u, b_lo + bo, hi, idesc, 1u);
+            acc = 1;
+        }
+        umma::mma_tf32_ts2(tmem_d, tmem_a_hi + ks * 8u, b_hi + bo, hi, idesc, acc);
+        acc = 1;
+    }
+}
+
 // stage an nn.Linear weight [rows=out, cols=in] as a chunk-major B operand (hi, lo planes)
 __device__ __forceinline__ void stage_weight(const float* __restrict__ w, uint8_t* plane_hi, uint32_t rows, uint32_t cols,
                                              bool split, uint32_t tid, uint32_t nthreads) {
@@ -122,19 +166,19 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // TMEM accumulator (64 columns of this thread's lane) -> ReLU -> hi/lo planes of the chunk-major H tile
+// TMEM accumulator (64 columns of this thread's lane) -> ReLU -> hi / lo operand planes of the next layer in TMEM.
 // `save` = the tile-chunk-major [B,64] activation kept for the backward (or NULL): chunk c of sample b at tcm_off(b, c, 16)
-__device__ __forceinline__ void relu_to_smem(uint32_t tmem_lane_col, uint8_t* h_hi, uint8_t* h_lo, uint32_t row, bool split,
-                                             float* save, uint32_t b) {
+__device__ __forceinline__ void relu_to_tmem(uint32_t lane_base, uint32_t c_acc, bool split, float* save, uint32_t b) {
 #pragma unroll
     for (uint32_t c0 = 0; c0 < head::kHid; c0 += 16) {
         float v[16];
-        umma::tmem_ld16(tmem_lane_col + c0, v);
+        umma::tmem_ld16(lane_base + c_acc + c0, v);
 #pragma unroll
         for (uint32_t j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+        split_to_tmem16(lane_base + head::cHhi + c0, lane_base + head::cHlo + c0, v, split);
+        if (save != nullptr) {
 #pragma unroll
-        for (uint32_t j = 0; j < 16; j += 4) {
-            put_chunk(h_hi, h_lo, head::kTile, row, (c0 + j) >> 2, v[j], v[j + 1], v[j + 2], v[j + 3], split);
-            if (save != nullptr)
+            for (uint32_t j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(save + tcm_off(b, (c0 + j) >> 2, 16)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
     }
@@ -178,6 +222,7 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
         // ===================== producers: encoding of one sample x 4 levels -> A-operand slot =====================
         const uint32_t g = tid - kMlpWarps * 32;
         const uint32_t r = g & (kTile - 1), lg = g >> 7;
+        const uint32_t enc_lane = umma::tmem_addr(tmem, (warp & 3u) * 32u, 0);      // r == 32 (warp & 3) + lane
         const float* __restrict__ table = p.table;
         for (uint32_t it = 0, tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
             const uint32_t slot = it & 1u;
@@ -240,10 +285,10 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
                 enc[0] = u.x; enc[1] = u.y; enc[2] = u.z; enc[3] = u.w;
                 enc[4] = v.x; enc[5] = v.y; enc[6] = v.z; enc[7] = v.w;
             }
-            uint8_t* a_hi = smem + oA1 + slot * 2 * kA1;
-            put_chunk(a_hi, a_hi + kA1, kTile, r, lg * 2, enc[0], enc[1], enc[2], enc[3], split);
-            put_chunk(a_hi, a_hi + kA1, kTile, r, lg * 2 + 1, enc[4], enc[5], enc[6], enc[7], split);
-            umma::fence_proxy_async();
+            // this sample's 8 features -> TMEM operand planes of slot `slot` (this warp owns TMEM lanes 32 (warp & 3) ..)
+            split_to_tmem8(enc_lane + cEnc + slot * 64u + lg * 8u, enc_lane + cEnc + slot * 64u + 32u + lg * 8u, enc, split);
+            umma::tmem_st_wait();
+            umma::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(umma::smem_u32(&s_full[slot]));
         }
@@ -254,9 +299,6 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
         const uint32_t dW1h = umma::desc_lo(umma::smem_u32(smem + oW1), kHid * 16u), dW1l = umma::desc_lo(umma::smem_u32(smem + oW1 + kW1), kHid * 16u);
         const uint32_t dW2h = umma::desc_lo(umma::smem_u32(smem + oW2), kHid * 16u), dW2l = umma::desc_lo(umma::smem_u32(smem + oW2 + kW2), kHid * 16u);
         const uint32_t dW3h = umma::desc_lo(umma::smem_u32(smem + oW3), kOut * 16u), dW3l = umma::desc_lo(umma::smem_u32(smem + oW3 + kW3), kOut * 16u);
-        const uint32_t dHh = umma::desc_lo(umma::smem_u32(smem + oH), kTile * 16u), dHl = umma::desc_lo(umma::smem_u32(smem + oH + kH), kTile * 16u);
-        uint8_t* h_hi = smem + oH;
-        uint8_t* h_lo = h_hi + kH;
         uint32_t mma_phase = 0;
         for (uint32_t it = 0, tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
             const uint32_t slot = it & 1u;
@@ -264,8 +306,7 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
                 umma::mbar_wait(umma::smem_u32(&s_full[slot]), (it >> 1) & 1u);
                 if (umma::elect_one()) {
                     umma::fence_after_sync();
-                    const uint32_t dAh = umma::desc_lo(umma::smem_u32(smem + oA1 + slot * 2 * kA1), kTile * 16u);
-                    issue_gemm<kHid, kIn, kHid>(tmem + cD1, dAh, dAh + (kA1 >> 4), dW1h, dW1l, split);
+                    issue_gemm_ts<kHid, kIn>(tmem + cD1, tmem + cEnc + slot * 64u, tmem + cEnc + slot * 64u + 32u, dW1h, dW1l, split);
                     umma::commit(umma::smem_u32(&s_empty[slot]));     // A slot free once layer 1 has consumed it
                     umma::commit(umma::smem_u32(&s_mma));
                 }
@@ -275,29 +316,28 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             umma::fence_after_sync();
             const uint32_t b = tile * kTile + tid;
             const bool keep = (p.h1_out != nullptr) && b < p.B;
-            relu_to_smem(lane_base + cD1, h_hi, h_lo, tid, split, keep ? p.h1_out : nullptr, b);
-            umma::fence_proxy_async();
+            relu_to_tmem(lane_base, cD1, split, keep ? p.h1_out : nullptr, b);
+            umma::tmem_st_wait();
             umma::fence_before_sync();
             named_bar_sync(1, kMlpWarps * 32);
             if (warp == 0) {
                 if (umma::elect_one()) {
                     umma::fence_after_sync();
-                    issue_gemm<kHid, kHid, kHid>(tmem + cD2, dHh, dHl, dW2h, dW2l, split);
+                    issue_gemm_ts<kHid, kHid>(tmem + cD2, tmem + cHhi, tmem + cHlo, dW2h, dW2l, split);
                     umma::commit(umma::smem_u32(&s_mma));
                 }
                 __syncwarp();
             }
             umma::mbar_wait(umma::smem_u32(&s_mma), mma_phase); mma_phase ^= 1u;
             umma::fence_after_sync();
-            relu_to_smem(lane_base + cD2, h_hi, h_lo, tid, split,    // layer 2 has completed: H may be overwritten
-                         keep ? p.h2_out : nullptr, b);
-            umma::fence_proxy_async();
+            relu_to_tmem(lane_base, cD2, split, keep ? p.h2_out : nullptr, b);     // layer 2 has completed: the H planes are free
+            umma::tmem_st_wait();
             umma::fence_before_sync();
             named_bar_sync(1, kMlpWarps * 32);
             if (warp == 0) {
                 if (umma::elect_one()) {
                     umma::fence_after_sync();
-                    issue_gemm<kOut, kHid, kOut>(tmem + cD3, dHh, dHl, dW3h, dW3l, split);
+                    issue_gemm_ts<kOut, kHid>(tmem + cD3, tmem + cHhi, tmem + cHlo, dW3h, dW3l, split);
                     umma::commit(umma::smem_u32(&s_mma));
                 }
                 __syncwarp();
@@ -421,28 +461,6 @@ __device__ __forceinline__ void put_tmem16(uint32_t lane_base, uint32_t col, con
     }
     umma::tmem_st16(lane_base + head::cAhi + col, hi);
     if (split) umma::tmem_st16(lane_base + head::cAlo + col, lo);
-}
-
-// D[128, N] = A[tmem: 128 lanes x K columns] . Wt[N, K]^T ; Wt = transposed weight tile (K-major, N rows); b_* are low
-// descriptor halves
-template <uint32_t N, uint32_t K>
-__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t b_hi,
-                                              uint32_t b_lo, bool split) {
-    constexpr uint32_t idesc = umma::idesc_tf32(128, N, 0, 0);
-    constexpr uint32_t b_step = (2u * N * 16u) >> 4;
-    constexpr uint32_t hi = umma::desc_hi(128u, umma::kLayoutNone);
-    uint32_t acc = 0;
-#pragma unroll
-    for (uint32_t ks = 0; ks < K / 8; ++ks) {
-        const uint32_t bo = ks * b_step;
-        if (split) {
-            umma::mma_tf32_ts2(tmem_d, tmem_a_lo + ks * 8u, b_hi + bo, hi, idesc, acc);
-            umma::mma_tf32_ts2(tmem_d, tmem_a_hi + ks * 8u, b_lo + bo, hi, idesc, 1u);
-            acc = 1;
-        }
-        umma::mma_tf32_ts2(tmem_d, tmem_a_hi + ks * 8u, b_hi + bo, hi, idesc, acc);
-        acc = 1;
-    }
 }
 
 // D[64, N] (+)= At^T . Bt : MN-major swizzled tiles whose 128 rows are the contraction index (low descriptor halves)

@@ -186,6 +186,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
            "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
            "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
 }
+// registers -> TMEM: 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+        :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+           "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+           "r"(__float_as_uint(v[7])) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // TMEM address of (lane, column) relative to an allocation base: lane in bits 31..16, column in bits 15..0
