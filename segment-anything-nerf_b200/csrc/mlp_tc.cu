@@ -179,7 +179,7 @@ __device__ __forceinline__ void relu_to_tmem(uint32_t lane_base, uint32_t c_acc,
         if (save != nullptr) {
 #pragma unroll
             for (uint32_t j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(save + tcm_off(b, (c0 + j) >> 2, 16)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __stcs(reinterpret_cast<float4*>(save + tcm_off(b, (c0 + j) >> 2, 16)), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
         }
     }
 }
@@ -272,8 +272,9 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
                     enc[2 * q + 1] = a1;
                 }
                 if (p.enc_out != nullptr && live) {          // tile-chunk-major: 32 consecutive samples = 512 contiguous bytes
-                    *reinterpret_cast<float4*>(p.enc_out + tcm_off(b, lg * 2, 8)) = make_float4(enc[0], enc[1], enc[2], enc[3]);
-                    *reinterpret_cast<float4*>(p.enc_out + tcm_off(b, lg * 2 + 1, 8)) = make_float4(enc[4], enc[5], enc[6], enc[7]);
+                    // streaming (evict-first) stores: 640 B/sample of saved activations must not push the table out of L2
+                    __stcs(reinterpret_cast<float4*>(p.enc_out + tcm_off(b, lg * 2, 8)), make_float4(enc[0], enc[1], enc[2], enc[3]));
+                    __stcs(reinterpret_cast<float4*>(p.enc_out + tcm_off(b, lg * 2 + 1, 8)), make_float4(enc[4], enc[5], enc[6], enc[7]));
                 }
             } else {
                 float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;

@@ -1,0 +1,176 @@
+"""Speed of the sm_100a path against the reference's own GPU path on the SAME B200 ("the real before").
+
+The reference side is the UNMODIFIED reference CUDA extension rebuilt for sm_100 (``oracle/_ref``), driven exactly as
+``gridencoder/grid.py:24-95`` drives it ([L,B,C] output + permute copy; permuted gradient copy + zero-filled gradient
+table + scatter kernel), and, for the step, the torch restatement of ``nerf/renderer.py`` + ``nerf/network.py``
+(``oracle/render_torch.py``: torch glue kernels, cuBLAS ``nn.Linear`` MLPs, autograd, ``torch.optim.Adam``) running on
+the GPU with those extension kernels as its grid encoders.  CUDA events, L2 flushed before every timed launch, median.
+
+The numbers are written to ``gpurun_out/speed_vs_reference.json`` (copied to ``profiles/`` per round); the assertions
+only require that the new path is not slower than the reference's.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gridencoder import GridEncoder
+from gridencoder.grid import grid_encode
+from oracle import render_torch as R
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RESULTS = {}
+
+
+def _record(key, value):
+    RESULTS[key] = value
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "speed_vs_reference.json"), "w") as f:
+            json.dump(RESULTS, f, indent=1, sort_keys=True)
+
+
+def _timeit(fn, flush, n=10, warm=3):
+    ts = []
+    for i in range(n + warm):
+        flush.fill_(float(i))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ts))
+
+
+@pytest.fixture(scope="module")
+def flush(cuda):
+    return torch.empty(256 * 1024 * 1024 // 4, device=cuda)
+
+
+def _ref_forward(ext, x, table, offsets, S, H):
+    """grid.py:27-69: [L,B,C] output, kernel, permute(1,0,2).reshape copy."""
+    B, D = x.shape
+    L, C = offsets.shape[0] - 1, table.shape[1]
+    out = torch.empty(L, B, C, device=x.device, dtype=table.dtype)
+    ext.grid_encode_forward(x, table, offsets, out, B, D, C, L, L, S, H, None, 0, False, 0)
+    return out.permute(1, 0, 2).reshape(B, L * C)
+
+
+def _ref_backward(ext, grad, x, table, offsets, S, H):
+    """grid.py:74-95: permuted contiguous gradient copy, zero-filled gradient table, scatter kernel."""
+    B, D = x.shape
+    L, C = offsets.shape[0] - 1, table.shape[1]
+    g = grad.view(B, L, C).permute(1, 0, 2).contiguous()
+    gt = torch.zeros_like(table)
+    ext.grid_encode_backward(g, x, table, offsets, gt, B, D, C, L, L, S, H, None, None, 0, False, 0)
+    return gt
+
+
+GRIDS = {
+    "main_L16_F2_T19_fp32": (2, 19, 4096, torch.float32, 262144),
+    "sam_L16_F8_T19_fp32": (8, 19, 512, torch.float32, 131072),
+    "cfg5_L16_F2_T22_fp16": (2, 22, 4096, torch.float16, 1 << 20),
+}
+
+
+@pytest.mark.parametrize("name", list(GRIDS))
+def test_grid_encode_not_slower_than_reference_kernel(cuda, ref_ext, flush, name):
+    C, log2T, desired, dtype, B = GRIDS[name]
+    ext = ref_ext("gridencoder")
+    torch.manual_seed(0)
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=C, base_resolution=16, log2_hashmap_size=log2T,
+                      desired_resolution=desired).to(cuda)
+    table = enc.embeddings.detach().to(dtype).contiguous()
+    x = torch.rand(B, 3, device=cuda)
+    grad = torch.randn(B, 16 * C, device=cuda).to(dtype)
+    S, H = float(np.log2(enc.per_level_scale)), int(enc.base_resolution)
+
+    # the operator a user of the reference calls (gridencoder.grid.grid_encode), forward then backward through autograd
+    tp = table.clone().requires_grad_(True)
+    state = {}
+
+    def ours_fwd():
+        state["y"] = grid_encode(x, tp, enc.offsets, enc.per_level_scale, H, False, 0, False, 0, None)
+
+    def ours_bwd():
+        tp.grad = None
+        state["y"].backward(grad, retain_graph=True)
+
+    t_ref_f = _timeit(lambda: _ref_forward(ext, x, table, enc.offsets, S, H), flush)
+    t_ref_b = _timeit(lambda: _ref_backward(ext, grad, x, table, enc.offsets, S, H), flush)
+    t_our_f = _timeit(ours_fwd, flush)
+    ours_fwd()
+    t_our_b = _timeit(ours_bwd, flush)
+    _record(f"grid/{name}", {"B": B, "reference_fwd_us": t_ref_f, "ours_fwd_us": t_our_f, "reference_bwd_us": t_ref_b,
+                             "ours_bwd_us": t_our_b, "fwd_speedup": t_ref_f / t_our_f, "bwd_speedup": t_ref_b / t_our_b})
+    assert t_our_f <= t_ref_f, (t_our_f, t_ref_f)
+    assert t_our_b <= t_ref_b, (t_our_b, t_ref_b)
+
+
+class _RefGridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, offsets, S, H, ext):
+        ctx.save_for_backward(x, table, offsets)
+        ctx.cfg = (S, H, ext)
+        return _ref_forward(ext, x, table, offsets, S, H)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, table, offsets = ctx.saved_tensors
+        S, H, ext = ctx.cfg
+        return None, _ref_backward(ext, grad.contiguous(), x, table, offsets, S, H), None, None, None, None
+
+
+def _ref_grid_cls(ext):
+    class RefExtGridEncoder(R.GridEncoderRef):
+        """GridEncoder of the reference (grid.py:102-168) on the rebuilt reference kernels."""
+
+        def forward(self, inputs, bound=1, max_level=None):
+            x = ((inputs + bound) / (2 * bound)).reshape(-1, self.input_dim).contiguous()
+            out = _RefGridFn.apply(x, self.embeddings, self.offsets, float(np.log2(self.per_level_scale)),
+                                   int(self.base_resolution), ext)
+            return out.view(list(inputs.shape[:-1]) + [self.output_dim])
+
+    return RefExtGridEncoder
+
+
+def test_rgb_training_step_not_slower_than_reference_gpu_path(cuda, ref_ext, flush):
+    """BASELINE configs[1]: 8192 rays x (128, 64, 32) samples, forward + backward + Adam, one B200."""
+    from nerf.network import NeRFNetwork
+    from sanerf_b200.train import RGBTrainer, default_opt
+
+    ext = ref_ext("gridencoder")
+    n_rays = 8192
+    g = torch.Generator().manual_seed(1234)
+    o = (torch.rand(n_rays, 3, generator=g) - 0.5).to(cuda)
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g), dim=-1).to(cuda)
+    rgb = torch.rand(n_rays, 3, generator=g).to(cuda)
+
+    torch.manual_seed(0)
+    ref = R.NeRFNetworkRef(grid_cls=_ref_grid_cls(ext)).to(cuda).train()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)      # main.py:296
+
+    def ref_step():
+        opt.zero_grad(set_to_none=False)
+        loss, _ = ref.rgb_loss(o, d, rgb, update_proposal=True, perturb=True)
+        loss.backward()
+        opt.step()
+
+    torch.manual_seed(0)
+    model = NeRFNetwork(default_opt()).to(cuda)
+    trainer = RGBTrainer(model, lr=1e-2, iters=20000, world_size=1)
+
+    def our_step():
+        trainer.step(o, d, rgb)
+
+    t_ref = _timeit(ref_step, flush, n=8, warm=3)
+    t_our = _timeit(our_step, flush, n=20, warm=5)
+    _record("rgb_training_step", {"rays": n_rays, "reference_gpu_path_us": t_ref, "ours_us": t_our,
+                                  "reference_rays_per_s": n_rays / t_ref * 1e6, "ours_rays_per_s": n_rays / t_our * 1e6,
+                                  "speedup": t_ref / t_our})
+    assert t_our <= t_ref, (t_our, t_ref)
