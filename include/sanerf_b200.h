@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 13
+#define SANERF_ABI_VERSION 14
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -95,6 +95,23 @@ SANERF_API int sanerf_grad_total_variation(const void* inputs, const void* embed
 SANERF_API int sanerf_grad_weight_decay(const void* embeddings, void* grad, const int32_t* offsets,
                              float weight, uint32_t B, uint32_t C, uint32_t L, int dtype,
                              void* stream);
+
+/* Ray-composited grid features (stage 2, SAM feature field): replaces `features = self.s_grid(xyzs)` +
+ * `f_sam = torch.sum(weights.unsqueeze(-1) * features, dim=-2)` (nerf/renderer.py:302-303, 377) and the autograd chain
+ * behind them (expand + multiply, permute copy, zeros_like, scatter: gridencoder/grid.py:74-95) by one kernel per
+ * direction; no per-sample [N*T, L*C] matrix exists.  Hash grid, linear interpolation, align_corners = false, D = 3,
+ * fp32, C in {2,4,8}.
+ *  x01      f32 [N*T, 3]  samples of N dense rays (T each), already mapped to [0,1]^3
+ *  weights  f32 [N*T]     compositing weights (constants here: the density field is frozen in stage 2, main.py:255-262)
+ *  out      f32 [N, L*C]  sum_i weights[r,i] * encode(x01[r,i])
+ *  g_out    f32 [N, L*C]  incoming gradient;  grad_embeddings f32 [rows, C] is accumulated into (caller zero-fills)
+ */
+SANERF_API int sanerf_ray_features_forward(const float* x01, const float* weights, const float* embeddings,
+                                const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
+                                uint32_t H, float* out, void* stream);
+SANERF_API int sanerf_ray_features_backward(const float* x01, const float* weights, const float* g_out,
+                                 const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
+                                 uint32_t H, float* grad_embeddings, void* stream);
 
 /* Debug / parity entry point (no reference equivalent — SURVEY §8 c7): for every sample,
  * level < L and corner < 2^D write the table row (relative to the level's offset) the

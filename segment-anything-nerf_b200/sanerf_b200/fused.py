@@ -7,6 +7,8 @@ or two sm_100a kernels behind the C ABI:
 * ``prop_density``                      — network.py:248-252: grid encode -> MLP(2L,16,1) -> trunc_exp
 * ``head_composite``                    — network.py:226-227 + renderer.py:309-338: trunc_exp on column 0 of the
                                           16-wide MLP output and compositing of columns 1..15, read in place
+* ``ray_features``                      — renderer.py:302-303, 377: s_grid encode + weighted sum over the ray, and its
+                                          scatter, without the per-sample [N*T, 128] feature / gradient matrices
 * ``proposal_loss`` / ``distort_loss``  — renderer.py:17-57 (loss and d loss / d weights together)
 * ``FusedAdam``                         — main.py:296,312-313: Adam(eps=1e-15) + LambdaLR on flat buffers
 """
@@ -302,6 +304,52 @@ def head_composite(f, deltas, ts, last_sample_opaque=True, t_thresh=0.0):
 
 
 # ----------------------------------------------------------------------------------------- losses
+class _RayFeatures(Function):
+    """f_sam[r] = sum_i w[r,i] * s_grid(x[r,i])  (renderer.py:302-303, 377) without the per-sample feature matrix; the
+    weights are constants (the density field is frozen in stage 2), the table receives the scatter."""
+
+    @staticmethod
+    def forward(ctx, x01, weights, table, offsets, S, H):
+        N, T = weights.shape
+        L, C = offsets.numel() - 1, table.shape[1]
+        x01 = x01.reshape(N * T, 3).contiguous().float()
+        weights = weights.detach().contiguous().float()
+        out = torch.empty(N, L * C, device=table.device, dtype=torch.float32)
+        with _lib.stats.span("ray_features_forward", N=N, T=T, C=C):
+            rc = _lib.load().sanerf_ray_features_forward(x01.data_ptr(), weights.data_ptr(), table.data_ptr(),
+                                                         offsets.data_ptr(), N, T, C, L, S, H, out.data_ptr(), _stream(table))
+        _lib.check(rc, "ray_features_forward")
+        ctx.save_for_backward(x01, weights, offsets)
+        ctx.meta = (N, T, C, L, S, H, tuple(table.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x01, weights, offsets = ctx.saved_tensors
+        N, T, C, L, S, H, shape = ctx.meta
+        g_table = torch.zeros(shape, device=g_out.device, dtype=torch.float32)
+        g_out = g_out.contiguous().float()
+        with _lib.stats.span("ray_features_backward", N=N, T=T, C=C):
+            rc = _lib.load().sanerf_ray_features_backward(x01.data_ptr(), weights.data_ptr(), g_out.data_ptr(),
+                                                          offsets.data_ptr(), N, T, C, L, S, H, g_table.data_ptr(),
+                                                          _stream(g_out))
+        _lib.check(rc, "ray_features_backward")
+        return None, None, g_table, None, None, None
+
+
+def ray_features_supported(encoder):
+    return (encoder.input_dim == 3 and encoder.level_dim in (2, 4, 8) and encoder.gridtype_id == 0
+            and encoder.interp_id == 0 and not encoder.align_corners and encoder.embeddings.dtype == torch.float32)
+
+
+def ray_features(x01, weights, encoder):
+    """x01 [N,T,3] in [0,1]^3, weights [N,T] -> [N, L*C] ray-composited features of ``encoder`` (a GridEncoder)."""
+    if not x01.is_cuda:
+        raise RuntimeError("ray_features needs CUDA tensors (there is no CPU fallback)")
+    return _RayFeatures.apply(x01, weights, encoder.embeddings, encoder.offsets, float(np.log2(encoder.per_level_scale)),
+                              int(encoder.base_resolution))
+
+
 class _ProposalLoss(Function):
     """sum over proposal levels of the inter-level loss; weights of the final level are constants."""
 

@@ -475,3 +475,181 @@ class FusedRGBFrame(FusedRGBStep):
                 self._launch_render()
         L = self.lv[2]
         return {"image": self.image, "depth": L["depth"], "weights_sum": L["ws"], "n_alive": self.n_alive}
+
+
+class FusedSAMStep:
+    """Hand-scheduled stage-2 (SAM feature field) training step (nerf/utils.py:1095-1106 + renderer.py:221-390 with
+    ``--with_sam``; stage-1 parameters frozen, main.py:255-262):
+
+      frozen front:  the forward-only RGB plan (``FusedRGBFrame``: samplers, proposal densities, field head on tcgen05,
+                     fused compositing, view head) -> final-level samples x01, weights, geo_sum, image, depth
+      feature field: ONE kernel  f_sam[r] = sum_i w[r,i] * s_grid(x01[r,i])  (no [N*T,128] feature matrix)
+      samvit head:   f = [f_sam, f_image, image, depth] -> samvit_mlp -> resize -> MSE; autograd over the 5-layer
+                     SkipConnMLP + LayerNorm only (f is a leaf), gradients accumulate into the flat bucket
+      scatter:       ONE kernel  g_table += cw * (w[r,i] * g_f[r,:128])  straight into ``FusedAdam.flat_grad`` (no
+                     compositing backward, no gradient matrix, no zeros_like + accumulate pass over the 168 MB table)
+      update:        samvit_mlp at the end of the step; the s_grid table (99 % of the parameters, 1.2 GB of optimizer
+                     traffic) at the START of the next step on a second stream, hidden behind the frozen front, which
+                     does not read it (multi-GPU: reduce-scatter + Adam on the local shard + all-gather there).
+
+    One CUDA graph per step on one GPU; two graphs around the eager NCCL calls otherwise.  ``flush()`` applies a
+    pending table update (call before reading parameters)."""
+
+    def __init__(self, model, optimizer, n_rays, h, w, target_shape, world_size=1, use_graph=True):
+        from .fused import ray_features_supported
+        opt = model.opt
+        if not opt.with_sam or opt.sum_after_mlp or opt.with_mask:
+            raise UnsupportedConfig("FusedSAMStep covers the stage-2 step (--with_sam, deferred shading, no mask heads)")
+        if not ray_features_supported(model.s_grid):
+            raise UnsupportedConfig("FusedSAMStep needs a 3-D fp32 hash s_grid with 2, 4 or 8 features per level")
+        if h * w != n_rays:
+            raise UnsupportedConfig("FusedSAMStep renders one h x w feature map per step")
+        self.model, self.optimizer, self.world_size = model, optimizer, world_size
+        self.frame = FusedRGBFrame(model, n_rays, use_graph=False, bg_color=1.0)      # launched inside this step's graph
+        self.N, self.h, self.w = int(n_rays), int(h), int(w)
+        self.use_graph = bool(use_graph)
+        dev = self.dev = self.frame.dev
+        f32 = dict(device=dev, dtype=torch.float32)
+        g = model.s_grid
+        self.f_sam = torch.empty(self.N, g.num_levels * g.level_dim, **f32)
+        self.target = torch.empty(tuple(target_shape), **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.update_stream = torch.cuda.Stream(dev)
+        self.pending_main = False
+        self.sharded_update = True
+        self.graphs = None
+        self.eager_runs = 0
+        self.last_f = None
+        a, b = self._main_range()
+        if a != 0 or g.embeddings.grad is None or not g.embeddings.grad.is_contiguous():
+            raise RuntimeError("FusedSAMStep needs s_grid.embeddings to lead a FusedAdam flat buffer")
+        self._head_params = [p for p in model.samvit_mlp.parameters()]
+
+    def _main_range(self):
+        return self.optimizer.ranges[id(self.model.s_grid.embeddings)]
+
+    # ------------------------------------------------------------------------------------------------------
+    def _launch_front(self):
+        """Frozen stage-1 forward: nothing here reads s_grid."""
+        with torch.no_grad():
+            self.frame._launch_render()
+            self.sh = self.model.view_encoder(self.frame.rays_d)                      # [N,16], once per ray
+
+    def _launch_back(self):
+        m, lib, N, fr = self.model, _lib.load(), self.N, self.frame
+        span, check = _lib.stats.span, _lib.check
+        L = fr.lv[2]
+        T = L["T"]
+        g = m.s_grid
+        S, H, C, nl = float(np.log2(g.per_level_scale)), int(g.base_resolution), int(g.level_dim), int(g.num_levels)
+        st = _lib.current_stream(self.dev)
+        with span("ray_features_forward", N=N, T=T, C=C):
+            rc = lib.sanerf_ray_features_forward(L["x01"].data_ptr(), L["weights"].data_ptr(), g.embeddings.data_ptr(),
+                                                 g.offsets.data_ptr(), N, T, C, nl, S, H, self.f_sam.data_ptr(), st)
+        check(rc, "ray_features_forward")
+        ws, depth = L["ws"], L["depth"]
+        if m.opt.sam_use_view_direction:                                             # renderer.py:380 / :383
+            parts = [self.f_sam, fr.geo_sum, ws.unsqueeze(-1) * self.sh, fr.image, depth.unsqueeze(-1)]
+        else:
+            parts = [self.f_sam, fr.geo_sum, fr.image, depth.unsqueeze(-1)]
+        f = torch.cat(parts, dim=-1).requires_grad_(True)
+        with torch.enable_grad():
+            samvit = m.samvit_mlp(f)
+            pred = samvit.view(self.h, self.w, -1).permute(2, 0, 1).unsqueeze(0)
+            if pred.shape[-2:] != self.target.shape[-2:]:
+                pred = torch.nn.functional.interpolate(pred, self.target.shape[-2:], mode="bilinear")
+            loss = torch.nn.functional.mse_loss(pred, self.target)
+        loss.backward(inputs=[f, *self._head_params])      # one traversal; parameter gradients accumulate into the flat views
+        self.loss.copy_(loss.detach().reshape(1))
+        self.last_f, self.samvit = f.detach(), samvit.detach()
+        g_sam = f.grad[:, :nl * C].contiguous()
+        st = _lib.current_stream(self.dev)
+        with span("ray_features_backward", N=N, T=T, C=C):
+            rc = lib.sanerf_ray_features_backward(L["x01"].data_ptr(), L["weights"].data_ptr(), g_sam.data_ptr(),
+                                                  g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), st)
+        check(rc, "ray_features_backward")
+
+    # ---- optimizer ----------------------------------------------------------------------------------------
+    def _update_main(self):
+        a, b = self._main_range()
+        opt = self.optimizer
+        if self.world_size == 1:
+            opt.apply(a, b, grad_scale=1.0, zero_grad=True)
+            return
+        world, rank = self.world_size, dist.get_rank()
+        if not self.sharded_update:
+            dist.all_reduce(opt.flat_grad[a:b], op=dist.ReduceOp.SUM)
+            opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True)
+            return
+        from .parallel import sharded_update
+        sharded_update(opt.flat_param, opt.flat_grad, a, b,
+                       lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True), world, rank)
+
+    def _update_rest(self):
+        b, n = self._main_range()[1], self.optimizer.flat_param.numel()
+        if self.world_size > 1:
+            dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
+        self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
+
+    def flush(self):
+        if self.pending_main:
+            with torch.cuda.device(self.dev):
+                self._update_main()
+            self.pending_main = False
+
+    def _deferred_update(self):
+        main, upd = torch.cuda.current_stream(self.dev), self.update_stream
+        upd.wait_stream(main)
+        with torch.cuda.stream(upd):
+            self._update_main()                            # previous step's table gradient (zero before the first step)
+            self.optimizer.schedule()                      # then this step's learning rate / bias corrections
+        return main, upd
+
+    def _whole_step(self):
+        main, upd = self._deferred_update()
+        self._launch_front()
+        main.wait_stream(upd)
+        self._launch_back()
+        self._update_rest()
+
+    def gradients_only(self, rays_o, rays_d, target):
+        """Forward + backward without any optimizer update (tests): gradients are left in the flat bucket."""
+        self.flush()
+        self.frame.rays_o.copy_(rays_o); self.frame.rays_d.copy_(rays_d); self.target.copy_(target)
+        with torch.cuda.device(self.dev):
+            self._launch_front()
+            self._launch_back()
+        return self.loss[0]
+
+    def __call__(self, rays_o, rays_d, target):
+        """One training step; inputs may live on the host (pinned) or the device.  Returns the loss (static buffer)."""
+        fr = self.frame
+        fr.rays_o.copy_(rays_o, non_blocking=True)
+        fr.rays_d.copy_(rays_d, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        with torch.cuda.device(self.dev):
+            if not self.use_graph or self.eager_runs < 1:
+                self.eager_runs += 1
+                self._whole_step()
+            elif self.world_size == 1:
+                if self.graphs is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._whole_step()
+                    self.graphs = (g,)
+                self.graphs[0].replay()
+            else:
+                if self.graphs is None:
+                    gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gf):
+                        self._launch_front()
+                    with torch.cuda.graph(gb):
+                        self._launch_back()
+                    self.graphs = (gf, gb)
+                main, upd = self._deferred_update()
+                self.graphs[0].replay()
+                main.wait_stream(upd)
+                self.graphs[1].replay()
+                self._update_rest()
+            self.pending_main = True
+        return self.loss[0]

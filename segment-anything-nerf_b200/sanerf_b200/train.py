@@ -101,12 +101,14 @@ class SAMTrainer:
     """Stage-2 step on frozen stage-1 parameters: render the [h,w] low-resolution rays' 256-d feature map and
     regress a target feature map (nerf/utils.py:1095-1106; the ViT-H target is replaced by a given tensor)."""
 
-    def __init__(self, model, lr=1e-2, iters=5000, world_size=1, use_graph=True):
+    def __init__(self, model, lr=1e-2, iters=5000, world_size=1, use_graph=True, fused_step=True):
         assert model.opt.with_sam
         self.model = model.train()
         self.world_size = world_size
         self.use_graph = bool(use_graph)
+        self.fused_step = bool(fused_step)
         self._graphs = {}                                 # (n_rays, h, w, target shape) -> captured step
+        self._plans = {}                                  # same key -> FusedSAMStep (hand-scheduled step) or None
         trainable = set()
         for m in (model.s_grid, model.samvit_mlp):
             trainable.update(id(p) for p in m.parameters())
@@ -133,6 +135,12 @@ class SAMTrainer:
         ~150 host-side launches that otherwise dominate this 4096-ray step."""
         dev = self.optimizer.flat_param.device
         key = (tuple(rays_o.shape), h, w, tuple(target.shape))
+        plan = self.plan(rays_o.shape[0], h, w, tuple(target.shape))
+        for other in self._plans.values():                # a pending table update of another shape's plan comes first
+            if other is not None and other is not plan:
+                other.flush()
+        if plan is not None:
+            return plan(rays_o, rays_d, target)
         entry = self._graphs.get(key)
         if not self.use_graph or entry is None:
             rays_o, rays_d, target = (t.to(dev, non_blocking=True) for t in (rays_o, rays_d, target))
@@ -161,6 +169,28 @@ class SAMTrainer:
         if self.world_size > 1:
             dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
         self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
+
+    def plan(self, n_rays, h, w, target_shape):
+        """The hand-scheduled stage-2 step (sanerf_b200/step.py: FusedSAMStep) for this input shape, or None when the
+        model is not the configuration it is written for (then the autograd path of ``step`` runs)."""
+        if not self.fused_step or not getattr(self.model, "tc_head", False) or not getattr(self.model, "fused", False):
+            return None
+        key = (n_rays, h, w, tuple(target_shape))
+        if key not in self._plans:
+            from .step import FusedSAMStep, UnsupportedConfig
+            try:
+                self._plans[key] = FusedSAMStep(self.model, self.optimizer, n_rays, h, w, target_shape,
+                                                world_size=self.world_size, use_graph=self.use_graph)
+            except UnsupportedConfig:
+                self._plans[key] = None
+        return self._plans[key]
+
+    def flush(self):
+        """Apply the s_grid update the hand-scheduled step defers to the start of the next step (call before reading
+        parameters: checkpoint, evaluation)."""
+        for plan in self._plans.values():
+            if plan is not None:
+                plan.flush()
 
 
 _FRAME_PLANS = {}

@@ -122,7 +122,7 @@ def test_sam_trainer_graph_replay_equals_eager(cuda):
         for enc in [model_a.grid, *model_a.prop_encoders, model_a.s_grid]:
             enc.embeddings.uniform_(-0.5, 0.5)
     model_b = copy.deepcopy(model_a)
-    ta, tb = SAMTrainer(model_a, use_graph=True), SAMTrainer(model_b, use_graph=False)
+    ta, tb = SAMTrainer(model_a, use_graph=True, fused_step=False), SAMTrainer(model_b, use_graph=False, fused_step=False)
     g = torch.Generator().manual_seed(5)
     o = (torch.rand(64, 3, generator=g) - 0.5).cuda()
     d = torch.nn.functional.normalize(torch.randn(64, 3, generator=g), dim=-1).cuda()
@@ -134,3 +134,94 @@ def test_sam_trainer_graph_replay_equals_eager(cuda):
     for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
     assert not model_a.grid.embeddings.requires_grad and model_a.s_grid.embeddings.requires_grad
+
+
+# ------------------------------------------------------------------------------------- stage 2 (SAM feature field)
+def _setup_sam(h, w, seed=0):
+    from nerf.network import NeRFNetwork
+    from sanerf_b200.train import default_opt
+    torch.manual_seed(seed)
+    model = NeRFNetwork(default_opt(with_sam=True)).cuda()
+    with torch.no_grad():
+        for enc in [model.grid, model.s_grid, *model.prop_encoders]:
+            offs = enc.offsets.tolist()
+            for l in range(len(offs) - 1):
+                enc.embeddings[offs[l]:offs[l + 1]].uniform_(-0.5, 0.5).mul_(1.0 / enc.per_level_scale ** l)
+    n = h * w
+    g = torch.Generator().manual_seed(seed + 1)
+    o = (torch.rand(n, 3, generator=g) - 0.5).cuda()
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+    target = torch.randn(1, 256, h, w, generator=g).cuda()
+    return model, o, d, target
+
+
+@pytest.mark.parametrize("C", [2, 4, 8])
+def test_ray_features_equal_encode_then_weighted_sum(cuda, C):
+    """fused.ray_features == sum_i w_i * GridEncoder(x_i) (renderer.py:302-303, 377), forward and table gradient."""
+    from gridencoder import GridEncoder
+    from sanerf_b200 import fused
+    torch.manual_seed(0)
+    enc = GridEncoder(input_dim=3, num_levels=8, level_dim=C, base_resolution=8, log2_hashmap_size=12,
+                      desired_resolution=256).cuda()
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    N, T = 300, 32
+    o = torch.rand(N, 1, 3, device="cuda") * 0.6 + 0.2
+    step = torch.randn(N, 1, 3, device="cuda") * 0.01
+    x01 = (o + step * torch.arange(T, device="cuda").view(1, T, 1)).clamp(0, 1).contiguous()   # ray-ordered: shared cells
+    x01[5, 3] = 1.5                                                                            # out of range: encodes to zero
+    w = torch.rand(N, T, device="cuda")
+    w[:, 20:] = 0.0                                                                            # terminated samples
+    g_out = torch.randn(N, 8 * C, device="cuda")
+
+    got = fused.ray_features(x01, w, enc)
+    got.backward(g_out)
+    g_got = enc.embeddings.grad.clone()
+    enc.embeddings.grad = None
+    feats = enc(x01 * 2 - 1, bound=1)                                                          # maps back to [0,1]
+    exp = (w.unsqueeze(-1) * feats).sum(-2)
+    exp.backward(g_out)
+    torch.testing.assert_close(got, exp, rtol=1e-4, atol=1e-5)
+    g_exp = enc.embeddings.grad
+    assert ((g_got - g_exp).norm() / g_exp.norm()).item() < 1e-5
+    torch.testing.assert_close(g_got, g_exp, rtol=1e-3, atol=1e-5 * float(g_exp.abs().max()))
+
+
+def test_fused_sam_step_gradients_match_autograd(cuda):
+    from sanerf_b200.step import FusedSAMStep
+    from sanerf_b200.train import SAMTrainer
+    h = w = 12
+    model, o, d, target = _setup_sam(h, w)
+    trainer = SAMTrainer(model, fused_step=False, use_graph=False)
+    loss_ref = trainer._forward_backward(o, d, target, h, w)
+    ref = {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
+    assert set(n.split(".")[0] for n in ref) == {"s_grid", "samvit_mlp"}
+    trainer.optimizer.zero_grad()
+    plan = FusedSAMStep(model, trainer.optimizer, h * w, h, w, target.shape, use_graph=False)
+    loss = plan.gradients_only(o, d, target)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(loss, loss_ref, rtol=1e-5, atol=1e-7)
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        a, b = p.grad, ref[n]
+        assert float(b.abs().max()) > 0, n
+        assert ((a - b).norm() / b.norm()).item() < 1e-4, n
+
+
+def test_fused_sam_step_graph_replay_equals_autograd_steps(cuda):
+    """Four optimizer steps: hand-scheduled step replayed as one CUDA graph == the autograd SAM step."""
+    from sanerf_b200.train import SAMTrainer
+    h = w = 16
+    model_a, o, d, target = _setup_sam(h, w, seed=2)
+    model_b = copy.deepcopy(model_a)
+    ta, tb = SAMTrainer(model_a), SAMTrainer(model_b, fused_step=False, use_graph=False)
+    assert ta.plan(h * w, h, w, tuple(target.shape)) is not None
+    la = lb = None
+    for _ in range(4):
+        la, lb = ta.step(o, d, target, h, w).clone(), tb.step(o, d, target, h, w).clone()
+        torch.testing.assert_close(la, lb, rtol=2e-4, atol=1e-6)
+    ta.flush()
+    assert ta._plans[(h * w, h, w, tuple(target.shape))].graphs is not None
+    for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
