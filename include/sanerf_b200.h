@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 14
+#define SANERF_ABI_VERSION 15
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -281,6 +281,26 @@ SANERF_API int sanerf_view_head(const float* geo_sum, const float* weights_sum, 
                      const float* w1, const float* w2, const float* w3, float bg, float loss_weight, uint32_t N,
                      float* image, float* loss, float* g_geo_sum, float* g_weights_sum, float* g_w1, float* g_w2,
                      float* g_w3, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * fp32-parity GEMM on the tensor cores (tcgen05.mma.kind::tf32, accumulators in tensor memory) with the elementwise
+ * neighbours of a Linear layer folded in: the building block of the SAM feature head
+ *   samvit_mlp = SkipConnMLP(163 -> 256 x 4 -> 256, bias, leaky ReLU, skip at layer 2)  (nerf/network.py:36-75, 120-123),
+ * replacing its nn.Linear / cuBLAS SGEMM + bias + activation (+ autograd: data-gradient GEMM, weight-gradient GEMM,
+ * activation backward) launches.
+ *   C[M,N] (op)= A . B^T ;  A f32 [M,K] (lda) or, a_trans != 0, stored [K,M];  B f32 [N,K] (ldb) or, b_trans != 0, [K,N]
+ *   epilogue 0: C  = act(acc + bias[n])          bias may be NULL; act != 0: leaky ReLU with `slope`
+ *   epilogue 1: C  = acc * (mask[m,n] > 0 ? 1 : slope) for n < mask_cols (mask f32 [M, >= mask_cols], ldm)
+ *   epilogue 2: C += acc  (reductions; K may be split over k_splits CTAs: weight gradients over the batch rows)
+ *   precision 0: 3-term tf32 split (fp32 parity, ~2^-21 per product), 1: one tf32 pass.
+ * Row strides need not be multiples of 4 (nn.Linear(163, .) / (419, .) weights): unaligned rows take scalar loads.
+ * sanerf_colsum_add: out[n] += sum_m X[m,n] (bias gradient).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const float* B, uint32_t ldb, int b_trans, float* C,
+                   uint32_t ldc, uint32_t M, uint32_t N, uint32_t K, uint32_t k_splits, int epilogue,
+                   const float* bias, int act, float slope, const float* mask, uint32_t ldm, uint32_t mask_cols,
+                   int precision, void* stream);
+SANERF_API int sanerf_colsum_add(const float* X, uint32_t ld, uint32_t M, uint32_t N, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adam over one flat fp32 buffer (main.py:296 Adam(eps=1e-15), :312-313 LambdaLR 0.1^min(it/iters,1)).

@@ -51,7 +51,14 @@ class SkipConnMLP(nn.Module):
             layers.append(nn.Linear(fan_in, dim_out if i == num_layers - 1 else dim_hidden, bias=bias))
         self.net = nn.ModuleList(layers)
 
+    tc = False               # set by NeRFNetwork: run on the tensor cores (sanerf_b200.fused.skip_mlp) when possible
+    precision = "fp32"
+
     def forward(self, x, save_intermedian_results=False):
+        if self.tc and not save_intermedian_results and x.dim() >= 2:
+            flat = x.reshape(-1, x.shape[-1])
+            if fused.skip_mlp_supported(self, flat):
+                return fused.skip_mlp(flat, self, self.precision).view(*x.shape[:-1], -1)
         x_in = x
         keep = [] if save_intermedian_results else None
         for i, layer in enumerate(self.net):
@@ -91,6 +98,7 @@ class NeRFNetwork(NeRFRenderer):
                 SkipConnMLP(self.s_dim + self.geom_feat_dim + self.view_in_dim + 4, 256, 256, 5, skip_layers=[2],
                             bias=True),
                 nn.LayerNorm(256))
+            self.samvit_mlp[0].tc, self.samvit_mlp[0].precision = self.tc_head, self.mlp_precision
 
         self.prop_encoders = nn.ModuleList()
         self.prop_mlp = nn.ModuleList()

@@ -350,6 +350,109 @@ def ray_features(x01, weights, encoder):
                               int(encoder.base_resolution))
 
 
+# ------------------------------------------------------------------------- wide MLP head on the tensor cores
+def gemm_tc(A, B, C, M, N, K, a_trans=False, b_trans=False, k_splits=1, epilogue=0, bias=None, act=False, slope=0.01,
+            mask=None, mask_cols=0, precision=0):
+    """C[M,N] (op)= A . B^T through ``sanerf_gemm_tc`` (csrc/gemm_tc.cu); row strides are taken from the tensors."""
+    for t in (A, B, C, mask):
+        if t is not None and (t.stride(-1) != 1 or t.dtype != torch.float32 or not t.is_cuda):
+            raise RuntimeError("gemm_tc needs fp32 CUDA matrices with unit column stride")
+    with _lib.stats.span("gemm_tc", M=M, N=N, K=K, epilogue=epilogue):
+        rc = _lib.load().sanerf_gemm_tc(A.data_ptr(), A.stride(0), int(a_trans), B.data_ptr(), B.stride(0), int(b_trans),
+                                        C.data_ptr(), C.stride(0), M, N, K, k_splits, epilogue, _lib.ptr(bias), int(act),
+                                        float(slope), _lib.ptr(mask), 0 if mask is None else mask.stride(0), mask_cols,
+                                        precision, _stream(C))
+    _lib.check(rc, "gemm_tc")
+
+
+def skip_mlp_forward(x, weights, biases, skip_layers, precision=0, slope=0.01):
+    """SkipConnMLP.forward (network.py:57-75): every layer = one tensor-core GEMM with bias + leaky ReLU in its epilogue.
+    Returns (output [M, out], the list of layer inputs saved for the backward)."""
+    M, n = x.shape[0], len(weights)
+    inputs, h = [], x
+    for i, (W, b) in enumerate(zip(weights, biases)):
+        if i in skip_layers:
+            h = torch.cat([h, x], dim=-1)
+        inputs.append(h)
+        out = torch.empty(M, W.shape[0], device=x.device, dtype=torch.float32)
+        gemm_tc(h, W, out, M, W.shape[0], W.shape[1], bias=b, act=(i + 1 < n), slope=slope, precision=precision)
+        h = out
+    return h, inputs
+
+
+def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, precision=0, slope=0.01,
+                      need_input_grad=True, k_splits=16):
+    """Backward of ``skip_mlp_forward``: ACCUMULATES weight / bias gradients into ``g_weights`` / ``g_biases`` (pre-zeroed
+    or holding earlier contributions) and returns the gradient of the MLP input.  Per layer: one weight-gradient GEMM
+    split over the batch rows, one column sum, one data-gradient GEMM whose epilogue applies the derivative of the
+    previous layer's leaky ReLU (its saved output is the mask)."""
+    M = g_out.shape[0]
+    lib = _lib.load()
+    g = g_out.contiguous()
+    g_skip = None
+    for i in range(len(weights) - 1, -1, -1):
+        W, h_in = weights[i], inputs[i]
+        n_out, n_in = W.shape
+        gemm_tc(g, h_in, g_weights[i], n_out, n_in, M, a_trans=True, b_trans=True, k_splits=k_splits, epilogue=2,
+                precision=precision)
+        if g_biases[i] is not None:
+            with _lib.stats.span("colsum_add", M=M, N=n_out):
+                rc = lib.sanerf_colsum_add(g.data_ptr(), g.stride(0), M, n_out, g_biases[i].data_ptr(), _stream(g))
+            _lib.check(rc, "colsum_add")
+        if i == 0:
+            if not need_input_grad:
+                return None
+            gx = torch.empty(M, n_in, device=g.device, dtype=torch.float32)
+            gemm_tc(g, W, gx, M, n_in, n_out, b_trans=True, precision=precision)
+            return gx if g_skip is None else gx + g_skip
+        hid = weights[i - 1].shape[0]
+        d_in = torch.empty(M, n_in, device=g.device, dtype=torch.float32)
+        gemm_tc(g, W, d_in, M, n_in, n_out, b_trans=True, epilogue=1, mask=h_in, mask_cols=hid, slope=slope,
+                precision=precision)
+        if i in skip_layers:
+            g_skip = d_in[:, hid:] if g_skip is None else g_skip + d_in[:, hid:]
+            g = d_in[:, :hid].contiguous()
+        else:
+            g = d_in
+
+
+class _SkipMLP(Function):
+    @staticmethod
+    def forward(ctx, x, skip_layers, precision, has_bias, *params):
+        n = len(params) // 2 if has_bias else len(params)
+        weights = [p.detach() for p in (params[0::2] if has_bias else params)]
+        biases = [p.detach() for p in params[1::2]] if has_bias else [None] * n
+        out, inputs = skip_mlp_forward(x.detach().contiguous().float(), weights, biases, skip_layers, precision)
+        ctx.save_for_backward(*inputs, *weights)
+        ctx.meta = (n, tuple(skip_layers), precision, has_bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        n, skip_layers, precision, has_bias = ctx.meta
+        saved = ctx.saved_tensors
+        inputs, weights = list(saved[:n]), list(saved[n:])
+        gW = [torch.zeros_like(w) for w in weights]
+        gB = [torch.zeros(w.shape[0], device=w.device) if has_bias else None for w in weights]
+        gx = skip_mlp_backward(g_out.float(), inputs, weights, skip_layers, gW, gB, precision,
+                               need_input_grad=ctx.needs_input_grad[0])
+        grads = [v for pair in zip(gW, gB) for v in pair] if has_bias else gW
+        return (gx, None, None, None, *grads)
+
+
+def skip_mlp_supported(mlp, x):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and not torch.is_autocast_enabled()
+            and all(l.weight.dtype == torch.float32 for l in mlp.net)
+            and len({l.bias is None for l in mlp.net}) == 1)
+
+
+def skip_mlp(x, mlp, precision="fp32"):
+    """SkipConnMLP on the tensor cores (autograd-aware); ``mlp`` = nerf.network.SkipConnMLP."""
+    has_bias = mlp.net[0].bias is not None
+    params = [t for l in mlp.net for t in ((l.weight, l.bias) if has_bias else (l.weight,))]
+    return _SkipMLP.apply(x, tuple(mlp.skip_layers), PRECISION_IDS[precision], has_bias, *params)
+
+
 class _ProposalLoss(Function):
     """sum over proposal levels of the inter-level loss; weights of the final level are constants."""
 

@@ -215,3 +215,57 @@ def test_field_head_backward_fused_scatter_equals_separate_kernel(cuda):
     torch.testing.assert_close(gt_b, gt_a, rtol=1e-3, atol=1e-5 * gt_a.abs().max().item())
     for a, b in zip(gw_a, gw_b):
         torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5 * a.abs().max().item())
+
+
+# ------------------------------------------------------------------------ wide MLP head (csrc/gemm_tc.cu)
+@pytest.mark.parametrize("M,N,K", [(300, 70, 45), (128, 64, 32), (4096, 256, 163), (257, 419, 256)])
+@pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, True)])
+def test_gemm_tc_fp32_parity(cuda, M, N, K, a_trans, b_trans):
+    """3xTF32 tensor-core GEMM against an fp64 product: far inside the 1e-3 fp32 bar, for ragged / unaligned shapes."""
+    from sanerf_b200 import fused
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = (A.double() @ B.double().t())
+    As = A.t().contiguous() if a_trans else A
+    Bs = B.t().contiguous() if b_trans else B
+    C = torch.full((M, N), 7.0, device="cuda")
+    fused.gemm_tc(As, Bs, C, M, N, K, a_trans=a_trans, b_trans=b_trans, bias=bias, act=True, slope=0.01)
+    exp = torch.nn.functional.leaky_relu(ref + bias.double(), 0.01)
+    scale = float(ref.abs().max())
+    assert float((C.double() - exp).abs().max()) < 2e-6 * scale * K ** 0.5
+    # one tf32 pass: the 1e-2 class
+    C1 = torch.empty(M, N, device="cuda")
+    fused.gemm_tc(As, Bs, C1, M, N, K, a_trans=a_trans, b_trans=b_trans, precision=1)
+    assert float((C1.double() - ref).abs().max()) < 2e-3 * scale
+    # masked data-gradient epilogue and split accumulating epilogue
+    mask = torch.randn(M, N, generator=g).cuda()
+    C2 = torch.empty(M, N, device="cuda")
+    fused.gemm_tc(As, Bs, C2, M, N, K, a_trans=a_trans, b_trans=b_trans, epilogue=1, mask=mask, mask_cols=N // 2, slope=0.01)
+    exp2 = ref.clone()
+    exp2[:, :N // 2] *= torch.where(mask[:, :N // 2] > 0, 1.0, 0.01).double()
+    assert float((C2.double() - exp2).abs().max()) < 2e-6 * scale * K ** 0.5
+    C3 = torch.ones(M, N, device="cuda")
+    fused.gemm_tc(As, Bs, C3, M, N, K, a_trans=a_trans, b_trans=b_trans, epilogue=2, k_splits=3)
+    assert float((C3.double() - (ref + 1)).abs().max()) < 2e-6 * scale * K ** 0.5
+
+
+def test_skip_mlp_tensor_core_equals_torch(cuda):
+    """samvit_mlp shape (network.py:120-123): forward, input gradient and every parameter gradient vs nn.Linear."""
+    import copy
+    from nerf.network import SkipConnMLP
+    torch.manual_seed(0)
+    ref = SkipConnMLP(163, 256, 256, 5, skip_layers=[2], bias=True).cuda()
+    tc = copy.deepcopy(ref)
+    tc.tc = True
+    x = torch.randn(500, 163, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = ref(xa), tc(xb)
+    torch.testing.assert_close(yb, ya, rtol=1e-4, atol=1e-5)
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+    torch.testing.assert_close(xb.grad, xa.grad, rtol=1e-4, atol=1e-5)
+    for (n, p), (_, q) in zip(ref.named_parameters(), tc.named_parameters()):
+        assert ((p.grad - q.grad).norm() / p.grad.norm()).item() < 1e-5, n
