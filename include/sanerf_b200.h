@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 15
+#define SANERF_ABI_VERSION 16
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -290,7 +290,8 @@ SANERF_API int sanerf_view_head(const float* geo_sum, const float* weights_sum, 
  * activation backward) launches.
  *   C[M,N] (op)= A . B^T ;  A f32 [M,K] (lda) or, a_trans != 0, stored [K,M];  B f32 [N,K] (ldb) or, b_trans != 0, [K,N]
  *   epilogue 0: C  = act(acc + bias[n])          bias may be NULL; act != 0: leaky ReLU with `slope`
- *   epilogue 1: C  = acc * (mask[m,n] > 0 ? 1 : slope) for n < mask_cols (mask f32 [M, >= mask_cols], ldm)
+ *   epilogue 1: C  = acc * (mask[m,n] > 0 ? 1 : slope) for n < mask_cols (mask f32 [M, >= mask_cols], ldm);
+ *               colsum f32 [mask_cols] or NULL: colsum[n] += sum_m C[m,n] (the bias gradient of the layer below)
  *   epilogue 2: C += acc  (reductions; K may be split over k_splits CTAs: weight gradients over the batch rows)
  *   precision 0: 3-term tf32 split (fp32 parity, ~2^-21 per product), 1: one tf32 pass.
  * Row strides need not be multiples of 4 (nn.Linear(163, .) / (419, .) weights): unaligned rows take scalar loads.
@@ -299,8 +300,20 @@ SANERF_API int sanerf_view_head(const float* geo_sum, const float* weights_sum, 
 SANERF_API int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const float* B, uint32_t ldb, int b_trans, float* C,
                    uint32_t ldc, uint32_t M, uint32_t N, uint32_t K, uint32_t k_splits, int epilogue,
                    const float* bias, int act, float slope, const float* mask, uint32_t ldm, uint32_t mask_cols,
-                   int precision, void* stream);
+                   float* colsum, int precision, void* stream);
 SANERF_API int sanerf_colsum_add(const float* X, uint32_t ld, uint32_t M, uint32_t N, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tail of the stage-2 step in one kernel: LayerNorm(256) closing samvit_mlp (nerf/network.py:120-123) + the MSE against
+ * the target feature map (nerf/utils.py:1100-1106), forward and backward.
+ *   x f32 [M,256] (MLP output), gamma / beta f32 [256], eps (torch default 1e-5);
+ *   target element (row, c) at target[c * t_col_stride + row * t_row_stride] (the [1,256,h,w] map read in place:
+ *   t_col_stride = h*w, t_row_stride = 1);  y_out f32 [M,256] or NULL (the normalised features);
+ *   loss (1 float) += mean((y - t)^2);  g_x f32 [M,256] is overwritten;  g_gamma / g_beta f32 [256] are accumulated into.
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_layernorm_mse(const float* x, const float* gamma, const float* beta, float eps, const float* target,
+                         uint64_t t_row_stride, uint64_t t_col_stride, uint32_t M, uint32_t N, float* y_out,
+                         float* loss, float* g_x, float* g_gamma, float* g_beta, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adam over one flat fp32 buffer (main.py:296 Adam(eps=1e-15), :312-313 LambdaLR 0.1^min(it/iters,1)).

@@ -9,7 +9,8 @@
 //                                 B: [N,K] row-major, or given transposed as [K,N]   (b_trans)
 //   epilogue 0:  C  = act(acc + bias[n])                       forward layer (act = leaky ReLU or identity)
 //   epilogue 1:  C  = acc * act'(mask[m,n])  for n < mask_cols  data gradient of a layer, times the derivative of the
-//                                                              PREVIOUS layer's activation (mask = its saved output)
+//                                                              PREVIOUS layer's activation (mask = its saved output);
+//                colsum[n] += sum_m C[m,n]                     = that layer's bias gradient, reduced in the same epilogue
 //   epilogue 2:  C += acc   (vector reductions)                weight gradient, split over the 4096 rows (gridDim.z)
 //
 // Arithmetic: tcgen05.mma.kind::tf32 with fp32 accumulators in tensor memory; precision 0 evaluates every product as
@@ -17,7 +18,7 @@
 // the field head (mlp_tc.cu); precision 1 = one pass on round-to-nearest tf32 operands.
 //
 // One CTA = one 128 x 64 tile of C.  K is consumed in chunks of 32: all 256 threads fetch the chunk from global memory
-// into registers one chunk ahead (float4 loads; transposed operands through a 4x4 register transpose), split it into hi /
+// into registers two chunks ahead (float4 loads; transposed operands through a 4x4 register transpose), split it into hi /
 // lo planes of the no-swizzle K-major UMMA layout in shared memory (two stages), and one elected thread issues the 12
 // MMAs of the chunk; tcgen05.commit on the stage's mbarrier releases it for the chunk after next.
 #include "common.cuh"
@@ -27,7 +28,13 @@ namespace sanerf {
 
 namespace gemm {
 constexpr uint32_t kBM = 128, kBN = 64, kKC = 32, kThreads = 256, kStages = 2;
-constexpr uint32_t kAPlane = kBM * kKC * 4, kBPlane = kBN * kKC * 4;
+// Byte stride between consecutive 4-element K chunks of a tile with `rows` rows (the descriptors' leading byte offset):
+// one 16-byte slot of padding per chunk column rotates the bank a (row, chunk) slot lands in, so a warp that writes
+// 4 rows x 8 chunks (coalesced global loads: 8 lanes per 128-byte row segment) stores without bank conflicts.
+__host__ __device__ constexpr uint32_t chunk_stride(uint32_t rows) { return rows * 16u + 16u; }
+constexpr uint32_t kAPlane = chunk_stride(kBM) * (kKC / 4) , kBPlane = chunk_stride(kBN) * (kKC / 4);
+static_assert(kAPlane % 128 == 0 && kBPlane % 128 == 0, "operand planes must stay 128-byte aligned");
+static_assert(kKC == 32, "the loaders map 8 lanes to the 8 chunks of a 32-wide K slice");
 constexpr uint32_t kStageBytes = 2 * kAPlane + 2 * kBPlane;           // A hi | A lo | B hi | B lo
 constexpr uint32_t kSmem = kStages * kStageBytes + 128;
 constexpr uint32_t kTmemCols = 64;
@@ -39,6 +46,7 @@ struct GemmParams {
     float* C;
     const float* bias;
     const float* mask;
+    float* colsum;
     uint32_t lda, ldb, ldc, ldm;
     uint32_t M, N, K;
     uint32_t chunks_per_split;
@@ -56,7 +64,7 @@ __device__ __forceinline__ float gemm_round_tf32(float x) {
 // 4 consecutive K elements of row r -> hi / lo planes of a chunk-major K-major tile with `rows` rows
 __device__ __forceinline__ void gemm_put_chunk(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t rows, uint32_t r, uint32_t chunk,
                                                float a, float b, float c, float d, bool split) {
-    const uint32_t off = chunk * (rows * 16u) + r * 16u;
+    const uint32_t off = chunk * gemm::chunk_stride(rows) + r * 16u;
     if (split) {
         float h0, h1, h2, h3, l0, l1, l2, l3;
         umma::split_tf32(a, h0, l0); umma::split_tf32(b, h1, l1); umma::split_tf32(c, h2, l2); umma::split_tf32(d, h3, l3);
@@ -81,8 +89,10 @@ __device__ __forceinline__ float4 gemm_load4(const float* __restrict__ p, uint32
 }
 
 // One operand's share of a K chunk, held in registers between the global loads and the shared-memory stores.
-//   normal  (src [rows][K], ld): item = (row, 4-element K chunk); ROWS*8 items, ROWS*8/256 per thread
-//   transposed (src [K][rows], ld): item = (4 rows, 4 K) block = 4 float4 loads along the contiguous row index
+//   normal  (src [rows][K], ld): item = (row, 4-element K chunk), 8 consecutive lanes = the 128 contiguous bytes of one
+//           row segment (4 lines per warp load instead of 32); ROWS*8 items, ROWS*8/256 per thread
+//   transposed (src [K][rows], ld): item = (4 rows, 4 K) block = 4 float4 loads along the contiguous row index; lanes
+//           vary fastest along K so that the four transposed 16-byte stores of a warp spread over all banks
 template <uint32_t ROWS>
 struct OperandRegs {
     static constexpr uint32_t kItems = ROWS * 8u / gemm::kThreads;       // normal orientation: 4 (A) or 2 (B)
@@ -94,13 +104,13 @@ struct OperandRegs {
 #pragma unroll
             for (uint32_t j = 0; j < kItems; ++j) {
                 const uint32_t id = tid + gemm::kThreads * j;
-                const uint32_t row = id % ROWS, chunk = id / ROWS;
+                const uint32_t row = id >> 3, chunk = id & 7u;
                 const uint32_t r = row0 + row, k = k0 + chunk * 4u;
                 v[j] = (r < row_limit) ? gemm_load4(src + (size_t)r * ld + k, k, k_limit, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
-            const uint32_t row4 = tid % (ROWS / 4u), k4 = tid / (ROWS / 4u);
-            const bool mine = k4 < gemm::kKC / 4u;
+            const uint32_t k4 = tid & 7u, row4 = tid >> 3;
+            const bool mine = row4 < ROWS / 4u;
 #pragma unroll
             for (uint32_t i = 0; i < 4; ++i) {
                 const uint32_t k = k0 + k4 * 4u + i, r = row0 + row4 * 4u;
@@ -115,11 +125,11 @@ struct OperandRegs {
 #pragma unroll
             for (uint32_t j = 0; j < kItems; ++j) {
                 const uint32_t id = tid + gemm::kThreads * j;
-                gemm_put_chunk(hi, lo, ROWS, id % ROWS, id / ROWS, v[j].x, v[j].y, v[j].z, v[j].w, split);
+                gemm_put_chunk(hi, lo, ROWS, id >> 3, id & 7u, v[j].x, v[j].y, v[j].z, v[j].w, split);
             }
         } else {
-            const uint32_t row4 = tid % (ROWS / 4u), k4 = tid / (ROWS / 4u);
-            if (k4 < gemm::kKC / 4u) {
+            const uint32_t k4 = tid & 7u, row4 = tid >> 3;
+            if (row4 < ROWS / 4u) {
                 gemm_put_chunk(hi, lo, ROWS, row4 * 4u + 0u, k4, v[0].x, v[1].x, v[2].x, v[3].x, split);
                 gemm_put_chunk(hi, lo, ROWS, row4 * 4u + 1u, k4, v[0].y, v[1].y, v[2].y, v[3].y, split);
                 gemm_put_chunk(hi, lo, ROWS, row4 * 4u + 2u, k4, v[0].z, v[1].z, v[2].z, v[3].z, split);
@@ -159,25 +169,24 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
     const bool b_vec = (p.ldb % 4u == 0u) && ((reinterpret_cast<uintptr_t>(p.B) & 15u) == 0u);
     const bool a_tr = p.a_trans != 0, b_tr = p.b_trans != 0;
 
-    OperandRegs<kBM> ra;
-    OperandRegs<kBN> rb;
-    ra.load(p.A, p.lda, a_tr, a_vec, m0, p.M, c_begin * kKC, p.K, tid);
-    rb.load(p.B, p.ldb, b_tr, b_vec, n0, p.N, c_begin * kKC, p.K, tid);
-
     constexpr uint32_t idesc = umma::idesc_tf32(kBM, kBN, 0, 0);
     constexpr uint32_t dhi = umma::desc_hi(128u, umma::kLayoutNone);
-    constexpr uint32_t a_step = (2u * kBM * 16u) >> 4, b_step = (2u * kBN * 16u) >> 4;     // 8 K elements = 2 chunks
+    constexpr uint32_t a_step = (2u * chunk_stride(kBM)) >> 4, b_step = (2u * chunk_stride(kBN)) >> 4;   // 8 K elements = 2 chunks
 
-    for (uint32_t c = 0; c < nc; ++c) {
+    // Two register sets: the global loads of chunks c+1 and c+2 are in flight while chunk c is split and stored, so the
+    // per-chunk critical path is the shared-memory stores + one CTA barrier, not an L2 round trip.
+    OperandRegs<kBM> ra0, ra1;
+    OperandRegs<kBN> rb0, rb1;
+    auto fetch = [&](OperandRegs<kBM>& ra, OperandRegs<kBN>& rb, uint32_t c) {
+        ra.load(p.A, p.lda, a_tr, a_vec, m0, p.M, (c_begin + c) * kKC, p.K, tid);
+        rb.load(p.B, p.ldb, b_tr, b_vec, n0, p.N, (c_begin + c) * kKC, p.K, tid);
+    };
+    auto consume = [&](const OperandRegs<kBM>& ra, const OperandRegs<kBN>& rb, uint32_t c) {
         const uint32_t s = c & 1u;
         uint8_t* stage = smem + s * kStageBytes;
         if (c >= kStages) umma::mbar_wait(umma::smem_u32(&s_bar[s]), ((c >> 1) - 1u) & 1u);     // MMAs of chunk c-2 done
         ra.store(stage, stage + kAPlane, a_tr, split, tid);
         rb.store(stage + 2 * kAPlane, stage + 2 * kAPlane + kBPlane, b_tr, split, tid);
-        if (c + 1u < nc) {                                            // next chunk's loads fly during this chunk's MMAs
-            ra.load(p.A, p.lda, a_tr, a_vec, m0, p.M, (c_begin + c + 1u) * kKC, p.K, tid);
-            rb.load(p.B, p.ldb, b_tr, b_vec, n0, p.N, (c_begin + c + 1u) * kKC, p.K, tid);
-        }
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
@@ -185,8 +194,8 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
             if (umma::elect_one()) {
                 umma::fence_after_sync();
                 const uint32_t sa = umma::smem_u32(stage);
-                const uint32_t dAh = umma::desc_lo(sa, kBM * 16u), dAl = umma::desc_lo(sa + kAPlane, kBM * 16u);
-                const uint32_t dBh = umma::desc_lo(sa + 2 * kAPlane, kBN * 16u), dBl = umma::desc_lo(sa + 2 * kAPlane + kBPlane, kBN * 16u);
+                const uint32_t dAh = umma::desc_lo(sa, chunk_stride(kBM)), dAl = umma::desc_lo(sa + kAPlane, chunk_stride(kBM));
+                const uint32_t dBh = umma::desc_lo(sa + 2 * kAPlane, chunk_stride(kBN)), dBl = umma::desc_lo(sa + 2 * kAPlane + kBPlane, chunk_stride(kBN));
                 uint32_t acc = (c > 0u) ? 1u : 0u;
 #pragma unroll
                 for (uint32_t ks = 0; ks < kKC / 8u; ++ks) {
@@ -202,6 +211,16 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
                 umma::commit(umma::smem_u32(&s_bar[s]));
             }
             __syncwarp();
+        }
+    };
+    fetch(ra0, rb0, 0u);
+    if (nc > 1u) fetch(ra1, rb1, 1u);
+    for (uint32_t c = 0; c < nc; c += 2u) {
+        consume(ra0, rb0, c);
+        if (c + 2u < nc) fetch(ra0, rb0, c + 2u);
+        if (c + 1u < nc) {
+            consume(ra1, rb1, c + 1u);
+            if (c + 3u < nc) fetch(ra1, rb1, c + 3u);
         }
     }
     {   // every MMA of this CTA has completed once the last commit has arrived
@@ -261,6 +280,13 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
                 }
             }
         }
+        if (p.colsum != nullptr && p.epilogue == 1 && nb < p.mask_cols) {     // warp-uniform: bias gradient of the layer below
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j) {
+                const float t = warp_sum((m < p.M) ? v[j] : 0.0f);
+                if (lane == 0 && nb + j < p.mask_cols && nb + j < p.N) red_add_f32(p.colsum + nb + j, t);
+            }
+        }
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -294,7 +320,7 @@ using namespace sanerf;
 extern "C" int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const float* B, uint32_t ldb, int b_trans, float* C,
                               uint32_t ldc, uint32_t M, uint32_t N, uint32_t K, uint32_t k_splits, int epilogue,
                               const float* bias, int act, float slope, const float* mask, uint32_t ldm, uint32_t mask_cols,
-                              int precision, void* stream) {
+                              float* colsum, int precision, void* stream) {
     if (M == 0 || N == 0) return SANERF_OK;
     SANERF_REQUIRE_PTR(A);
     SANERF_REQUIRE_PTR(B);
@@ -308,7 +334,7 @@ extern "C" int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const f
         return fail(SANERF_ERR_INVALID_ARG, "gemm_tc: K can only be split with the accumulating epilogue");
     const uint32_t chunks = (K + gemm::kKC - 1u) / gemm::kKC;
     GemmParams p;
-    p.A = A; p.B = B; p.C = C; p.bias = bias; p.mask = mask;
+    p.A = A; p.B = B; p.C = C; p.bias = bias; p.mask = mask; p.colsum = colsum;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldm = ldm;
     p.M = M; p.N = N; p.K = K;
     p.chunks_per_split = (chunks + k_splits - 1u) / k_splits;

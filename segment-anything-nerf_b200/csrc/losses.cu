@@ -169,12 +169,32 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
         vv = beta2 * vv + (1.0f - beta2) * gg * gg;
         pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
     };
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
-        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    // Every element is read and written exactly once per step: streaming (evict-first) accesses keep the pass from
+    // flushing the tables and activations of the kernels it overlaps with out of the L2.
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {                // two elements per trip: 8 independent 16-byte loads in flight
+        const size_t j = i + stride;
+        float4 pp = __ldcs(reinterpret_cast<float4*>(p) + i), gg = __ldcs(reinterpret_cast<float4*>(g) + i);
+        float4 mm = __ldcs(reinterpret_cast<float4*>(m) + i), vv = __ldcs(reinterpret_cast<float4*>(v) + i);
+        float4 pq = __ldcs(reinterpret_cast<float4*>(p) + j), gq = __ldcs(reinterpret_cast<float4*>(g) + j);
+        float4 mq = __ldcs(reinterpret_cast<float4*>(m) + j), vq = __ldcs(reinterpret_cast<float4*>(v) + j);
         update(pp.x, gg.x, mm.x, vv.x); update(pp.y, gg.y, mm.y, vv.y);
         update(pp.z, gg.z, mm.z, vv.z); update(pp.w, gg.w, mm.w, vv.w);
-        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+        update(pq.x, gq.x, mq.x, vq.x); update(pq.y, gq.y, mq.y, vq.y);
+        update(pq.z, gq.z, mq.z, vq.z); update(pq.w, gq.w, mq.w, vq.w);
+        __stcs(reinterpret_cast<float4*>(p) + i, pp); __stcs(reinterpret_cast<float4*>(m) + i, mm); __stcs(reinterpret_cast<float4*>(v) + i, vv);
+        __stcs(reinterpret_cast<float4*>(p) + j, pq); __stcs(reinterpret_cast<float4*>(m) + j, mq); __stcs(reinterpret_cast<float4*>(v) + j, vq);
+        if (zero_grad) {
+            __stcs(reinterpret_cast<float4*>(g) + i, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            __stcs(reinterpret_cast<float4*>(g) + j, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        }
+    }
+    for (; i < n4; i += stride) {
+        float4 pp = __ldcs(reinterpret_cast<float4*>(p) + i), gg = __ldcs(reinterpret_cast<float4*>(g) + i);
+        float4 mm = __ldcs(reinterpret_cast<float4*>(m) + i), vv = __ldcs(reinterpret_cast<float4*>(v) + i);
+        update(pp.x, gg.x, mm.x, vv.x); update(pp.y, gg.y, mm.y, vv.y);
+        update(pp.z, gg.z, mm.z, vv.z); update(pp.w, gg.w, mm.w, vv.w);
+        __stcs(reinterpret_cast<float4*>(p) + i, pp); __stcs(reinterpret_cast<float4*>(m) + i, mm); __stcs(reinterpret_cast<float4*>(v) + i, vv);
         if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -228,8 +248,11 @@ extern "C" int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
     if (align & 15u) return fail(SANERF_ERR_MISALIGNED, "adam_step: buffers must be 16-byte aligned");
     const size_t n4 = (size_t)n / 4;
     size_t blocks = div_up(n4 > 0 ? n4 : (size_t)1, (size_t)256);
-    const size_t cap = (size_t)kNumSMs * 8;
-    if (blocks > cap) blocks = cap;
+    // Short-lived CTAs (4 grid-stride trips each) instead of a persistent grid that owns every thread slot of the machine
+    // for the whole pass: the deferred table update runs on a default-priority stream beside the step's high-priority
+    // critical chain, whose CTAs can only be placed when CTAs of this kernel retire.  (Measured alternative: two
+    // persistent CTAs per SM - no better; the interference is in the memory system, see the streaming accesses above.)
+    blocks = div_up(blocks, (size_t)4);
     adam_step_kernel<<<(uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad);
     return check_launch("adam_step_kernel");

@@ -352,7 +352,7 @@ def ray_features(x01, weights, encoder):
 
 # ------------------------------------------------------------------------- wide MLP head on the tensor cores
 def gemm_tc(A, B, C, M, N, K, a_trans=False, b_trans=False, k_splits=1, epilogue=0, bias=None, act=False, slope=0.01,
-            mask=None, mask_cols=0, precision=0):
+            mask=None, mask_cols=0, colsum=None, precision=0):
     """C[M,N] (op)= A . B^T through ``sanerf_gemm_tc`` (csrc/gemm_tc.cu); row strides are taken from the tensors."""
     for t in (A, B, C, mask):
         if t is not None and (t.stride(-1) != 1 or t.dtype != torch.float32 or not t.is_cuda):
@@ -361,7 +361,7 @@ def gemm_tc(A, B, C, M, N, K, a_trans=False, b_trans=False, k_splits=1, epilogue
         rc = _lib.load().sanerf_gemm_tc(A.data_ptr(), A.stride(0), int(a_trans), B.data_ptr(), B.stride(0), int(b_trans),
                                         C.data_ptr(), C.stride(0), M, N, K, k_splits, epilogue, _lib.ptr(bias), int(act),
                                         float(slope), _lib.ptr(mask), 0 if mask is None else mask.stride(0), mask_cols,
-                                        precision, _stream(C))
+                                        _lib.ptr(colsum), precision, _stream(C))
     _lib.check(rc, "gemm_tc")
 
 
@@ -381,11 +381,12 @@ def skip_mlp_forward(x, weights, biases, skip_layers, precision=0, slope=0.01):
 
 
 def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, precision=0, slope=0.01,
-                      need_input_grad=True, k_splits=16):
+                      need_input_grad=True, k_splits=16, input_cols=None):
     """Backward of ``skip_mlp_forward``: ACCUMULATES weight / bias gradients into ``g_weights`` / ``g_biases`` (pre-zeroed
     or holding earlier contributions) and returns the gradient of the MLP input.  Per layer: one weight-gradient GEMM
-    split over the batch rows, one column sum, one data-gradient GEMM whose epilogue applies the derivative of the
-    previous layer's leaky ReLU (its saved output is the mask)."""
+    split over the batch rows and one data-gradient GEMM whose epilogue applies the derivative of the previous layer's
+    leaky ReLU (its saved output is the mask) and reduces that layer's bias gradient.  ``input_cols``: return only that many leading
+    columns of the input gradient."""
     M = g_out.shape[0]
     lib = _lib.load()
     g = g_out.contiguous()
@@ -395,25 +396,43 @@ def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, 
         n_out, n_in = W.shape
         gemm_tc(g, h_in, g_weights[i], n_out, n_in, M, a_trans=True, b_trans=True, k_splits=k_splits, epilogue=2,
                 precision=precision)
-        if g_biases[i] is not None:
+        if g_biases[i] is not None and i == len(weights) - 1:      # the other layers: in the epilogue that produced g
             with _lib.stats.span("colsum_add", M=M, N=n_out):
                 rc = lib.sanerf_colsum_add(g.data_ptr(), g.stride(0), M, n_out, g_biases[i].data_ptr(), _stream(g))
             _lib.check(rc, "colsum_add")
         if i == 0:
             if not need_input_grad:
                 return None
-            gx = torch.empty(M, n_in, device=g.device, dtype=torch.float32)
-            gemm_tc(g, W, gx, M, n_in, n_out, b_trans=True, precision=precision)
-            return gx if g_skip is None else gx + g_skip
+            cols = n_in if input_cols is None else min(int(input_cols), n_in)    # only the leading columns are wanted
+            gx = torch.empty(M, cols, device=g.device, dtype=torch.float32)
+            gemm_tc(g, W, gx, M, cols, n_out, b_trans=True, precision=precision)
+            return gx if g_skip is None else gx + g_skip[:, :cols]
         hid = weights[i - 1].shape[0]
         d_in = torch.empty(M, n_in, device=g.device, dtype=torch.float32)
         gemm_tc(g, W, d_in, M, n_in, n_out, b_trans=True, epilogue=1, mask=h_in, mask_cols=hid, slope=slope,
-                precision=precision)
+                colsum=g_biases[i - 1], precision=precision)
         if i in skip_layers:
             g_skip = d_in[:, hid:] if g_skip is None else g_skip + d_in[:, hid:]
             g = d_in[:, :hid].contiguous()
         else:
             g = d_in
+
+
+def layernorm_mse(x, ln, target_map, loss, y_out=None):
+    """LayerNorm + MSE against ``target_map`` [1, C, h, w] (row r of x <-> pixel r), forward and backward in one kernel:
+    accumulates the loss into ``loss`` (1 float) and the affine gradients into ``ln.weight.grad`` / ``ln.bias.grad``,
+    returns d loss / d x."""
+    M, N = x.shape
+    hw = target_map.shape[-2] * target_map.shape[-1]
+    if hw != M or target_map.shape[1] != N or not target_map.is_contiguous():
+        raise RuntimeError("layernorm_mse needs a contiguous [1, C, h, w] target with h*w rows")
+    g_x = torch.empty_like(x)
+    with _lib.stats.span("layernorm_mse", M=M):
+        rc = _lib.load().sanerf_layernorm_mse(x.data_ptr(), ln.weight.data_ptr(), ln.bias.data_ptr(), float(ln.eps),
+                                              target_map.data_ptr(), 1, hw, M, N, _lib.ptr(y_out), loss.data_ptr(),
+                                              g_x.data_ptr(), ln.weight.grad.data_ptr(), ln.bias.grad.data_ptr(), _stream(x))
+    _lib.check(rc, "layernorm_mse")
+    return g_x
 
 
 class _SkipMLP(Function):

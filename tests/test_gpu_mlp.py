@@ -269,3 +269,30 @@ def test_skip_mlp_tensor_core_equals_torch(cuda):
     torch.testing.assert_close(xb.grad, xa.grad, rtol=1e-4, atol=1e-5)
     for (n, p), (_, q) in zip(ref.named_parameters(), tc.named_parameters()):
         assert ((p.grad - q.grad).norm() / p.grad.norm()).item() < 1e-5, n
+
+
+def test_layernorm_mse_fused_equals_torch(cuda):
+    """LayerNorm(256) + permute + mse_loss (network.py:122, utils.py:1100-1106), forward and backward, in one kernel."""
+    from sanerf_b200 import fused
+    torch.manual_seed(1)
+    h, w = 12, 10
+    ln = torch.nn.LayerNorm(256).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(h * w, 256, device="cuda") * 3 + 1
+    target = torch.randn(1, 256, h, w, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    y_ref = ln(xr)
+    loss_ref = torch.nn.functional.mse_loss(y_ref.view(h, w, -1).permute(2, 0, 1).unsqueeze(0), target)
+    loss_ref.backward()
+    gw_ref, gb_ref = ln.weight.grad.clone(), ln.bias.grad.clone()
+    ln.weight.grad.zero_(); ln.bias.grad.zero_()
+    loss = torch.zeros(1, device="cuda")
+    y = torch.empty_like(x)
+    g_x = fused.layernorm_mse(x, ln, target, loss, y)
+    torch.testing.assert_close(y, y_ref.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(loss[0], loss_ref.detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(g_x, xr.grad, rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(ln.weight.grad, gw_ref, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(ln.bias.grad, gb_ref, rtol=1e-4, atol=1e-7)

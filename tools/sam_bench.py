@@ -20,7 +20,7 @@ for _ in range(5):
     trainer.step(o, d, target, 64, 64)
 torch.cuda.synchronize()
 ts = []
-for i in range(20):
+for i in range(int(os.environ.get('SAM_STEPS', 20))):
     flush.fill_(float(i))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); loss = trainer.step(o, d, target, 64, 64); b.record(); torch.cuda.synchronize()
