@@ -395,7 +395,9 @@ def run_sam(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "configs[2]: stage-2 SAM feature-field step, 4096 rays (64x64) per GPU x (128,64,32) samples, s_grid "
                                "L16 F8 T2^19 + samvit_mlp (163->256x5, LayerNorm), frozen stage-1 field, [1,256,64,64] target",
-                   "execution": "autograd step captured as a CUDA graph", "l2": "flushed between timed iterations",
+                   "execution": "hand-scheduled step (FusedSAMStep) replayed as one CUDA graph per step" if world == 1 else
+                                "hand-scheduled step: two CUDA graphs around the eager NCCL reduce-scatter / all-gather",
+                   "l2": "flushed between timed iterations",
                    "parallelism": f"ray-sharded data parallel x{world}"},
         "clocks": clocks,
         "e2e": {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,

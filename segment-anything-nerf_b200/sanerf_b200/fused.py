@@ -381,34 +381,45 @@ def skip_mlp_forward(x, weights, biases, skip_layers, precision=0, slope=0.01):
 
 
 def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, precision=0, slope=0.01,
-                      need_input_grad=True, k_splits=16, input_cols=None):
+                      need_input_grad=True, k_splits=16, input_cols=None, side_stream=None, join=True):
     """Backward of ``skip_mlp_forward``: ACCUMULATES weight / bias gradients into ``g_weights`` / ``g_biases`` (pre-zeroed
     or holding earlier contributions) and returns the gradient of the MLP input.  Per layer: one weight-gradient GEMM
     split over the batch rows and one data-gradient GEMM whose epilogue applies the derivative of the previous layer's
-    leaky ReLU (its saved output is the mask) and reduces that layer's bias gradient.  ``input_cols``: return only that many leading
-    columns of the input gradient."""
+    leaky ReLU (its saved output is the mask) and reduces that layer's bias gradient.  ``input_cols``: return only that
+    many leading columns of the input gradient.  ``side_stream``: the weight-gradient GEMMs (nothing downstream reads
+    them) run there, off the dependent chain of data-gradient GEMMs; joined before returning, or, with ``join=False``,
+    by the caller (``current.wait_stream(side_stream)``), who then receives ``(grad, keep)`` and must hold ``keep`` —
+    the tensors the side stream still reads — until that join is enqueued."""
     M = g_out.shape[0]
     lib = _lib.load()
+    dev = g_out.device
+    main = torch.cuda.current_stream(dev)
     g = g_out.contiguous()
-    g_skip = None
+    g_skip, gx = None, None
+    keep = []                                              # tensors the side stream reads: alive until the join
     for i in range(len(weights) - 1, -1, -1):
         W, h_in = weights[i], inputs[i]
         n_out, n_in = W.shape
-        gemm_tc(g, h_in, g_weights[i], n_out, n_in, M, a_trans=True, b_trans=True, k_splits=k_splits, epilogue=2,
-                precision=precision)
-        if g_biases[i] is not None and i == len(weights) - 1:      # the other layers: in the epilogue that produced g
-            with _lib.stats.span("colsum_add", M=M, N=n_out):
-                rc = lib.sanerf_colsum_add(g.data_ptr(), g.stride(0), M, n_out, g_biases[i].data_ptr(), _stream(g))
-            _lib.check(rc, "colsum_add")
+        keep.append(g)
+        if side_stream is not None:
+            side_stream.wait_stream(main)                  # g (and everything before it) is complete
+        with torch.cuda.stream(side_stream if side_stream is not None else main):
+            gemm_tc(g, h_in, g_weights[i], n_out, n_in, M, a_trans=True, b_trans=True, k_splits=k_splits, epilogue=2,
+                    precision=precision)
+            if g_biases[i] is not None and i == len(weights) - 1:      # the other layers: in the epilogue that produced g
+                with _lib.stats.span("colsum_add", M=M, N=n_out):
+                    rc = lib.sanerf_colsum_add(g.data_ptr(), g.stride(0), M, n_out, g_biases[i].data_ptr(), _stream(g))
+                _lib.check(rc, "colsum_add")
         if i == 0:
-            if not need_input_grad:
-                return None
-            cols = n_in if input_cols is None else min(int(input_cols), n_in)    # only the leading columns are wanted
-            gx = torch.empty(M, cols, device=g.device, dtype=torch.float32)
-            gemm_tc(g, W, gx, M, cols, n_out, b_trans=True, precision=precision)
-            return gx if g_skip is None else gx + g_skip[:, :cols]
+            if need_input_grad:
+                cols = n_in if input_cols is None else min(int(input_cols), n_in)    # only the leading columns are wanted
+                gx = torch.empty(M, cols, device=dev, dtype=torch.float32)
+                gemm_tc(g, W, gx, M, cols, n_out, b_trans=True, precision=precision)
+                if g_skip is not None:
+                    gx = gx + g_skip[:, :cols]
+            break
         hid = weights[i - 1].shape[0]
-        d_in = torch.empty(M, n_in, device=g.device, dtype=torch.float32)
+        d_in = torch.empty(M, n_in, device=dev, dtype=torch.float32)
         gemm_tc(g, W, d_in, M, n_in, n_out, b_trans=True, epilogue=1, mask=h_in, mask_cols=hid, slope=slope,
                 colsum=g_biases[i - 1], precision=precision)
         if i in skip_layers:
@@ -416,6 +427,12 @@ def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, 
             g = d_in[:, :hid].contiguous()
         else:
             g = d_in
+    if side_stream is not None and not join:
+        return gx, keep
+    if side_stream is not None:
+        main.wait_stream(side_stream)
+    del keep
+    return gx
 
 
 def layernorm_mse(x, ln, target_map, loss, y_out=None):

@@ -533,6 +533,7 @@ class FusedSAMStep:
         self.target = torch.empty(tuple(target_shape), **f32)
         self.loss = torch.zeros(1, **f32)
         self.update_stream = torch.cuda.Stream(dev)
+        self.side_stream = torch.cuda.Stream(dev)          # weight-gradient GEMMs of the samvit head
         self.critical_stream = torch.cuda.Stream(dev, priority=-1)
         self.pending_main = False
         self.sharded_update = True
@@ -586,8 +587,9 @@ class FusedSAMStep:
             self.samvit = torch.empty_like(out)
             self.loss.zero_()
             g_out = fused.layernorm_mse(out, ln, self.target, self.loss, self.samvit)
-            g_sam = fused.skip_mlp_backward(g_out, inputs, weights, mlp.skip_layers, [l.weight.grad for l in mlp.net],
-                                            [l.bias.grad for l in mlp.net], prec, input_cols=nl * C)
+            g_sam, keep = fused.skip_mlp_backward(g_out, inputs, weights, mlp.skip_layers,
+                                                  [l.weight.grad for l in mlp.net], [l.bias.grad for l in mlp.net], prec,
+                                                  input_cols=nl * C, side_stream=self.side_stream, join=False)
             self.last_f = f
         else:
             f.requires_grad_(True)
@@ -606,6 +608,9 @@ class FusedSAMStep:
             rc = lib.sanerf_ray_features_backward(L["x01"].data_ptr(), L["weights"].data_ptr(), g_sam.data_ptr(),
                                                   g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), st)
         check(rc, "ray_features_backward")
+        if direct:                                         # weight-gradient GEMMs ran beside the data-gradient chain + scatter
+            torch.cuda.current_stream(self.dev).wait_stream(self.side_stream)
+            del keep
 
     # ---- optimizer ----------------------------------------------------------------------------------------
     def _update_main(self):
