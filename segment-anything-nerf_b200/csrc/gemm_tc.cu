@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
     const uint32_t c_end = min(c_begin + p.chunks_per_split, total_chunks);
     if (c_begin >= c_end) return;                                    // empty split of a reduction epilogue (uniform)
     const uint32_t nc = c_end - c_begin;
-    const bool split = (p.precision == 0);
+    const bool split = ((p.precision & 15) == 0);
+    const int dbg = p.precision >> 4;      // diagnostics (tools/time_gemm.py): 1 = no MMA, 2 = no shared stores, 4 = no global loads
 
     if (warp == 0) umma::tmem_alloc<kTmemCols>(umma::smem_u32(&s_tmem));
     if (tid == 32) {
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
     OperandRegs<kBM> ra0, ra1;
     OperandRegs<kBN> rb0, rb1;
     auto fetch = [&](OperandRegs<kBM>& ra, OperandRegs<kBN>& rb, uint32_t c) {
+        if ((dbg & 4) && c >= 2u) return;
         ra.load(p.A, p.lda, a_tr, a_vec, m0, p.M, (c_begin + c) * kKC, p.K, tid);
         rb.load(p.B, p.ldb, b_tr, b_vec, n0, p.N, (c_begin + c) * kKC, p.K, tid);
     };
@@ -185,8 +187,10 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
         const uint32_t s = c & 1u;
         uint8_t* stage = smem + s * kStageBytes;
         if (c >= kStages) umma::mbar_wait(umma::smem_u32(&s_bar[s]), ((c >> 1) - 1u) & 1u);     // MMAs of chunk c-2 done
-        ra.store(stage, stage + kAPlane, a_tr, split, tid);
-        rb.store(stage + 2 * kAPlane, stage + 2 * kAPlane + kBPlane, b_tr, split, tid);
+        if (!(dbg & 2)) {
+            ra.store(stage, stage + kAPlane, a_tr, split, tid);
+            rb.store(stage + 2 * kAPlane, stage + 2 * kAPlane + kBPlane, b_tr, split, tid);
+        }
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
                 uint32_t acc = (c > 0u) ? 1u : 0u;
 #pragma unroll
                 for (uint32_t ks = 0; ks < kKC / 8u; ++ks) {
+                    if ((dbg & 1) && !(c == 0u && ks == 0u)) break;
                     const uint32_t ao = ks * a_step, bo = ks * b_step;
                     if (split) {
                         umma::mma_tf32_ss2(tmem, dAl + ao, dhi, dBh + bo, dhi, idesc, acc);
@@ -249,12 +254,23 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
                     v[j] = t;
                 }
             } else if (p.epilogue == 1) {
+                const float* mrow = p.mask + (size_t)m * p.ldm + nb;
+                const bool m_vec = (p.ldm % 4u == 0u) && ((reinterpret_cast<uintptr_t>(p.mask) & 15u) == 0u) &&
+                                   nb + 16u <= p.mask_cols && nb + 16u <= p.N;
+                if (m_vec) {                                    // a thread owns a row: 4 x 16-byte loads instead of 16 scalar ones
 #pragma unroll
-                for (uint32_t j = 0; j < 16; ++j) {
-                    const uint32_t n = nb + j;
-                    if (n < p.mask_cols && n < p.N) {
-                        const float h = __ldg(p.mask + (size_t)m * p.ldm + n);
-                        v[j] = (h > 0.0f) ? v[j] : v[j] * p.slope;
+                    for (uint32_t j = 0; j < 16; j += 4) {
+                        const float4 h = __ldg(reinterpret_cast<const float4*>(mrow + j));
+                        v[j] = (h.x > 0.0f) ? v[j] : v[j] * p.slope;
+                        v[j + 1] = (h.y > 0.0f) ? v[j + 1] : v[j + 1] * p.slope;
+                        v[j + 2] = (h.z > 0.0f) ? v[j + 2] : v[j + 2] * p.slope;
+                        v[j + 3] = (h.w > 0.0f) ? v[j + 3] : v[j + 3] * p.slope;
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t j = 0; j < 16; ++j) {
+                        const uint32_t n = nb + j;
+                        if (n < p.mask_cols && n < p.N) v[j] = (__ldg(mrow + j) > 0.0f) ? v[j] : v[j] * p.slope;
                     }
                 }
             }
@@ -328,7 +344,7 @@ extern "C" int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const f
     if (K == 0) return fail(SANERF_ERR_INVALID_ARG, "gemm_tc: K must be positive");
     if (epilogue < 0 || epilogue > 2) return fail(SANERF_ERR_INVALID_ARG, "gemm_tc: epilogue must be 0, 1 or 2");
     if (epilogue == 1 && mask == nullptr) return fail(SANERF_ERR_NULL_POINTER, "gemm_tc: mask is NULL");
-    if (precision != 0 && precision != 1) return fail(SANERF_ERR_INVALID_ARG, "gemm_tc: precision must be 0 or 1");
+    if ((precision & 15) != 0 && (precision & 15) != 1) return fail(SANERF_ERR_INVALID_ARG, "gemm_tc: precision must be 0 or 1");
     if (k_splits == 0) k_splits = 1;
     if (k_splits > 1 && epilogue != 2)
         return fail(SANERF_ERR_INVALID_ARG, "gemm_tc: K can only be split with the accumulating epilogue");

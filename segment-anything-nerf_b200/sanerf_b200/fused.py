@@ -384,8 +384,8 @@ def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, 
                       need_input_grad=True, k_splits=16, input_cols=None, side_stream=None, join=True):
     """Backward of ``skip_mlp_forward``: ACCUMULATES weight / bias gradients into ``g_weights`` / ``g_biases`` (pre-zeroed
     or holding earlier contributions) and returns the gradient of the MLP input.  Per layer: one weight-gradient GEMM
-    split over the batch rows and one data-gradient GEMM whose epilogue applies the derivative of the previous layer's
-    leaky ReLU (its saved output is the mask) and reduces that layer's bias gradient.  ``input_cols``: return only that
+    split over the batch rows + a column sum (bias), and one data-gradient GEMM whose epilogue applies the derivative of
+    the previous layer's leaky ReLU (its saved output is the mask).  ``input_cols``: return only that
     many leading columns of the input gradient.  ``side_stream``: the weight-gradient GEMMs (nothing downstream reads
     them) run there, off the dependent chain of data-gradient GEMMs; joined before returning, or, with ``join=False``,
     by the caller (``current.wait_stream(side_stream)``), who then receives ``(grad, keep)`` and must hold ``keep`` —
@@ -406,7 +406,7 @@ def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, 
         with torch.cuda.stream(side_stream if side_stream is not None else main):
             gemm_tc(g, h_in, g_weights[i], n_out, n_in, M, a_trans=True, b_trans=True, k_splits=k_splits, epilogue=2,
                     precision=precision)
-            if g_biases[i] is not None and i == len(weights) - 1:      # the other layers: in the epilogue that produced g
+            if g_biases[i] is not None:                    # bias gradient: column sums of g, beside the weight-gradient GEMM
                 with _lib.stats.span("colsum_add", M=M, N=n_out):
                     rc = lib.sanerf_colsum_add(g.data_ptr(), g.stride(0), M, n_out, g_biases[i].data_ptr(), _stream(g))
                 _lib.check(rc, "colsum_add")
@@ -421,7 +421,7 @@ def skip_mlp_backward(g_out, inputs, weights, skip_layers, g_weights, g_biases, 
         hid = weights[i - 1].shape[0]
         d_in = torch.empty(M, n_in, device=dev, dtype=torch.float32)
         gemm_tc(g, W, d_in, M, n_in, n_out, b_trans=True, epilogue=1, mask=h_in, mask_cols=hid, slope=slope,
-                colsum=g_biases[i - 1], precision=precision)
+                precision=precision)       # (colsum= in this epilogue costs 11 us of same-address reductions on the chain)
         if i in skip_layers:
             g_skip = d_in[:, hid:] if g_skip is None else g_skip + d_in[:, hid:]
             g = d_in[:, :hid].contiguous()
