@@ -18,6 +18,14 @@ int fail(int status, const char* fmt, ...) {
     return status;
 }
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("SANERF_PDL");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on;
+}
+
 }  // namespace sanerf
 
 extern "C" int sanerf_abi_version(void) { return SANERF_ABI_VERSION; }

@@ -30,6 +30,7 @@ template <int KC>  // KC = ceil(C/32) for the lane-per-channel path; 0 = lane-pe
 __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_forward_kernel(
     const CompositeArgs a, float* __restrict__ weights, float* __restrict__ weights_sum,
     float* __restrict__ depth, float* __restrict__ out, int32_t* __restrict__ n_alive) {
+    pdl_begin();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t r = blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
     if (r >= a.N) return;
@@ -149,6 +150,7 @@ template <int KC, int NCHUNK>
 __global__ void __launch_bounds__(32 * kRaysPerBlock) composite_backward_kernel(
     const CompositeArgs a, const CompositeGrads g, float* __restrict__ grad_sigmas,
     float* __restrict__ grad_feats) {
+    pdl_begin();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t r = blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
     if (r >= a.N) return;
@@ -329,10 +331,10 @@ static int launch_bwd_chunks(const CompositeArgs& a, const CompositeGrads& g, fl
                              cudaStream_t st) {
     const uint32_t blocks = div_up(a.N, (uint32_t)kRaysPerBlock);
     const uint32_t chunks = div_up(a.T, 32u);
-    if (chunks <= 1) composite_backward_kernel<KC, 1><<<blocks, 32 * kRaysPerBlock, 0, st>>>(a, g, gs, gf);
-    else if (chunks <= 2) composite_backward_kernel<KC, 2><<<blocks, 32 * kRaysPerBlock, 0, st>>>(a, g, gs, gf);
-    else if (chunks <= 4) composite_backward_kernel<KC, 4><<<blocks, 32 * kRaysPerBlock, 0, st>>>(a, g, gs, gf);
-    else composite_backward_kernel<KC, kMaxChunks><<<blocks, 32 * kRaysPerBlock, 0, st>>>(a, g, gs, gf);
+    if (chunks <= 1) SANERF_LAUNCH((composite_backward_kernel<KC, 1>), blocks, 32 * kRaysPerBlock, 0, st, a, g, gs, gf);
+    else if (chunks <= 2) SANERF_LAUNCH((composite_backward_kernel<KC, 2>), blocks, 32 * kRaysPerBlock, 0, st, a, g, gs, gf);
+    else if (chunks <= 4) SANERF_LAUNCH((composite_backward_kernel<KC, 4>), blocks, 32 * kRaysPerBlock, 0, st, a, g, gs, gf);
+    else SANERF_LAUNCH((composite_backward_kernel<KC, kMaxChunks>), blocks, 32 * kRaysPerBlock, 0, st, a, g, gs, gf);
     return check_launch("composite_backward_kernel");
 }
 
@@ -368,11 +370,11 @@ extern "C" int sanerf_composite_forward(const float* sigmas, const float* deltas
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t blocks = div_up(N, (uint32_t)kRaysPerBlock);
     const int threads = 32 * kRaysPerBlock;
-    if (C <= 8) composite_forward_kernel<0><<<blocks, threads, 0, st>>>(a, weights, weights_sum, depth, out, n_alive);
-    else if (C <= 32) composite_forward_kernel<1><<<blocks, threads, 0, st>>>(a, weights, weights_sum, depth, out, n_alive);
-    else if (C <= 64) composite_forward_kernel<2><<<blocks, threads, 0, st>>>(a, weights, weights_sum, depth, out, n_alive);
-    else if (C <= 128) composite_forward_kernel<4><<<blocks, threads, 0, st>>>(a, weights, weights_sum, depth, out, n_alive);
-    else composite_forward_kernel<8><<<blocks, threads, 0, st>>>(a, weights, weights_sum, depth, out, n_alive);
+    if (C <= 8) SANERF_LAUNCH((composite_forward_kernel<0>), blocks, threads, 0, st, a, weights, weights_sum, depth, out, n_alive);
+    else if (C <= 32) SANERF_LAUNCH((composite_forward_kernel<1>), blocks, threads, 0, st, a, weights, weights_sum, depth, out, n_alive);
+    else if (C <= 64) SANERF_LAUNCH((composite_forward_kernel<2>), blocks, threads, 0, st, a, weights, weights_sum, depth, out, n_alive);
+    else if (C <= 128) SANERF_LAUNCH((composite_forward_kernel<4>), blocks, threads, 0, st, a, weights, weights_sum, depth, out, n_alive);
+    else SANERF_LAUNCH((composite_forward_kernel<8>), blocks, threads, 0, st, a, weights, weights_sum, depth, out, n_alive);
     return check_launch("composite_forward_kernel");
 }
 

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kFlWarps * 32) layernorm_mse_kernel(
     const float* __restrict__ target, size_t t_row_stride, size_t t_col_stride, uint32_t M, uint32_t rows_per_block,
     float* __restrict__ y_out, float* __restrict__ loss, float* __restrict__ g_x, float* __restrict__ g_gamma,
     float* __restrict__ g_beta) {
+    pdl_begin();
     __shared__ float s_g[kFlWarps][kFlN], s_b[kFlWarps][kFlN];
     __shared__ float s_loss[kFlWarps];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -121,7 +122,7 @@ extern "C" int sanerf_layernorm_mse(const float* x, const float* gamma, const fl
     SANERF_REQUIRE_PTR(g_beta);
     if (N != kFlN) return fail(SANERF_ERR_INVALID_ARG, "layernorm_mse: the feature width must be 256 (network.py:122)");
     const uint32_t rows_per_block = 32;                         // 4 rows per warp: 128 blocks at 4096 rays
-    layernorm_mse_kernel<<<div_up(M, rows_per_block), kFlWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    SANERF_LAUNCH(layernorm_mse_kernel, div_up(M, rows_per_block), kFlWarps * 32, 0, static_cast<cudaStream_t>(stream), 
         x, gamma, beta, eps, target, (size_t)t_row_stride, (size_t)t_col_stride, M, rows_per_block, y_out, loss, g_x, g_gamma,
         g_beta);
     return check_launch("layernorm_mse_kernel");

@@ -140,6 +140,7 @@ struct OperandRegs {
 };
 
 __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParams p) {
+    pdl_begin();
     using namespace gemm;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kStages];
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
 // out[n] += sum_m act'(mask) is NOT applied here: X is already the pre-activation gradient.  out[n] += sum_m X[m, n].
 __global__ void __launch_bounds__(256) colsum_add_kernel(const float* __restrict__ X, uint32_t ld, uint32_t M, uint32_t N,
                                                          uint32_t rows_per_block, float* __restrict__ out) {
+    pdl_begin();
     __shared__ float part[8][33];
     const uint32_t cx = threadIdx.x & 31u, ry = threadIdx.x >> 5;
     const uint32_t n = blockIdx.x * 32u + cx;
@@ -364,7 +366,7 @@ extern "C" int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const f
         configured = true;
     }
     dim3 grid(div_up(M, gemm::kBM), div_up(N, gemm::kBN), k_splits);
-    gemm_tc_kernel<<<grid, gemm::kThreads, gemm::kSmem, static_cast<cudaStream_t>(stream)>>>(p);
+    SANERF_LAUNCH(gemm_tc_kernel, grid, gemm::kThreads, gemm::kSmem, static_cast<cudaStream_t>(stream), p);
     return check_launch("gemm_tc_kernel");
 }
 
@@ -374,6 +376,6 @@ extern "C" int sanerf_colsum_add(const float* X, uint32_t ld, uint32_t M, uint32
     SANERF_REQUIRE_PTR(out);
     const uint32_t rows_per_block = 256;
     dim3 grid(div_up(N, 32u), div_up(M, rows_per_block), 1);
-    colsum_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ld, M, N, rows_per_block, out);
+    SANERF_LAUNCH(colsum_add_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), X, ld, M, N, rows_per_block, out);
     return check_launch("colsum_add_kernel");
 }

@@ -31,6 +31,7 @@ struct GridBwdParams {
 
 template <typename T, uint32_t D, uint32_t C, uint32_t G, uint32_t CH>
 __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams p) {
+    pdl_begin();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t level0 = blockIdx.y * G;
     // fp32 tables with few values per cell: merge consecutive samples of a ray that share a cell before the
@@ -246,7 +247,7 @@ static int launch_backward(const GridBwdParams& p, cudaStream_t stream) {
     constexpr uint32_t kThreads = 256;
     if (p.max_level == 0 || p.B == 0) return SANERF_OK;
     dim3 grid(div_up(p.B, kThreads), div_up(p.max_level, G), 1);
-    grid_backward_kernel<T, D, C, G, CH><<<grid, kThreads, 0, stream>>>(p);
+    SANERF_LAUNCH((grid_backward_kernel<T, D, C, G, CH>), grid, kThreads, 0, stream, p);
     return check_launch("grid_backward_kernel");
 }
 

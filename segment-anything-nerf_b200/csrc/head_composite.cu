@@ -97,6 +97,7 @@ __device__ __forceinline__ float transpose_sum16(float (&v)[16], uint32_t lane) 
 __global__ void __launch_bounds__(32 * hc::kRaysPerBlock) head_composite_forward_kernel(
     const hc::Args a, float* __restrict__ sigma, float* __restrict__ weights, float* __restrict__ weights_sum,
     float* __restrict__ depth, float* __restrict__ out, int32_t* __restrict__ n_alive) {
+    pdl_begin();
     using namespace hc;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t r = blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(32 * hc::kRaysPerBlock) head_composite_backwar
     const hc::Args a, const float* __restrict__ g_weights, const float* __restrict__ g_weights_sum,
     const float* __restrict__ g_depth, const float* __restrict__ g_out, const float* __restrict__ g_sigma_direct,
     float* __restrict__ g_head) {
+    pdl_begin();
     using namespace hc;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t r = blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
@@ -230,8 +232,7 @@ extern "C" int sanerf_head_composite_forward(const float* head, const float* del
     SANERF_REQUIRE_PTR(weights); SANERF_REQUIRE_PTR(weights_sum); SANERF_REQUIRE_PTR(depth); SANERF_REQUIRE_PTR(out);
     if ((uintptr_t)head & 15u) return fail(SANERF_ERR_MISALIGNED, "head_composite: head must be 16-byte aligned");
     hc::Args a{head, deltas, ts, N, T, last_sample_opaque, t_thresh};
-    head_composite_forward_kernel<<<div_up(N, (uint32_t)hc::kRaysPerBlock), 32 * hc::kRaysPerBlock, 0,
-                                    static_cast<cudaStream_t>(stream)>>>(a, sigma, weights, weights_sum, depth, out, n_alive);
+    SANERF_LAUNCH(head_composite_forward_kernel, div_up(N, (uint32_t)hc::kRaysPerBlock), 32 * hc::kRaysPerBlock, 0, static_cast<cudaStream_t>(stream), a, sigma, weights, weights_sum, depth, out, n_alive);
     return check_launch("head_composite_forward_kernel");
 }
 
@@ -243,8 +244,7 @@ extern "C" int sanerf_head_composite_backward(const float* head, const float* de
     SANERF_REQUIRE_PTR(head); SANERF_REQUIRE_PTR(deltas); SANERF_REQUIRE_PTR(ts); SANERF_REQUIRE_PTR(g_head);
     if (((uintptr_t)head | (uintptr_t)g_head) & 15u) return fail(SANERF_ERR_MISALIGNED, "head_composite: 16-byte alignment");
     hc::Args a{head, deltas, ts, N, T, last_sample_opaque, t_thresh};
-    head_composite_backward_kernel<<<div_up(N, (uint32_t)hc::kRaysPerBlock), 32 * hc::kRaysPerBlock, 0,
-                                     static_cast<cudaStream_t>(stream)>>>(a, g_weights, g_weights_sum, g_depth, g_out,
+    SANERF_LAUNCH(head_composite_backward_kernel, div_up(N, (uint32_t)hc::kRaysPerBlock), 32 * hc::kRaysPerBlock, 0, static_cast<cudaStream_t>(stream), a, g_weights, g_weights_sum, g_depth, g_out,
                                                                           g_sigma_direct, g_head);
     return check_launch("head_composite_backward_kernel");
 }

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(32 * kLossWarps) proposal_loss_kernel(
     const float* __restrict__ t_ref, const float* __restrict__ w_ref, uint32_t Tr, const float* __restrict__ t_p,
     const float* __restrict__ w_p, uint32_t Tp, uint32_t N, float weight, float* __restrict__ loss_out,
     float* __restrict__ g_wp) {
+    pdl_begin();
     extern __shared__ float smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kLossWarps + warp;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(32 * kLossWarps) proposal_loss_kernel(
 __global__ void __launch_bounds__(32 * kLossWarps) distortion_loss_kernel(
     const float* __restrict__ bins, const float* __restrict__ w, uint32_t T, uint32_t N, float weight,
     float* __restrict__ loss_out, float* __restrict__ g_w) {
+    pdl_begin();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kLossWarps + warp;
     if (r >= N) return;
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(32 * kLossWarps) distortion_loss_kernel(
 // p -= lr / (1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  `dyn` = {lr_t, 1-b1^t, 1-b2^t} lives on the device so
 // that a captured CUDA graph can be replayed with a moving step count / learning-rate schedule.
 __global__ void adam_schedule_kernel(int32_t* step, float* dyn, float lr0, float beta1, float beta2, float decay_iters) {
+    pdl_begin();
     const int32_t t = *step + 1;
     *step = t;
     // LambdaLR(0.1 ** min(iter / iters, 1)) evaluated at iter = t-1 (main.py:312-313; scheduler steps after the optimizer)
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
                                                         float* __restrict__ v, size_t n4, size_t n,
                                                         const float* __restrict__ dyn, float beta1, float beta2,
                                                         float eps, float grad_scale, int zero_grad) {
+    pdl_begin();
     const float lr = __ldg(dyn), bc1 = __ldg(dyn + 1), bc2 = __ldg(dyn + 2);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -217,7 +221,7 @@ extern "C" int sanerf_proposal_loss(const float* t_ref, const float* w_ref, uint
     const size_t smem = (size_t)kLossWarps * 3u * (Tp + 1u) * sizeof(float);
     if (smem > 48 * 1024) return fail(SANERF_ERR_INVALID_ARG, "proposal_loss: Tp too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    proposal_loss_kernel<<<div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, smem, st>>>(t_ref, w_ref, Tr, t_p, w_p, Tp,
+    SANERF_LAUNCH(proposal_loss_kernel, div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, smem, st, t_ref, w_ref, Tr, t_p, w_p, Tp,
                                                                                          N, weight, loss_out, g_wp);
     return check_launch("proposal_loss_kernel");
 }
@@ -227,14 +231,14 @@ extern "C" int sanerf_distortion_loss(const float* bins, const float* w, uint32_
     if (N == 0 || T == 0) return SANERF_OK;
     SANERF_REQUIRE_PTR(bins); SANERF_REQUIRE_PTR(w); SANERF_REQUIRE_PTR(loss_out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    distortion_loss_kernel<<<div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, 0, st>>>(bins, w, T, N, weight, loss_out, g_w);
+    SANERF_LAUNCH(distortion_loss_kernel, div_up(N, (uint32_t)kLossWarps), 32 * kLossWarps, 0, st, bins, w, T, N, weight, loss_out, g_w);
     return check_launch("distortion_loss_kernel");
 }
 
 extern "C" int sanerf_adam_schedule(int32_t* step, float* dyn, float lr0, float beta1, float beta2, float decay_iters,
                                     void* stream) {
     SANERF_REQUIRE_PTR(step); SANERF_REQUIRE_PTR(dyn);
-    adam_schedule_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step, dyn, lr0, beta1, beta2, decay_iters);
+    SANERF_LAUNCH(adam_schedule_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), step, dyn, lr0, beta1, beta2, decay_iters);
     return check_launch("adam_schedule_kernel");
 }
 
@@ -253,7 +257,7 @@ extern "C" int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
     // critical chain, whose CTAs can only be placed when CTAs of this kernel retire.  (Measured alternative: two
     // persistent CTAs per SM - no better; the interference is in the memory system, see the streaming accesses above.)
     blocks = div_up(blocks, (size_t)4);
-    adam_step_kernel<<<(uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    SANERF_LAUNCH(adam_step_kernel, (uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream), 
         params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad);
     return check_launch("adam_step_kernel");
 }

@@ -185,6 +185,7 @@ __device__ __forceinline__ void relu_to_tmem(uint32_t lane_base, uint32_t c_acc,
 }
 
 __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const HeadFwdParams p, const uint32_t tiles) {
+    pdl_begin();
     using namespace head;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_mma;
@@ -538,6 +539,7 @@ __device__ __noinline__ void scatter_level(const float* __restrict__ x01, float*
 // epilogues, the 16 accumulator columns 16 (w >> 2) ..; in the staging phases it moves the 8 tile rows 8 w .. 8 w + 7.
 // Every phase therefore runs with four warps per scheduler instead of one.
 __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(const HeadBwdParams p, const uint32_t tiles) {
+    pdl_begin();
     using namespace head;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mma;
@@ -819,7 +821,7 @@ extern "C" int sanerf_field_head_forward(const float* x01, const float* table, c
     const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     cudaError_t e = cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kFwdSmem);
     if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "field_head_forward: %s", cudaGetErrorString(e));
-    head_forward_kernel<<<blocks, head::kThreads, head::kFwdSmem, static_cast<cudaStream_t>(stream)>>>(p, tiles);
+    SANERF_LAUNCH(head_forward_kernel, blocks, head::kThreads, head::kFwdSmem, static_cast<cudaStream_t>(stream), p, tiles);
     return check_launch("head_forward_kernel");
 }
 
@@ -848,6 +850,6 @@ extern "C" int sanerf_field_head_backward(const float* enc, const float* h1, con
     const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     cudaError_t e = cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kBwdSmem);
     if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "field_head_backward: %s", cudaGetErrorString(e));
-    head_backward_kernel<<<blocks, head::kBwdThreads, head::kBwdSmem, static_cast<cudaStream_t>(stream)>>>(p, tiles);
+    SANERF_LAUNCH(head_backward_kernel, blocks, head::kBwdThreads, head::kBwdSmem, static_cast<cudaStream_t>(stream), p, tiles);
     return check_launch("head_backward_kernel");
 }

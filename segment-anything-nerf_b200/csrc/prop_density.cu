@@ -70,6 +70,7 @@ __device__ __forceinline__ void prop_encode(const PropParams& p, const float (&x
 template <uint32_t L>
 __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropParams p, float* __restrict__ sigma,
                                                                     float* __restrict__ enc_out) {
+    pdl_begin();
     constexpr uint32_t IN = 2 * L;
     __shared__ float s_w1[kPropHidden * IN];
     __shared__ float s_w2[kPropHidden];
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kPropThreads, 2) prop_backward_kernel(const Pr
                                                                         float* __restrict__ grad_table,
                                                                         float* __restrict__ grad_w1,
                                                                         float* __restrict__ grad_w2, uint32_t tiles) {
+    pdl_begin();
     constexpr uint32_t IN = 2 * L;
     constexpr uint32_t kWarps = kPropThreads / 32;
     __shared__ float s_w1[kPropHidden * IN];
@@ -318,7 +320,7 @@ extern "C" int sanerf_prop_density_forward(const float* x01, const float* table,
     SANERF_REQUIRE_PTR(sigma);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t blocks = div_up(B, kPropThreads);
-    SANERF_PROP_DISPATCH(L, (prop_forward_kernel<LL><<<blocks, kPropThreads, 0, st>>>(p, sigma, enc_out)));
+    SANERF_PROP_DISPATCH(L, (SANERF_LAUNCH((prop_forward_kernel<LL>), blocks, kPropThreads, 0, st, p, sigma, enc_out)));
     return check_launch("prop_forward_kernel");
 }
 
@@ -336,10 +338,10 @@ extern "C" int sanerf_prop_density_backward(const float* x01, const float* table
     const uint32_t cap = (uint32_t)kNumSMs * 2u;                              // persistent: resident CTAs only
     const uint32_t blocks = tiles < cap ? tiles : cap;
     if (enc != nullptr) {
-        SANERF_PROP_DISPATCH(L, (prop_backward_kernel<LL, true><<<blocks, kPropThreads, 0, st>>>(p, enc, g_sigma, grad_table,
+        SANERF_PROP_DISPATCH(L, (SANERF_LAUNCH((prop_backward_kernel<LL, true>), blocks, kPropThreads, 0, st, p, enc, g_sigma, grad_table,
                                                                                                 grad_w1, grad_w2, tiles)));
     } else {
-        SANERF_PROP_DISPATCH(L, (prop_backward_kernel<LL, false><<<blocks, kPropThreads, 0, st>>>(p, enc, g_sigma, grad_table,
+        SANERF_PROP_DISPATCH(L, (SANERF_LAUNCH((prop_backward_kernel<LL, false>), blocks, kPropThreads, 0, st, p, enc, g_sigma, grad_table,
                                                                                                  grad_w1, grad_w2, tiles)));
     }
     return check_launch("prop_backward_kernel");

@@ -39,6 +39,7 @@ constexpr uint32_t kRayWarps = 8;
 
 template <uint32_t C>
 __global__ void __launch_bounds__(kRayWarps * 32) ray_features_forward_kernel(const RayFeatParams p) {
+    pdl_begin();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t ray = blockIdx.x * kRayWarps + warp, level = blockIdx.y;
     if (ray >= p.N) return;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) ray_features_forward_kernel(co
 
 template <uint32_t C>
 __global__ void __launch_bounds__(kRayWarps * 32) ray_features_backward_kernel(const RayFeatParams p) {
+    pdl_begin();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t ray = blockIdx.x * kRayWarps + warp, level = blockIdx.y;
     if (ray >= p.N) return;
@@ -129,16 +131,16 @@ static int launch_ray_features(const RayFeatParams& p, uint32_t C, cudaStream_t 
     const uint32_t threads = kRayWarps * 32;
     switch (C) {
         case 2:
-            if (kBackward) ray_features_backward_kernel<2><<<grid, threads, 0, st>>>(p);
-            else ray_features_forward_kernel<2><<<grid, threads, 0, st>>>(p);
+            if (kBackward) SANERF_LAUNCH((ray_features_backward_kernel<2>), grid, threads, 0, st, p);
+            else SANERF_LAUNCH((ray_features_forward_kernel<2>), grid, threads, 0, st, p);
             break;
         case 4:
-            if (kBackward) ray_features_backward_kernel<4><<<grid, threads, 0, st>>>(p);
-            else ray_features_forward_kernel<4><<<grid, threads, 0, st>>>(p);
+            if (kBackward) SANERF_LAUNCH((ray_features_backward_kernel<4>), grid, threads, 0, st, p);
+            else SANERF_LAUNCH((ray_features_forward_kernel<4>), grid, threads, 0, st, p);
             break;
         case 8:
-            if (kBackward) ray_features_backward_kernel<8><<<grid, threads, 0, st>>>(p);
-            else ray_features_forward_kernel<8><<<grid, threads, 0, st>>>(p);
+            if (kBackward) SANERF_LAUNCH((ray_features_backward_kernel<8>), grid, threads, 0, st, p);
+            else SANERF_LAUNCH((ray_features_forward_kernel<8>), grid, threads, 0, st, p);
             break;
         default: return fail(SANERF_ERR_INVALID_ARG, "ray features: C must be 2, 4 or 8");
     }

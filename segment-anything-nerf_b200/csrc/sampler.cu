@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) sample_uniform_kernel(
     float min_near, const float* __restrict__ cam_near_far, uint32_t cnf_stride, const float* __restrict__ noise,
     uint32_t N, uint32_t T, int contract, float bound, float* __restrict__ bins, float* __restrict__ t_mid,
     float* __restrict__ deltas, float* __restrict__ x01) {
+    pdl_begin();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * T) return;
     const uint32_t r = (uint32_t)(i / T), j = (uint32_t)(i - (size_t)r * T);
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(32 * kSamplerWarps) sample_pdf_kernel(
     float* __restrict__ bins, float* __restrict__ t_mid, float* __restrict__ deltas, float* __restrict__ x01,
     const float* __restrict__ prev_sigmas, const float* __restrict__ prev_deltas, int last_opaque,
     float* __restrict__ prev_weights_out) {
+    pdl_begin();
     extern __shared__ float smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kSamplerWarps + warp;
@@ -213,7 +215,7 @@ extern "C" int sanerf_sample_uniform(const float* rays_o, const float* rays_d, c
     if (!(bound > 0.0f)) return fail(SANERF_ERR_INVALID_ARG, "sample_uniform: bound must be > 0");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t blocks = (uint32_t)div_up((size_t)N * T, (size_t)256);
-    sample_uniform_kernel<<<blocks, 256, 0, st>>>(rays_o, rays_d, aabb, min_near, cam_near_far, cnf_stride, noise, N, T,
+    SANERF_LAUNCH(sample_uniform_kernel, blocks, 256, 0, st, rays_o, rays_d, aabb, min_near, cam_near_far, cnf_stride, noise, N, T,
                                                   contract, bound, bins, t_mid, deltas, x01);
     return check_launch("sample_uniform_kernel");
 }
@@ -240,7 +242,7 @@ extern "C" int sanerf_sample_pdf(const float* rays_o, const float* rays_d, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sample_pdf_kernel<<<div_up(N, (uint32_t)kSamplerWarps), 32 * kSamplerWarps, smem, st>>>(
+    SANERF_LAUNCH(sample_pdf_kernel, div_up(N, (uint32_t)kSamplerWarps), 32 * kSamplerWarps, smem, st, 
         rays_o, rays_d, aabb, min_near, cam_near_far, cnf_stride, prev_bins, prev_weights, T0, noise, N, T, contract,
         bound, bins, t_mid, deltas, x01, prev_sigmas, prev_deltas, last_sample_opaque, prev_weights_out);
     return check_launch("sample_pdf_kernel");

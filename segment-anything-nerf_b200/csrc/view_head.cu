@@ -45,6 +45,7 @@ struct ViewHeadParams {
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(vh::kRays) view_head_kernel(const ViewHeadParams p) {
+    pdl_begin();
     using namespace vh;
     extern __shared__ float smem[];
     float* sW1 = smem;
@@ -199,6 +200,7 @@ constexpr size_t kSmem = (size_t)kFloats * sizeof(float);
 }  // namespace vt
 
 __global__ void __launch_bounds__(vt::kThreads) view_head_train_kernel(const ViewHeadParams p) {
+    pdl_begin();
     using namespace vt;
     extern __shared__ float smem[];
     float *sW1 = smem + oW1, *sW2 = smem + oW2, *sW3 = smem + oW3, *sF = smem + oF, *sH1 = smem + oH1, *sH2 = smem + oH2;
@@ -368,9 +370,9 @@ extern "C" int sanerf_view_head(const float* geo_sum, const float* weights_sum, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t blocks = div_up(N, (uint32_t)vh::kRays);
     if (train) {
-        view_head_train_kernel<<<div_up(N, (uint32_t)vt::kR), vt::kThreads, vt::kSmem, st>>>(p);
+        SANERF_LAUNCH(view_head_train_kernel, div_up(N, (uint32_t)vt::kR), vt::kThreads, vt::kSmem, st, p);
         return check_launch("view_head_train_kernel");
     }
-    else view_head_kernel<false><<<blocks, vh::kRays, vh::kSmemFwd, st>>>(p);
+    else SANERF_LAUNCH((view_head_kernel<false>), blocks, vh::kRays, vh::kSmemFwd, st, p);
     return check_launch("view_head_kernel");
 }
