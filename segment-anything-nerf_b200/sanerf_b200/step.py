@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, fused
+from .parallel import shard_bounds
 from .fused import PRECISION_IDS, field_head_supported, prop_density_supported
 
 
@@ -305,6 +306,11 @@ class FusedRGBStep:
             opt.apply(a, b, grad_scale=1.0, zero_grad=True)
             return
         world, rank = self.world_size, dist.get_rank()
+        if os.environ.get("SANERF_DBG_SKIP_MAIN_NCCL"):    # timing diagnostics only (tools/ab_nccl_g8.sh): wrong gradients
+            lo, hi = shard_bounds(a, b, world, rank)
+            opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True)
+            opt.flat_grad[a:b].zero_()
+            return
         if not self.sharded_update:                        # plain all-reduce + full-size Adam (checker for the sharded form)
             dist.all_reduce(opt.flat_grad[a:b], op=dist.ReduceOp.SUM)
             opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True)
@@ -325,7 +331,7 @@ class FusedRGBStep:
             for w in self._works:
                 w.wait()
             self._works = []
-        elif self.world_size > 1:
+        elif self.world_size > 1 and not os.environ.get("SANERF_DBG_SKIP_TAIL_NCCL"):
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
 
@@ -357,7 +363,10 @@ class FusedRGBStep:
         self._launch_front(update_proposal)
         main.wait_stream(upd)
         # (starting the small ranges' all-reduces inside the backward was measured slower: NCCL's CTAs spin on SMs the
-        # persistent one-CTA-per-SM field-head kernels count on, so they stay at the end of the step)
+        # persistent one-CTA-per-SM field-head kernels count on, so they stay at the end of the step; a variant that
+        # captures ONE all-reduce of the small ranges on the side branch beside the hash-grid scatter was also no faster
+        # at 2 GPUs: 0.949-0.959 vs 0.942-0.944 ms.  At 8 GPUs this tail reduction costs 75 us and the deferred
+        # main-table exchange another 74 us: tools/ab_nccl_g8.sh, 1.054 / 0.980 / 0.979 / 0.914 ms.)
         self._launch_back(update_proposal, reduce_small=False)
         self._update_rest()
 
