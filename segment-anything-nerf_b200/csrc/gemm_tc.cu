@@ -17,17 +17,20 @@
 // hi*hi + hi*lo + lo*hi (hi = tf32 truncation, lo = exact remainder): ~2^-21 relative per product, the same scheme as
 // the field head (mlp_tc.cu); precision 1 = one pass on round-to-nearest tf32 operands.
 //
-// One CTA = one 128 x 64 tile of C.  K is consumed in chunks of 32: all 256 threads fetch the chunk from global memory
-// into registers two chunks ahead (float4 loads; transposed operands through a 4x4 register transpose), split it into hi /
-// lo planes of the no-swizzle K-major UMMA layout in shared memory (two stages), and one elected thread issues the 12
-// MMAs of the chunk; tcgen05.commit on the stage's mbarrier releases it for the chunk after next.
+// One CTA = one 128 x 64 tile of C.  K is consumed in chunks of 32 through a three-stage shared-memory ring: eight loader
+// warps fetch a chunk from global memory into registers two chunks ahead (float4 loads; transposed operands through a 4x4
+// register transpose), split it into hi / lo planes of the no-swizzle K-major UMMA layout and arrive on the stage's `full`
+// mbarrier; a ninth warp waits for it, issues the 12 MMAs of the chunk from one elected lane and tcgen05.commit-s to the
+// stage's `empty` mbarrier.  No CTA-wide barrier inside the K loop: loads, splits / stores and tensor-core work of different
+// chunks overlap (with a __syncthreads per chunk they added up: 1.2 us per chunk, tools/time_gemm.py).
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace sanerf {
 
 namespace gemm {
-constexpr uint32_t kBM = 128, kBN = 64, kKC = 32, kThreads = 256, kStages = 2;
+constexpr uint32_t kBM = 128, kBN = 64, kKC = 32, kThreads = 256 /* loader threads */, kStages = 3;
+constexpr uint32_t kCtaThreads = kThreads + 32;                    // + one warp that only issues the MMAs
 // Byte stride between consecutive 4-element K chunks of a tile with `rows` rows (the descriptors' leading byte offset):
 // one 16-byte slot of padding per chunk column rotates the bank a (row, chunk) slot lands in, so a warp that writes
 // 4 rows x 8 chunks (coalesced global loads: 8 lanes per 128-byte row segment) stores without bank conflicts.
@@ -59,6 +62,10 @@ __device__ __forceinline__ float gemm_round_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void gemm_mbar_arrive(uint32_t saddr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(saddr) : "memory");
 }
 
 // 4 consecutive K elements of row r -> hi / lo planes of a chunk-major K-major tile with `rows` rows
@@ -139,11 +146,11 @@ struct OperandRegs {
     }
 };
 
-__global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(gemm::kCtaThreads) gemm_tc_kernel(const GemmParams p) {
     pdl_begin();
     using namespace gemm;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar[kStages];
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_done;
     __shared__ uint32_t s_tmem;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127u) & ~uintptr_t(127));
 
@@ -159,7 +166,11 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
 
     if (warp == 0) umma::tmem_alloc<kTmemCols>(umma::smem_u32(&s_tmem));
     if (tid == 32) {
-        for (uint32_t s = 0; s < kStages; ++s) umma::mbar_init(umma::smem_u32(&s_bar[s]), 1);
+        for (uint32_t s = 0; s < kStages; ++s) {
+            umma::mbar_init(umma::smem_u32(&s_full[s]), kThreads / 32);     // one arrival per loader warp
+            umma::mbar_init(umma::smem_u32(&s_empty[s]), 1);                // tcgen05.commit of the chunk that used the stage
+        }
+        umma::mbar_init(umma::smem_u32(&s_done), 1);
         umma::fence_mbar_init();
     }
     umma::fence_before_sync();
@@ -175,30 +186,14 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
     constexpr uint32_t dhi = umma::desc_hi(128u, umma::kLayoutNone);
     constexpr uint32_t a_step = (2u * chunk_stride(kBM)) >> 4, b_step = (2u * chunk_stride(kBN)) >> 4;   // 8 K elements = 2 chunks
 
-    // Two register sets: the global loads of chunks c+1 and c+2 are in flight while chunk c is split and stored, so the
-    // per-chunk critical path is the shared-memory stores + one CTA barrier, not an L2 round trip.
-    OperandRegs<kBM> ra0, ra1;
-    OperandRegs<kBN> rb0, rb1;
-    auto fetch = [&](OperandRegs<kBM>& ra, OperandRegs<kBN>& rb, uint32_t c) {
-        if ((dbg & 4) && c >= 2u) return;
-        ra.load(p.A, p.lda, a_tr, a_vec, m0, p.M, (c_begin + c) * kKC, p.K, tid);
-        rb.load(p.B, p.ldb, b_tr, b_vec, n0, p.N, (c_begin + c) * kKC, p.K, tid);
-    };
-    auto consume = [&](const OperandRegs<kBM>& ra, const OperandRegs<kBN>& rb, uint32_t c) {
-        const uint32_t s = c & 1u;
-        uint8_t* stage = smem + s * kStageBytes;
-        if (c >= kStages) umma::mbar_wait(umma::smem_u32(&s_bar[s]), ((c >> 1) - 1u) & 1u);     // MMAs of chunk c-2 done
-        if (!(dbg & 2)) {
-            ra.store(stage, stage + kAPlane, a_tr, split, tid);
-            rb.store(stage + 2 * kAPlane, stage + 2 * kAPlane + kBPlane, b_tr, split, tid);
-        }
-        umma::fence_proxy_async();
-        umma::fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {
+    if (warp == kThreads / 32) {
+        // ===================== issuing warp: waits for a full stage, issues the chunk's MMAs, releases the stage ===========
+        for (uint32_t c = 0; c < nc; ++c) {
+            const uint32_t s = c % kStages;
+            umma::mbar_wait(umma::smem_u32(&s_full[s]), (c / kStages) & 1u);
             if (umma::elect_one()) {
                 umma::fence_after_sync();
-                const uint32_t sa = umma::smem_u32(stage);
+                const uint32_t sa = umma::smem_u32(smem + s * kStageBytes);
                 const uint32_t dAh = umma::desc_lo(sa, chunk_stride(kBM)), dAl = umma::desc_lo(sa + kAPlane, chunk_stride(kBM));
                 const uint32_t dBh = umma::desc_lo(sa + 2 * kAPlane, chunk_stride(kBN)), dBl = umma::desc_lo(sa + 2 * kAPlane + kBPlane, chunk_stride(kBN));
                 uint32_t acc = (c > 0u) ? 1u : 0u;
@@ -214,28 +209,50 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
                     umma::mma_tf32_ss2(tmem, dAh + ao, dhi, dBh + bo, dhi, idesc, acc);
                     acc = 1u;
                 }
-                umma::commit(umma::smem_u32(&s_bar[s]));
+                umma::commit(umma::smem_u32(&s_empty[s]));
+                if (c + 1u == nc) umma::commit(umma::smem_u32(&s_done));
             }
             __syncwarp();
         }
-    };
-    fetch(ra0, rb0, 0u);
-    if (nc > 1u) fetch(ra1, rb1, 1u);
-    for (uint32_t c = 0; c < nc; c += 2u) {
-        consume(ra0, rb0, c);
-        if (c + 2u < nc) fetch(ra0, rb0, c + 2u);
-        if (c + 1u < nc) {
-            consume(ra1, rb1, c + 1u);
-            if (c + 3u < nc) fetch(ra1, rb1, c + 3u);
+    } else {
+        // ===================== loader warps: global -> registers (two chunks ahead) -> hi / lo planes of a free stage =====
+        // No CTA-wide barrier per chunk: a warp that has stored its share arrives on the stage's `full` barrier and moves on;
+        // it blocks only when the ring is full (`empty` = the MMAs that read the stage have completed).
+        OperandRegs<kBM> ra0, ra1;
+        OperandRegs<kBN> rb0, rb1;
+        auto fetch = [&](OperandRegs<kBM>& ra, OperandRegs<kBN>& rb, uint32_t c) {
+            if ((dbg & 4) && c >= 2u) return;
+            ra.load(p.A, p.lda, a_tr, a_vec, m0, p.M, (c_begin + c) * kKC, p.K, tid);
+            rb.load(p.B, p.ldb, b_tr, b_vec, n0, p.N, (c_begin + c) * kKC, p.K, tid);
+        };
+        auto consume = [&](const OperandRegs<kBM>& ra, const OperandRegs<kBN>& rb, uint32_t c) {
+            const uint32_t s = c % kStages;
+            uint8_t* stage = smem + s * kStageBytes;
+            if (c >= kStages) umma::mbar_wait(umma::smem_u32(&s_empty[s]), ((c / kStages) - 1u) & 1u);
+            if (!(dbg & 2)) {
+                ra.store(stage, stage + kAPlane, a_tr, split, tid);
+                rb.store(stage + 2 * kAPlane, stage + 2 * kAPlane + kBPlane, b_tr, split, tid);
+            }
+            umma::fence_proxy_async();                   // this thread's generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) gemm_mbar_arrive(umma::smem_u32(&s_full[s]));
+        };
+        fetch(ra0, rb0, 0u);
+        if (nc > 1u) fetch(ra1, rb1, 1u);
+        for (uint32_t c = 0; c < nc; c += 2u) {
+            consume(ra0, rb0, c);
+            if (c + 2u < nc) fetch(ra0, rb0, c + 2u);
+            if (c + 1u < nc) {
+                consume(ra1, rb1, c + 1u);
+                if (c + 3u < nc) fetch(ra1, rb1, c + 3u);
+            }
         }
     }
-    {   // every MMA of this CTA has completed once the last commit has arrived
-        const uint32_t last = nc - 1u;
-        umma::mbar_wait(umma::smem_u32(&s_bar[last & 1u]), (last >> 1) & 1u);
-        umma::fence_after_sync();
-    }
+    umma::mbar_wait(umma::smem_u32(&s_done), 0u);        // every MMA of this CTA has completed
+    umma::fence_after_sync();
 
-    // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (rows), columns 32 (w >> 2) .. +31
+    // ---- epilogue: warp w < 8 reads TMEM lanes 32 (w & 3) .. +31 (rows), columns 32 (w >> 2) .. +31
+    if (warp < kThreads / 32) {
     const uint32_t q = warp & 3u, half = warp >> 2;
     const uint32_t m = m0 + q * 32u + lane;
     const uint32_t taddr = umma::tmem_addr(tmem, q * 32u, half * 32u);
@@ -305,6 +322,7 @@ __global__ void __launch_bounds__(gemm::kThreads) gemm_tc_kernel(const GemmParam
             }
         }
     }
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc<kTmemCols>(tmem);
@@ -366,7 +384,7 @@ extern "C" int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const f
         configured = true;
     }
     dim3 grid(div_up(M, gemm::kBM), div_up(N, gemm::kBN), k_splits);
-    SANERF_LAUNCH(gemm_tc_kernel, grid, gemm::kThreads, gemm::kSmem, static_cast<cudaStream_t>(stream), p);
+    SANERF_LAUNCH(gemm_tc_kernel, grid, gemm::kCtaThreads, gemm::kSmem, static_cast<cudaStream_t>(stream), p);
     return check_launch("gemm_tc_kernel");
 }
 
