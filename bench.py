@@ -185,7 +185,7 @@ def cpu_baseline_sample(budget_s=20.0):
 # dram__bytes_read.sum + dram__bytes_write.sum of one head_forward_kernel launch inside the training step
 # (ncu --set full, profiles/r1_head_forward_ncu.md); the 50 MB table is L2-resident, so this is far below the
 # algorithmic bytes
-HEAD_FWD_TRAFFIC = 259.9e6      # profiles/r1h_ncu_kernels.md: 107.4 MB read + 152.5 MB written
+HEAD_FWD_TRAFFIC = 236.4e6      # profiles/r1i_launch_summary.md (ncu --set full): 86.2 MB read + 150.2 MB written
 
 
 def algorithmic_bytes_encode(B, L, C, D=3, table_bytes=4, out_bytes=4):
