@@ -53,6 +53,7 @@ struct GemmParams {
     uint32_t lda, ldb, ldc, ldm;
     uint32_t M, N, K;
     uint32_t chunks_per_split;
+    uint32_t stages;         // 2 or 3 (3 = one CTA per SM; 2 = two CTAs per SM when the grid has more CTAs than SMs)
     uint32_t mask_cols;
     int a_trans, b_trans, epilogue, act, precision;
     float slope;
@@ -189,8 +190,8 @@ __global__ void __launch_bounds__(gemm::kCtaThreads) gemm_tc_kernel(const GemmPa
     if (warp == kThreads / 32) {
         // ===================== issuing warp: waits for a full stage, issues the chunk's MMAs, releases the stage ===========
         for (uint32_t c = 0; c < nc; ++c) {
-            const uint32_t s = c % kStages;
-            umma::mbar_wait(umma::smem_u32(&s_full[s]), (c / kStages) & 1u);
+            const uint32_t s = c % p.stages;
+            umma::mbar_wait(umma::smem_u32(&s_full[s]), (c / p.stages) & 1u);
             if (umma::elect_one()) {
                 umma::fence_after_sync();
                 const uint32_t sa = umma::smem_u32(smem + s * kStageBytes);
@@ -226,9 +227,9 @@ __global__ void __launch_bounds__(gemm::kCtaThreads) gemm_tc_kernel(const GemmPa
             rb.load(p.B, p.ldb, b_tr, b_vec, n0, p.N, (c_begin + c) * kKC, p.K, tid);
         };
         auto consume = [&](const OperandRegs<kBM>& ra, const OperandRegs<kBN>& rb, uint32_t c) {
-            const uint32_t s = c % kStages;
+            const uint32_t s = c % p.stages;
             uint8_t* stage = smem + s * kStageBytes;
-            if (c >= kStages) umma::mbar_wait(umma::smem_u32(&s_empty[s]), ((c / kStages) - 1u) & 1u);
+            if (c >= p.stages) umma::mbar_wait(umma::smem_u32(&s_empty[s]), ((c / p.stages) - 1u) & 1u);
             if (!(dbg & 2)) {
                 ra.store(stage, stage + kAPlane, a_tr, split, tid);
                 rb.store(stage + 2 * kAPlane, stage + 2 * kAPlane + kBPlane, b_tr, split, tid);
@@ -377,14 +378,16 @@ extern "C" int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const f
     p.mask_cols = mask_cols;
     p.a_trans = a_trans; p.b_trans = b_trans; p.epilogue = epilogue; p.act = act; p.precision = precision;
     p.slope = slope;
+    dim3 grid(div_up(M, gemm::kBM), div_up(N, gemm::kBN), k_splits);
+    p.stages = ((size_t)grid.x * grid.y * grid.z > (size_t)kNumSMs) ? 2u : gemm::kStages;     // second wave -> co-residency
+    const size_t smem = (size_t)p.stages * gemm::kStageBytes + 128;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::kSmem);
         if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "gemm_tc: %s", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid(div_up(M, gemm::kBM), div_up(N, gemm::kBN), k_splits);
-    SANERF_LAUNCH(gemm_tc_kernel, grid, gemm::kCtaThreads, gemm::kSmem, static_cast<cudaStream_t>(stream), p);
+    SANERF_LAUNCH(gemm_tc_kernel, grid, gemm::kCtaThreads, smem, static_cast<cudaStream_t>(stream), p);
     return check_launch("gemm_tc_kernel");
 }
 
