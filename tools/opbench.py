@@ -121,6 +121,42 @@ for order in ("ray-ordered", "uniform random"):
     hf(True)
     report("field head backward (MLP, 3xTF32)", f"B=262144, {order}", timeit(hb), B * (640 + 64 + 128))
 
+# ---- stage-2 kernels: ray-composited grid features, tensor-core GEMM of the samvit head, LayerNorm + MSE
+from sanerf_b200 import fused as F2
+enc = GridEncoder(input_dim=3, num_levels=16, level_dim=8, base_resolution=16, log2_hashmap_size=19, desired_resolution=512).to(dev)
+Nr, Tr = 4096, 32
+xr = ray_samples(Nr, Tr).view(Nr, Tr, 3).contiguous()
+wr = torch.rand(Nr, Tr, device=dev)
+f_out = torch.empty(Nr, 128, device=dev); g_ray = torch.randn(Nr, 128, device=dev); g_tab = torch.zeros_like(enc.embeddings)
+S, H = float(np.log2(enc.per_level_scale)), int(enc.base_resolution)
+st = _lib.current_stream(dev)
+rf_bytes = Nr * Tr * (16 + 16 * 8 * 8 * 4) + Nr * 128 * 4
+report("ray features forward (encode + weighted ray sum)", "SAM grid L16 F8 T2^19, 4096 rays x 32, ray-ordered",
+       timeit(lambda: _lib.check(lib.sanerf_ray_features_forward(xr.data_ptr(), wr.data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
+                                                                 Nr, Tr, 8, 16, S, H, f_out.data_ptr(), st), "rf")), rf_bytes)
+report("ray features backward (factorised-gradient scatter)", "SAM grid L16 F8 T2^19, 4096 rays x 32, ray-ordered",
+       timeit(lambda: _lib.check(lib.sanerf_ray_features_backward(xr.data_ptr(), wr.data_ptr(), g_ray.data_ptr(), enc.offsets.data_ptr(),
+                                                                  Nr, Tr, 8, 16, S, H, g_tab.data_ptr(), st), "rb")), rf_bytes)
+del enc, g_tab
+Mg = 4096
+for name, (N_, K_, kw) in {"forward layer 4096x256x256 (bias + leaky ReLU)": (256, 256, dict(act=True)),
+                           "forward layer 4096x256x419 (skip layer, unaligned rows)": (256, 419, dict(act=True)),
+                           "data gradient 4096x256x256 (B transposed, activation mask)": (256, 256, dict(b_trans=True, epilogue=1))}.items():
+    A = torch.randn(Mg, K_, device=dev); Bm = torch.randn((K_, N_) if kw.get("b_trans") else (N_, K_), device=dev)
+    Cm = torch.empty(Mg, N_, device=dev); bias = torch.randn(N_, device=dev); mask = torch.randn(Mg, N_, device=dev)
+    us = timeit(lambda: F2.gemm_tc(A, Bm, Cm, Mg, N_, K_, bias=None if kw.get("epilogue") else bias, mask=mask if kw.get("epilogue") else None,
+                                   mask_cols=N_ if kw.get("epilogue") else 0, **kw))
+    rows.append(f"| gemm_tc (tcgen05 3xTF32) | {name} | {us:.1f} | {(Mg * K_ + N_ * K_ + Mg * N_) * 4 / 1e6:.1f} | "
+                f"{2 * Mg * N_ * K_ / us / 1e6:.1f} TFLOP/s fp32-equivalent ({6 * Mg * N_ * K_ / us / 1e6:.1f} tf32 issued) | — |")
+Ad = torch.randn(Mg, 256, device=dev); Xd = torch.randn(Mg, 256, device=dev); gW = torch.zeros(256, 256, device=dev)
+us = timeit(lambda: F2.gemm_tc(Ad, Xd, gW, 256, 256, Mg, a_trans=True, b_trans=True, k_splits=16, epilogue=2))
+rows.append(f"| gemm_tc (tcgen05 3xTF32) | weight gradient 256x256x4096 (both operands transposed, split-K 16, red.add) | {us:.1f} | "
+            f"{(2 * Mg * 256 + 256 * 256) * 4 / 1e6:.1f} | {2 * 256 * 256 * Mg / us / 1e6:.1f} TFLOP/s fp32-equivalent | — |")
+ln = torch.nn.LayerNorm(256).to(dev); ln.weight.grad = torch.zeros_like(ln.weight); ln.bias.grad = torch.zeros_like(ln.bias)
+xo = torch.randn(Mg, 256, device=dev); tgt = torch.randn(1, 256, 64, 64, device=dev); lossb = torch.zeros(1, device=dev); yb = torch.empty_like(xo)
+report("LayerNorm(256) + MSE, forward + backward in one kernel", "4096 rays, [1,256,64,64] target read in place",
+       timeit(lambda: F2.layernorm_mse(xo, ln, tgt, lossb, yb)), Mg * 256 * 4 * 4)
+
 # ---- SH
 d = torch.nn.functional.normalize(torch.randn(262144, 3, device=dev), dim=-1)
 sh_out = torch.empty(262144, 16, device=dev)
