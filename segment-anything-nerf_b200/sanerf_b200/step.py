@@ -112,7 +112,6 @@ class FusedRGBStep:
         self.critical_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_CRIT_PRIO", -1)))
         self.distort_done = torch.cuda.Event()
         self.pending_main = False
-        self._works = []
         self.sharded_update = True
         self.graphs = {}
         self.eager_runs = {}
@@ -167,9 +166,8 @@ class FusedRGBStep:
                                                          L["enc"].data_ptr() if update_proposal else None, st)
                 check(rc, "prop_density_forward")
 
-    def _launch_back(self, update_proposal, reduce_small=False):
-        """Final level forward, losses, backward of everything (``reduce_small``: start the all-reduces of the small
-        gradient ranges as soon as they are complete)."""
+    def _launch_back(self, update_proposal):
+        """Final level forward, losses, backward of everything."""
         m, lib, N = self.model, _lib.load(), self.N
         st = _lib.current_stream(self.dev)
         span, check = _lib.stats.span, _lib.check
@@ -241,8 +239,6 @@ class FusedRGBStep:
                                                               enc.embeddings.grad.data_ptr(), mlp.net[0].weight.grad.data_ptr(),
                                                               mlp.net[1].weight.grad.data_ptr(), st2)
                     check(rc, "prop_density_backward")
-                if reduce_small:                          # proposal tables + MLPs: reduced while the final-level chain runs
-                    self._reduce_async(self._prop_start(), self.optimizer.flat_param.numel())
         # ---------------- final level: view head + photometric loss (forward and backward), distortion loss
         v1, v2, v3 = (l.weight for l in m.view_mlp.net)
         with span("view_head", N=N):
@@ -271,8 +267,6 @@ class FusedRGBStep:
                                                  g.offsets.data_ptr(), g.embeddings.grad.data_ptr(), B, 3, 2, 16, 16, S, H, None,
                                                  None, 0, 0, 0, _lib.SANERF_F32, _lib.LAYOUT_BLC, st)
         check(rc, "grid_encode_backward")
-        if reduce_small:                                  # grid_mlp + view_mlp gradients are complete: tiny reduction
-            self._reduce_async(self._main_range()[1], self._prop_start())
         if lam_p > 0 or have_gw2:
             main.wait_stream(self.side_stream)            # join
 
@@ -283,16 +277,6 @@ class FusedRGBStep:
     # reading the parameters: checkpoints, evaluation, tests).
     def _main_range(self):
         return self.optimizer.ranges[id(self.model.grid.embeddings)]
-
-    def _prop_start(self):
-        """Flat offset where the proposal networks' parameters begin (they trail the buffer: nerf/network.py declares
-        grid, grid_mlp, view_mlp, prop_encoders, prop_mlp in this order)."""
-        m = self.model
-        starts = [self.optimizer.ranges[id(p)][0] for p in [*m.prop_encoders.parameters(), *m.prop_mlp.parameters()]]
-        others = [self.optimizer.ranges[id(p)][1] for p in [m.grid.embeddings, *m.grid_mlp.parameters(), *m.view_mlp.parameters()]]
-        b0 = min(starts)
-        assert max(others) <= b0, "proposal parameters are expected to trail the flat parameter buffer"
-        return b0
 
     def _update_main(self):
         """Update of the main table.  Multi-GPU: reduce-scatter of its gradient, Adam on this rank's 1/world shard only
@@ -319,19 +303,11 @@ class FusedRGBStep:
         sharded_update(opt.flat_param, opt.flat_grad, a, b,
                        lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True), world, rank)
 
-    def _reduce_async(self, lo, hi):
-        if self.world_size > 1 and hi > lo:
-            self._works.append(dist.all_reduce(self.optimizer.flat_grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
-
     def _update_rest(self):
         a, b = self._main_range()
         n = self.optimizer.flat_param.numel()
         assert a == 0, "the main table is expected to lead the flat parameter buffer"
-        if self._works:                                    # reductions of the small ranges, started inside the backward
-            for w in self._works:
-                w.wait()
-            self._works = []
-        elif self.world_size > 1 and not os.environ.get("SANERF_DBG_SKIP_TAIL_NCCL"):
+        if self.world_size > 1 and not os.environ.get("SANERF_DBG_SKIP_TAIL_NCCL"):
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
 
@@ -367,7 +343,7 @@ class FusedRGBStep:
         # captures ONE all-reduce of the small ranges on the side branch beside the hash-grid scatter was also no faster
         # at 2 GPUs: 0.949-0.959 vs 0.942-0.944 ms.  At 8 GPUs this tail reduction costs 75 us and the deferred
         # main-table exchange another 74 us: tools/ab_nccl_g8.sh, 1.054 / 0.980 / 0.979 / 0.914 ms.)
-        self._launch_back(update_proposal, reduce_small=False)
+        self._launch_back(update_proposal)
         self._update_rest()
 
     def _graphs(self, update_proposal):
@@ -385,7 +361,7 @@ class FusedRGBStep:
                 with torch.cuda.graph(gf):
                     _critical(self, lambda: self._launch_front(update_proposal))
                 with torch.cuda.graph(gb):
-                    _critical(self, lambda: self._launch_back(update_proposal, reduce_small=False))
+                    _critical(self, lambda: self._launch_back(update_proposal))
                 self.graphs[key] = (gf, gb)
         return self.graphs[key]
 
