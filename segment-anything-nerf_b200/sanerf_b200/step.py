@@ -107,7 +107,7 @@ class FusedRGBStep:
         self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)
         self.image = torch.empty(N, 3, **f32)
         self.loss = torch.zeros(1, **f32)
-        self.side_stream = torch.cuda.Stream(dev)
+        self.side_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_SIDE_PRIO", 0)))
         self.update_stream = torch.cuda.Stream(dev, priority=_update_priority(world_size))
         self.critical_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_CRIT_PRIO", -1)))
         self.distort_done = torch.cuda.Event()
