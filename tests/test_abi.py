@@ -124,3 +124,37 @@ def test_ops_fail_loudly_without_cuda():
         trunc_exp(torch.zeros(3))
     with pytest.raises(RuntimeError):
         composite(torch.ones(2, 4), torch.ones(2, 4), torch.ones(2, 4))
+
+
+def test_stage2_ops_fail_loudly_without_cuda():
+    """The stage-2 operators (ray features, tensor-core GEMM, LayerNorm + MSE) have no CPU path either, and the
+    SAM head falls back to nothing: SkipConnMLP on CPU tensors runs the plain torch layers of the reference."""
+    from gridencoder import GridEncoder
+    from nerf.network import SkipConnMLP
+    from sanerf_b200 import fused
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    enc = GridEncoder(num_levels=2, level_dim=8, base_resolution=4, log2_hashmap_size=6, desired_resolution=8)
+    with pytest.raises(RuntimeError):
+        fused.ray_features(torch.zeros(2, 4, 3), torch.ones(2, 4), enc)
+    a, b, c = torch.zeros(8, 8), torch.zeros(8, 8), torch.zeros(8, 8)
+    with pytest.raises(RuntimeError):
+        fused.gemm_tc(a, b, c, 8, 8, 8)
+    mlp = SkipConnMLP(6, 4, 8, 3, skip_layers=[1])
+    mlp.tc = True
+    x = torch.randn(5, 6)
+    assert not fused.skip_mlp_supported(mlp, x)            # CPU tensor: the torch layers run (module semantics of the reference)
+    y = mlp(x)
+    h = torch.nn.functional.leaky_relu(mlp.net[0](x))
+    h = torch.nn.functional.leaky_relu(mlp.net[1](torch.cat([h, x], dim=-1)))
+    torch.testing.assert_close(y, mlp.net[2](h))
+
+
+def test_update_stream_priority_policy(monkeypatch):
+    from sanerf_b200.step import _update_priority
+
+    monkeypatch.delenv("SANERF_UPD_PRIO", raising=False)
+    assert _update_priority(1) == 0 and _update_priority(2) == -1 and _update_priority(8) == -1
+    monkeypatch.setenv("SANERF_UPD_PRIO", "0")
+    assert _update_priority(8) == 0
