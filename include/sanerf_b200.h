@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 16
+#define SANERF_ABI_VERSION 17
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -104,14 +104,17 @@ SANERF_API int sanerf_grad_weight_decay(const void* embeddings, void* grad, cons
  *  x01      f32 [N*T, 3]  samples of N dense rays (T each), already mapped to [0,1]^3
  *  weights  f32 [N*T]     compositing weights (constants here: the density field is frozen in stage 2, main.py:255-262)
  *  out      f32 [N, L*C]  sum_i weights[r,i] * encode(x01[r,i])
- *  g_out    f32 [N, L*C]  incoming gradient;  grad_embeddings f32 [rows, C] is accumulated into (caller zero-fills)
+ *  g_out    f32 [N, L*C]  incoming gradient;  grad_embeddings f32 [rows, C] is accumulated into (caller zero-fills);
+ *           the backward scatters levels [level_begin, level_end) only (0, L = all): a data-parallel trainer launches it
+ *           per level group and starts the reduce-scatter of a finished slice of the table while the next group runs
  */
 SANERF_API int sanerf_ray_features_forward(const float* x01, const float* weights, const float* embeddings,
                                 const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
                                 uint32_t H, float* out, void* stream);
 SANERF_API int sanerf_ray_features_backward(const float* x01, const float* weights, const float* g_out,
                                  const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
-                                 uint32_t H, float* grad_embeddings, void* stream);
+                                 uint32_t H, float* grad_embeddings, uint32_t level_begin, uint32_t level_end,
+                                 void* stream);
 
 /* Debug / parity entry point (no reference equivalent — SURVEY §8 c7): for every sample,
  * level < L and corner < 2^D write the table row (relative to the level's offset) the

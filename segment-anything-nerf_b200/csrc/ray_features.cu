@@ -33,6 +33,7 @@ struct RayFeatParams {
     float* g_table;          // [rows, C]   (backward, accumulated into)
     uint32_t N, T, L, H;
     float S;
+    uint32_t level_begin, level_end;   // backward: levels [level_begin, level_end) of this launch (forward: all)
 };
 
 constexpr uint32_t kRayWarps = 8;
@@ -83,7 +84,7 @@ template <uint32_t C>
 __global__ void __launch_bounds__(kRayWarps * 32) ray_features_backward_kernel(const RayFeatParams p) {
     pdl_begin();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t ray = blockIdx.x * kRayWarps + warp, level = blockIdx.y;
+    const uint32_t ray = blockIdx.x * kRayWarps + warp, level = p.level_begin + blockIdx.y;
     if (ray >= p.N) return;
     float g[C];
     RowIO<float, C>::load(p.g_out + ((size_t)ray * p.L + level) * C, g);     // same address in every lane: one broadcast
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) ray_features_backward_kernel(c
 template <bool kBackward>
 static int launch_ray_features(const RayFeatParams& p, uint32_t C, cudaStream_t st) {
     if (p.N == 0 || p.T == 0 || p.L == 0) return SANERF_OK;
-    dim3 grid(div_up(p.N, kRayWarps), p.L, 1);
+    dim3 grid(div_up(p.N, kRayWarps), kBackward ? p.level_end - p.level_begin : p.L, 1);
     const uint32_t threads = kRayWarps * 32;
     switch (C) {
         case 2:
@@ -160,19 +161,21 @@ extern "C" int sanerf_ray_features_forward(const float* x01, const float* weight
     SANERF_REQUIRE_PTR(embeddings);
     SANERF_REQUIRE_PTR(offsets);
     SANERF_REQUIRE_PTR(out);
-    RayFeatParams p{x01, weights, embeddings, nullptr, offsets, out, nullptr, N, T, L, H, S};
+    RayFeatParams p{x01, weights, embeddings, nullptr, offsets, out, nullptr, N, T, L, H, S, 0u, L};
     return launch_ray_features<false>(p, C, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sanerf_ray_features_backward(const float* x01, const float* weights, const float* g_out,
                                             const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
-                                            uint32_t H, float* grad_embeddings, void* stream) {
-    if (N == 0) return SANERF_OK;
+                                            uint32_t H, float* grad_embeddings, uint32_t level_begin, uint32_t level_end,
+                                            void* stream) {
+    if (level_end > L) level_end = L;
+    if (N == 0 || level_begin >= level_end) return SANERF_OK;
     SANERF_REQUIRE_PTR(x01);
     SANERF_REQUIRE_PTR(weights);
     SANERF_REQUIRE_PTR(g_out);
     SANERF_REQUIRE_PTR(offsets);
     SANERF_REQUIRE_PTR(grad_embeddings);
-    RayFeatParams p{x01, weights, nullptr, g_out, offsets, nullptr, grad_embeddings, N, T, L, H, S};
+    RayFeatParams p{x01, weights, nullptr, g_out, offsets, nullptr, grad_embeddings, N, T, L, H, S, level_begin, level_end};
     return launch_ray_features<true>(p, C, static_cast<cudaStream_t>(stream));
 }

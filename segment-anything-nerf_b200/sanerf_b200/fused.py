@@ -331,7 +331,7 @@ class _RayFeatures(Function):
         g_out = g_out.contiguous().float()
         with _lib.stats.span("ray_features_backward", N=N, T=T, C=C):
             rc = _lib.load().sanerf_ray_features_backward(x01.data_ptr(), weights.data_ptr(), g_out.data_ptr(),
-                                                          offsets.data_ptr(), N, T, C, L, S, H, g_table.data_ptr(),
+                                                          offsets.data_ptr(), N, T, C, L, S, H, g_table.data_ptr(), 0, L,
                                                           _stream(g_out))
         _lib.check(rc, "ray_features_backward")
         return None, None, g_table, None, None, None

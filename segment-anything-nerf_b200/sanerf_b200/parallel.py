@@ -39,14 +39,9 @@ def shard_bounds(a, b, world_size, rank):
     return a + rank * shard, a + (rank + 1) * shard
 
 
-def sharded_update(flat_param, flat_grad, a, b, apply_fn, world_size=None, rank=None):
-    """Update ``flat_param[a:b]`` from per-rank gradients ``flat_grad[a:b]``:
-
-      reduce-scatter of the gradient  ->  ``apply_fn(lo, hi)`` on this rank's shard only (it must consume
-      ``flat_grad[lo:hi]``, holding the SUM over ranks, and leave it zeroed)  ->  all-gather of the updated shard.
-
-    Same bytes on the wire as an all-reduce, 1/world of the optimizer traffic, bit-identical parameters on every rank.
-    The rest of ``flat_grad[a:b]`` is zeroed.  Backends without reduce-scatter (gloo, CPU tests) all-reduce instead."""
+def reduce_scatter_range(flat_grad, a, b, world_size=None, rank=None):
+    """First half of the sharded update of ``[a, b)``: after it, ``flat_grad[lo:hi]`` (this rank's shard) holds the SUM
+    over ranks.  Backends without reduce-scatter (gloo, CPU tests) all-reduce the whole range instead."""
     world_size = dist.get_world_size() if world_size is None else world_size
     rank = dist.get_rank() if rank is None else rank
     lo, hi = shard_bounds(a, b, world_size, rank)
@@ -54,6 +49,15 @@ def sharded_update(flat_param, flat_grad, a, b, apply_fn, world_size=None, rank=
         dist.reduce_scatter_tensor(flat_grad[lo:hi], flat_grad[a:b], op=dist.ReduceOp.SUM)        # in place
     else:
         dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM)
+    return lo, hi
+
+
+def apply_and_gather_range(flat_param, flat_grad, a, b, apply_fn, world_size=None, rank=None):
+    """Second half: ``apply_fn(lo, hi)`` on this rank's shard (it must consume ``flat_grad[lo:hi]`` and leave it zeroed),
+    the rest of ``flat_grad[a:b]`` is zeroed, and the updated shards are all-gathered into ``flat_param[a:b]``."""
+    world_size = dist.get_world_size() if world_size is None else world_size
+    rank = dist.get_rank() if rank is None else rank
+    lo, hi = shard_bounds(a, b, world_size, rank)
     apply_fn(lo, hi)
     if lo > a:
         flat_grad[a:lo].zero_()
@@ -65,3 +69,17 @@ def sharded_update(flat_param, flat_grad, a, b, apply_fn, world_size=None, rank=
         shard = hi - lo
         dist.all_gather([flat_param[a + r * shard:a + (r + 1) * shard] for r in range(world_size)], flat_param[lo:hi].clone())
     return lo, hi
+
+
+def sharded_update(flat_param, flat_grad, a, b, apply_fn, world_size=None, rank=None):
+    """Update ``flat_param[a:b]`` from per-rank gradients ``flat_grad[a:b]``:
+
+      reduce-scatter of the gradient  ->  ``apply_fn(lo, hi)`` on this rank's shard only (it must consume
+      ``flat_grad[lo:hi]``, holding the SUM over ranks, and leave it zeroed)  ->  all-gather of the updated shard.
+
+    Same bytes on the wire as an all-reduce, 1/world of the optimizer traffic, bit-identical parameters on every rank.
+    The rest of ``flat_grad[a:b]`` is zeroed.  The two halves are separate functions so that a trainer can run the
+    reduce-scatter of a finished slice of a table while the backward of the next slice is still running
+    (``sanerf_b200/step.py: FusedSAMStep``)."""
+    reduce_scatter_range(flat_grad, a, b, world_size, rank)
+    return apply_and_gather_range(flat_param, flat_grad, a, b, apply_fn, world_size, rank)

@@ -601,7 +601,7 @@ class FusedSAMStep:
         st = _lib.current_stream(self.dev)
         with span("ray_features_backward", N=N, T=T, C=C):
             rc = lib.sanerf_ray_features_backward(L["x01"].data_ptr(), L["weights"].data_ptr(), g_sam.data_ptr(),
-                                                  g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), st)
+                                                  g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), 0, nl, st)
         check(rc, "ray_features_backward")
         if direct:                                         # weight-gradient GEMMs ran beside the data-gradient chain + scatter
             torch.cuda.current_stream(self.dev).wait_stream(self.side_stream)
