@@ -387,6 +387,28 @@ def run_sam(args, rank, world, local_rank):
         last[0] = trainer.step(*host[i % 4], target_host, 64, 64).item()
     e2e_ms = _timed(e2e, args.steps, dev, world, flush)
     clocks = sampler.stop() if rank == 0 else {}
+    # roofline of the dominant kernel (profiles/r1i_sam_step.md: the s_grid scatter): the same step replayed eagerly
+    # with CUDA events around its launches, as in run_ours
+    plan = trainer.plan(n, 64, 64, tuple(target.shape))
+    roofline, launches = None, None
+    if plan is not None:
+        trainer.flush()
+        plan.use_graph = False
+        n_eager = max(3, min(args.steps, 10))
+        _lib.stats.reset("ray_features_backward", None)
+        _timed(lambda i: trainer.step(*sets[i % 4], target_dev, 64, 64), n_eager, dev, world, flush)
+        launches = (_lib.stats.count // n_eager) * args.steps
+        spans = [ms_ for ms_, _ in _lib.stats.durations_ms()]
+        plan.use_graph = True
+        if spans:
+            peak, peak_src = load_peaks()
+            alg = n * 32 * (16 + 16 * 8 * 8 * 4) + n * 128 * 4
+            avg = sum(spans) / len(spans)
+            roofline = {"bound": "hbm", "kernel": "ray_features_backward_kernel<8> (s_grid L16 F8 T2^19 scatter with the factorised "
+                        "gradient w_i * g_ray, 4096 rays x 32 samples): 16 B in + 4096 B of reductions per sample + 512 B per ray",
+                        "achieved": alg / avg / 1e6, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                        "frac": alg / avg / 1e6 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                        "avg_launch_ms": avg, "launches_timed": len(spans)}
     if rank != 0:
         return
     print(json.dumps({
@@ -402,7 +424,7 @@ def run_sam(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": 2 * n * 3 * 4 + 256 * 64 * 64 * 4, "d2h_bytes_per_step": 4, "last_loss": last[0]},
-        "gpu_launches": None, "roofline": None, "cpu_baseline": None}), flush=True)
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None}), flush=True)
 
 
 def run_frame(args, rank, world, local_rank):
