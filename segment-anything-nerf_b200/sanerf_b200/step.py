@@ -342,8 +342,10 @@ class FusedRGBStep:
         # (starting the small ranges' all-reduces inside the backward was measured slower: NCCL's CTAs spin on SMs the
         # persistent one-CTA-per-SM field-head kernels count on, so they stay at the end of the step; a variant that
         # captures ONE all-reduce of the small ranges on the side branch beside the hash-grid scatter was also no faster
-        # at 2 GPUs: 0.949-0.959 vs 0.942-0.944 ms.  At 8 GPUs this tail reduction costs 75 us and the deferred
-        # main-table exchange another 74 us: tools/ab_nccl_g8.sh, 1.054 / 0.980 / 0.979 / 0.914 ms.)
+        # at 2 GPUs: 0.949-0.959 vs 0.942-0.944 ms.  At 8 GPUs removing this tail reduction saves 75 us and removing the
+        # deferred main-table exchange another 74 us (tools/ab_nccl_g8.sh: 1.054 / 0.980 / 0.979 / 0.914 ms), but MOVING the
+        # tail reduction beside the hash-grid scatter (a third graph for the scatter, NCCL on the update stream) changes
+        # nothing: 1.0528 vs 1.0556 ms at 8 GPUs, 0.950 vs 0.949 at 2 - what the collectives absorb is rank skew.)
         self._launch_back(update_proposal)
         self._update_rest()
 
