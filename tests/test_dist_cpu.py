@@ -83,6 +83,39 @@ def test_sharded_update_equals_allreduce_update():
     _spawn(_sharded_update_case)
 
 
+def _sliced_update_case(rank, world):
+    """The two halves used separately, slice by slice (a trainer reduces a finished slice of a table while the next
+    slice's gradient is still being written): reduce every slice first, update + gather later == one all-reduce update."""
+    torch.manual_seed(1)
+    n = 64 * 6
+    slices = [(0, 64), (64, 64 * 3), (64 * 3, 64 * 6)]
+    param0 = torch.randn(n)
+    grads = [torch.randn(n, generator=torch.Generator().manual_seed(20 + r)) for r in range(world)]
+    lr = 0.05
+    param, grad = param0.clone(), torch.zeros(n)
+
+    def apply(lo, hi):
+        param[lo:hi] -= lr * grad[lo:hi] / world
+        grad[lo:hi].zero_()
+
+    for a, b in slices:                                  # the slice's gradient "arrives", then its reduction starts
+        grad[a:b] = grads[rank][a:b]
+        lo, hi = parallel.reduce_scatter_range(grad, a, b, world, rank)
+        assert (lo, hi) == parallel.shard_bounds(a, b, world, rank)
+        assert torch.equal(grad[lo:hi], sum(g[lo:hi] for g in grads))      # the local shard holds the sum over ranks
+    for a, b in slices:
+        parallel.apply_and_gather_range(param, grad, a, b, apply, world, rank)
+    expect = param0 - lr * sum(grads) / world
+    assert torch.equal(param, expect) and float(grad.abs().max()) == 0.0
+    ref = param.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(ref, param)
+
+
+def test_sliced_reduce_then_update_equals_allreduce_update():
+    _spawn(_sliced_update_case)
+
+
 def test_shard_bounds_reject_unaligned_ranges():
     assert parallel.shard_bounds(0, 12_599_936, 8, 3) == (3 * 1_574_992, 4 * 1_574_992)
     with pytest.raises(ValueError):
