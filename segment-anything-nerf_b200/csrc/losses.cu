@@ -148,10 +148,14 @@ __global__ void __launch_bounds__(32 * kLossWarps) distortion_loss_kernel(
 // torch.optim.Adam semantics (no weight decay, no amsgrad):  m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
 // p -= lr / (1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  `dyn` = {lr_t, 1-b1^t, 1-b2^t} lives on the device so
 // that a captured CUDA graph can be replayed with a moving step count / learning-rate schedule.
-__global__ void adam_schedule_kernel(int32_t* step, float* dyn, float lr0, float beta1, float beta2, float decay_iters) {
+__global__ void adam_schedule_kernel(int32_t* step, float* dyn, float lr0, float beta1, float beta2, float decay_iters,
+                                     int32_t* gate, float ema_decay) {
     pdl_begin();
     const int32_t t = *step + 1;
     *step = t;
+    // torch_ema.ExponentialMovingAverage.update (nerf/utils.py:616, 1862): decay_t = min(decay, (1 + t) / (10 + t))
+    dyn[3] = 1.0f - fminf(ema_decay, (1.0f + (float)t) / (10.0f + (float)t));
+    if (gate) *gate = 1;      // the step that starts here leaves a gradient behind for every deferred range
     // LambdaLR(0.1 ** min(iter / iters, 1)) evaluated at iter = t-1 (main.py:312-313; scheduler steps after the optimizer)
     const float frac = (decay_iters > 0.0f) ? fminf((float)(t - 1) / decay_iters, 1.0f) : 0.0f;
     dyn[0] = lr0 * powf(0.1f, frac);
@@ -162,9 +166,13 @@ __global__ void adam_schedule_kernel(int32_t* step, float* dyn, float lr0, float
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, size_t n4, size_t n,
                                                         const float* __restrict__ dyn, float beta1, float beta2,
-                                                        float eps, float grad_scale, int zero_grad) {
+                                                        float eps, float grad_scale, int zero_grad,
+                                                        const int32_t* __restrict__ gate, float* __restrict__ ema) {
     pdl_begin();
-    const float lr = __ldg(dyn), bc1 = __ldg(dyn + 1), bc2 = __ldg(dyn + 2);
+    // A deferred range is updated at the START of the next step; after a flush() (which applied the update early and
+    // cleared the gate) there is nothing pending and a pass over zero gradients must not move the parameters by momentum.
+    if (gate != nullptr && *gate == 0) return;
+    const float lr = __ldg(dyn), bc1 = __ldg(dyn + 1), bc2 = __ldg(dyn + 2), ema_w = __ldg(dyn + 3);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     auto update = [&](float& pp, float gg, float& mm, float& vv) {
@@ -172,6 +180,12 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
         mm = beta1 * mm + (1.0f - beta1) * gg;
         vv = beta2 * vv + (1.0f - beta2) * gg * gg;
         pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+    };
+    // shadow -= (1 - decay_t) * (shadow - param), with the parameter just updated (torch_ema update after optimizer.step)
+    auto ema4 = [&](size_t k, const float4& q) {
+        float4 e = __ldcs(reinterpret_cast<float4*>(ema) + k);
+        e.x -= ema_w * (e.x - q.x); e.y -= ema_w * (e.y - q.y); e.z -= ema_w * (e.z - q.z); e.w -= ema_w * (e.w - q.w);
+        __stcs(reinterpret_cast<float4*>(ema) + k, e);
     };
     // Every element is read and written exactly once per step: streaming (evict-first) accesses keep the pass from
     // flushing the tables and activations of the kernels it overlaps with out of the L2.
@@ -188,6 +202,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
         update(pq.z, gq.z, mq.z, vq.z); update(pq.w, gq.w, mq.w, vq.w);
         __stcs(reinterpret_cast<float4*>(p) + i, pp); __stcs(reinterpret_cast<float4*>(m) + i, mm); __stcs(reinterpret_cast<float4*>(v) + i, vv);
         __stcs(reinterpret_cast<float4*>(p) + j, pq); __stcs(reinterpret_cast<float4*>(m) + j, mq); __stcs(reinterpret_cast<float4*>(v) + j, vq);
+        if (ema) { ema4(i, pp); ema4(j, pq); }
         if (zero_grad) {
             __stcs(reinterpret_cast<float4*>(g) + i, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
             __stcs(reinterpret_cast<float4*>(g) + j, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -199,10 +214,12 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
         update(pp.x, gg.x, mm.x, vv.x); update(pp.y, gg.y, mm.y, vv.y);
         update(pp.z, gg.z, mm.z, vv.z); update(pp.w, gg.w, mm.w, vv.w);
         __stcs(reinterpret_cast<float4*>(p) + i, pp); __stcs(reinterpret_cast<float4*>(m) + i, mm); __stcs(reinterpret_cast<float4*>(v) + i, vv);
+        if (ema) ema4(i, pp);
         if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         update(p[i], g[i], m[i], v[i]);
+        if (ema) ema[i] -= ema_w * (ema[i] - p[i]);
         if (zero_grad) g[i] = 0.0f;
     }
 }
@@ -236,19 +253,20 @@ extern "C" int sanerf_distortion_loss(const float* bins, const float* w, uint32_
 }
 
 extern "C" int sanerf_adam_schedule(int32_t* step, float* dyn, float lr0, float beta1, float beta2, float decay_iters,
-                                    void* stream) {
+                                    int32_t* gate, float ema_decay, void* stream) {
     SANERF_REQUIRE_PTR(step); SANERF_REQUIRE_PTR(dyn);
-    SANERF_LAUNCH(adam_schedule_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), step, dyn, lr0, beta1, beta2, decay_iters);
+    SANERF_LAUNCH(adam_schedule_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), step, dyn, lr0, beta1, beta2, decay_iters,
+                  gate, ema_decay);
     return check_launch("adam_schedule_kernel");
 }
 
 extern "C" int sanerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint64_t n,
                                 const float* dyn, float beta1, float beta2, float eps, float grad_scale,
-                                int zero_grad, void* stream) {
+                                int zero_grad, const int32_t* gate, float* ema, void* stream) {
     if (n == 0) return SANERF_OK;
     SANERF_REQUIRE_PTR(params); SANERF_REQUIRE_PTR(grads); SANERF_REQUIRE_PTR(exp_avg); SANERF_REQUIRE_PTR(exp_avg_sq);
     SANERF_REQUIRE_PTR(dyn);
-    const uintptr_t align = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq;
+    const uintptr_t align = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)ema;
     if (align & 15u) return fail(SANERF_ERR_MISALIGNED, "adam_step: buffers must be 16-byte aligned");
     const size_t n4 = (size_t)n / 4;
     size_t blocks = div_up(n4 > 0 ? n4 : (size_t)1, (size_t)256);
@@ -258,6 +276,6 @@ extern "C" int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
     // persistent CTAs per SM - no better; the interference is in the memory system, see the streaming accesses above.)
     blocks = div_up(blocks, (size_t)4);
     SANERF_LAUNCH(adam_step_kernel, (uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream), 
-        params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad);
+        params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad, gate, ema);
     return check_launch("adam_step_kernel");
 }

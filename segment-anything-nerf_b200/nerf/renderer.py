@@ -139,8 +139,9 @@ class NeRFRenderer(nn.Module):
     def update_aabb(self, aabb):
         if not torch.is_tensor(aabb):
             aabb = torch.as_tensor(aabb).float()
-        self.aabb_train = aabb.clamp(-self.real_bound, self.real_bound).to(self.aabb_train.device)
-        self.aabb_infer = self.aabb_train.clone()
+        # in place: captured CUDA graphs (sanerf_b200/step.py) hold the addresses of these two buffers
+        self.aabb_train.copy_(aabb.clamp(-self.real_bound, self.real_bound).to(self.aabb_train.device))
+        self.aabb_infer.copy_(self.aabb_train)
 
     def render(self, rays_o, rays_d, staged=False, cam_near_far=None, **kwargs):
         """Same contract as renderer.py:185-219: ``staged`` splits the rays into ``opt.max_ray_batch`` chunks."""

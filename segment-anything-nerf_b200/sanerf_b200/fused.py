@@ -554,14 +554,24 @@ def distort_loss(bins, weights):
 
 # ----------------------------------------------------------------------------------------- optimizer
 class FusedAdam:
-    """Adam(eps=1e-15) + LambdaLR(0.1**min(it/iters,1)) over parameters flattened into ONE fp32 buffer.
+    """Adam(eps=1e-15) + LambdaLR(0.1**min(it/iters,1)) (+ optional EMA, ``ema_decay``) over parameters flattened into ONE
+    fp32 buffer.
 
     Parameters and gradients become views of ``flat_param`` / ``flat_grad`` (the gradient bucket doubles as the
     NCCL all-reduce buffer); one kernel updates everything and clears the gradient in the same pass.  The step
     counter and the schedule live on the device, so a captured CUDA graph replays with a moving learning rate.
+
+    ``ema_decay`` (the reference trains with 0.95: main.py:316, nerf/utils.py:616 ``torch_ema.ExponentialMovingAverage``
+    updated after every optimizer step, :1862): a shadow copy of the flat parameters follows them inside the same
+    kernel pass, with torch_ema's warm-up ``min(decay, (1 + t) / (10 + t))``.
+
+    ``gate`` (1 int32 on the device) makes a DEFERRED range update idempotent: ``schedule()`` sets it at the start of
+    a step, ``apply(..., gated=True)`` does nothing while it is 0, and ``clear_gate()`` (called by a trainer's
+    ``flush()`` after it applied the pending update early) resets it — so the deferred pass baked into the next
+    step's CUDA graph finds nothing to do instead of moving the parameters by momentum on a zero gradient.
     """
 
-    def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000):
+    def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000, ema_decay=None):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
         # every slot is a multiple of 32 elements: views stay 16-byte aligned and any range of whole slots splits into
@@ -583,22 +593,39 @@ class FusedAdam:
             off += n
         self.lr, self.betas, self.eps, self.decay_iters = float(lr), betas, float(eps), float(decay_iters)
         self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
-        self.dyn = torch.tensor([self.lr, 1.0, 1.0, 0.0], device=dev)     # {lr_t, 1-b1^t, 1-b2^t}: neutral before step 1
+        self.dyn = torch.tensor([self.lr, 1.0, 1.0, 0.0], device=dev)     # {lr_t, 1-b1^t, 1-b2^t, 1-ema_t}: neutral before step 1
+        self.gate = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.ema_decay = None if ema_decay is None else float(ema_decay)
+        self.ema = self.flat_param.clone() if ema_decay is not None else None
+        self._ema_backup = None
 
     def zero_grad(self):
         self.flat_grad.zero_()
 
+    def range_of(self, params):
+        """Smallest flat range [start, stop) covering ``params``; raises unless they fill it without foreign slots."""
+        spans = sorted(self.ranges[id(p)] for p in params)
+        if not spans:
+            return 0, 0
+        for (_, b0), (a1, _) in zip(spans, spans[1:]):
+            if b0 != a1:
+                raise ValueError("parameters are not contiguous in the flat buffer")
+        return spans[0][0], spans[-1][1]
+
     def schedule(self):
-        """Advance the device-side step counter and learning-rate / bias-correction terms (one tiny kernel)."""
+        """Advance the device-side step counter and learning-rate / bias-correction / EMA terms (one tiny kernel);
+        marks the deferred ranges as pending (``gate`` = 1)."""
         lib = _lib.load()
         dev = self.flat_param.device
         with torch.cuda.device(dev), _lib.stats.span("adam_schedule"):
             rc = lib.sanerf_adam_schedule(self.step_count.data_ptr(), self.dyn.data_ptr(), self.lr, self.betas[0],
-                                          self.betas[1], self.decay_iters, _lib.current_stream(dev))
+                                          self.betas[1], self.decay_iters, self.gate.data_ptr(),
+                                          0.0 if self.ema_decay is None else self.ema_decay, _lib.current_stream(dev))
         _lib.check(rc, "adam_schedule")
 
-    def apply(self, start=0, stop=None, grad_scale=1.0, zero_grad=True):
-        """Adam update of the flat range [start, stop) with the terms of the LAST ``schedule()`` (multiples of 4)."""
+    def apply(self, start=0, stop=None, grad_scale=1.0, zero_grad=True, gated=False):
+        """Adam update of the flat range [start, stop) with the terms of the LAST ``schedule()`` (multiples of 4).
+        ``gated``: a deferred range — skipped on the device while ``gate`` is 0."""
         stop = self.flat_param.numel() if stop is None else stop
         n = stop - start
         if n <= 0:
@@ -610,9 +637,47 @@ class FusedAdam:
             rc = lib.sanerf_adam_step(self.flat_param.data_ptr() + off, self.flat_grad.data_ptr() + off,
                                       self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off, n, self.dyn.data_ptr(),
                                       self.betas[0], self.betas[1], self.eps, float(grad_scale), int(zero_grad),
-                                      _lib.current_stream(dev))
+                                      self.gate.data_ptr() if gated else None,
+                                      None if self.ema is None else self.ema.data_ptr() + off, _lib.current_stream(dev))
         _lib.check(rc, "adam_step")
+
+    def clear_gate(self):
+        self.gate.zero_()
 
     def step(self, grad_scale=1.0, zero_grad=True):
         self.schedule()
         self.apply(0, None, grad_scale, zero_grad)
+
+    # ---- EMA (torch_ema surface the reference's Trainer uses: update is inside ``apply``; store / copy_to / restore
+    # bracket evaluation and best-checkpoint saving, nerf/utils.py:1684-1695, 1900-1902, 2035-2036, 2083-2095)
+    def ema_store(self):
+        self._ema_backup = self.flat_param.clone()
+
+    def ema_copy_to(self):
+        if self.ema is None:
+            raise RuntimeError("FusedAdam was built without ema_decay")
+        self.flat_param.copy_(self.ema)
+
+    def ema_restore(self):
+        if self._ema_backup is None:
+            raise RuntimeError("ema_restore() without ema_store()")
+        self.flat_param.copy_(self._ema_backup)
+        self._ema_backup = None
+
+    def ema_state_dict(self):
+        """Same layout as ``torch_ema.ExponentialMovingAverage.state_dict()`` over the trainable parameters."""
+        if self.ema is None:
+            raise RuntimeError("FusedAdam was built without ema_decay")
+        shadow = [self.ema[a:a + p.numel()].view_as(p).clone() for p, (a, _) in ((p, self.ranges[id(p)]) for p in self.params)]
+        return {"decay": self.ema_decay, "num_updates": int(self.step_count.item()), "shadow_params": shadow,
+                "collected_params": None}
+
+    def load_ema_state_dict(self, state):
+        if self.ema is None:
+            raise RuntimeError("FusedAdam was built without ema_decay")
+        shadow = state["shadow_params"]
+        if len(shadow) != len(self.params):
+            raise ValueError("EMA state holds a different number of parameters")
+        for p, s in zip(self.params, shadow):
+            a, _ = self.ranges[id(p)]
+            self.ema[a:a + p.numel()].copy_(s.reshape(-1))

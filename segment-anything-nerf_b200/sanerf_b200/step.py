@@ -121,6 +121,9 @@ class FusedRGBStep:
                   *model.prop_encoders.parameters(), *model.prop_mlp.parameters()]:
             if p.grad is None or not p.grad.is_contiguous():
                 raise RuntimeError("FusedRGBStep needs parameters registered with FusedAdam (flat gradient views)")
+        self.prop_range = optimizer.range_of([*model.prop_encoders.parameters(), *model.prop_mlp.parameters()])
+        if self.prop_range[1] != optimizer.flat_param.numel():
+            raise UnsupportedConfig("FusedRGBStep expects the proposal networks at the tail of the flat parameter buffer")
 
     # ------------------------------------------------------------------------------------------------------
     def _launch(self, update_proposal):
@@ -288,34 +291,44 @@ class FusedRGBStep:
         a, b = self._main_range()
         opt = self.optimizer
         if self.world_size == 1:
-            opt.apply(a, b, grad_scale=1.0, zero_grad=True)
+            opt.apply(a, b, grad_scale=1.0, zero_grad=True, gated=True)
             return
         world, rank = self.world_size, dist.get_rank()
         if os.environ.get("SANERF_DBG_SKIP_MAIN_NCCL"):    # timing diagnostics only (tools/ab_nccl_g8.sh): wrong gradients
             lo, hi = shard_bounds(a, b, world, rank)
-            opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True)
+            opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True, gated=True)
             opt.flat_grad[a:b].zero_()
             return
         if not self.sharded_update:                        # plain all-reduce + full-size Adam (checker for the sharded form)
             dist.all_reduce(opt.flat_grad[a:b], op=dist.ReduceOp.SUM)
-            opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True)
+            opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True, gated=True)
             return
         from .parallel import sharded_update
         sharded_update(opt.flat_param, opt.flat_grad, a, b,
-                       lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True), world, rank)
+                       lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True, gated=True), world, rank)
 
-    def _update_rest(self):
+    def _update_rest(self, update_proposal=True):
+        """MLPs and proposal tables, at the end of the step.  On steps that do not train the proposal networks
+        (nerf/utils.py:910-911: 4 of 5 steps after step 3000) their parameters receive NO gradient in the reference
+        (``zero_grad(set_to_none=True)`` leaves ``.grad`` None and torch's Adam skips them), so their range — the tail of
+        the flat buffer — is left out of the exchange and of the update instead of moving by momentum."""
         a, b = self._main_range()
         n = self.optimizer.flat_param.numel()
         assert a == 0, "the main table is expected to lead the flat parameter buffer"
+        if not update_proposal:
+            n = self.prop_range[0]
         if self.world_size > 1 and not os.environ.get("SANERF_DBG_SKIP_TAIL_NCCL"):
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
 
     def flush(self):
+        """Apply a pending deferred table update now (checkpoint, evaluation, tests, switching plans).  The device-side
+        gate is cleared afterwards, so the deferred pass at the start of the next step (baked into its CUDA graph) is a
+        no-op instead of a momentum-only update on a zero gradient."""
         if self.pending_main:
             with torch.cuda.device(self.dev):
                 self._update_main()
+                self.optimizer.clear_gate()
             self.pending_main = False
 
     def gradients_only(self, rays_o, rays_d, gt, update_proposal=True):
@@ -347,13 +360,13 @@ class FusedRGBStep:
         # tail reduction beside the hash-grid scatter (a third graph for the scatter, NCCL on the update stream) changes
         # nothing: 1.0528 vs 1.0556 ms at 8 GPUs, 0.950 vs 0.949 at 2 - what the collectives absorb is rank skew.)
         self._launch_back(update_proposal)
-        self._update_rest()
+        self._update_rest(update_proposal)
 
     def _graphs(self, update_proposal):
         """Single GPU: the whole step is one graph.  Multi-GPU: the forward / backward halves are two graphs and the
         NCCL exchanges stay eager between them.  Capturing them into ONE graph (``SANERF_ONE_GRAPH=1``) works and measures
         the same at 2 GPUs (0.947 / 0.955 vs 0.947 / 0.951 ms), so the eager form, which keeps NCCL's watchdog, is the default."""
-        key = bool(update_proposal)
+        key = (bool(update_proposal), bool(self.model.training))    # the captured launches bake in aabb_train / aabb_infer
         if key not in self.graphs:
             if self.world_size == 1 or self.one_graph:
                 g = torch.cuda.CUDAGraph()
@@ -378,7 +391,7 @@ class FusedRGBStep:
         self.rays_d.copy_(rays_d, non_blocking=True)
         self.gt.copy_(gt, non_blocking=True)
         with torch.cuda.device(self.dev):
-            key = bool(update_proposal)
+            key = (bool(update_proposal), bool(self.model.training))
             graphed = self.use_graph and self.eager_runs.get(key, 0) >= 1   # first step of each variant runs eagerly (warm-up)
             if not graphed:
                 self.eager_runs[key] = self.eager_runs.get(key, 0) + 1
@@ -396,7 +409,7 @@ class FusedRGBStep:
                 gf.replay()
                 main.wait_stream(upd)
                 gb.replay()
-                self._update_rest()
+                self._update_rest(update_proposal)
             self.pending_main = True
         return self.loss[0]
 
@@ -444,7 +457,7 @@ class FusedRGBFrame(FusedRGBStep):
         self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)
         self.image = torch.empty(N, 3, **f32)
         self.loss = torch.zeros(1, **f32)
-        self.graph = None
+        self.graph = {}                                    # model.training -> captured forward (aabb_train / aabb_infer)
         self.eager_runs = 0
 
     def _launch_render(self):
@@ -482,11 +495,12 @@ class FusedRGBFrame(FusedRGBStep):
         self.rays_d.copy_(rays_d, non_blocking=True)
         with torch.cuda.device(self.dev):
             if self.use_graph and self.eager_runs >= 1:
-                if self.graph is None:
-                    self.graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self.graph):
+                mode = bool(self.model.training)
+                if mode not in self.graph:
+                    self.graph[mode] = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph[mode]):
                         self._launch_render()
-                self.graph.replay()
+                self.graph[mode].replay()
             else:
                 self.eager_runs += 1
                 self._launch_render()
@@ -536,7 +550,7 @@ class FusedSAMStep:
         self.critical_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_CRIT_PRIO", -1)))
         self.pending_main = False
         self.sharded_update = True
-        self.graphs = None
+        self.graphs = {}                                   # model.training -> captured step
         self.eager_runs = 0
         self.last_f = None
         a, b = self._main_range()
@@ -616,16 +630,16 @@ class FusedSAMStep:
         a, b = self._main_range()
         opt = self.optimizer
         if self.world_size == 1:
-            opt.apply(a, b, grad_scale=1.0, zero_grad=True)
+            opt.apply(a, b, grad_scale=1.0, zero_grad=True, gated=True)
             return
         world, rank = self.world_size, dist.get_rank()
         if not self.sharded_update:
             dist.all_reduce(opt.flat_grad[a:b], op=dist.ReduceOp.SUM)
-            opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True)
+            opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True, gated=True)
             return
         from .parallel import sharded_update
         sharded_update(opt.flat_param, opt.flat_grad, a, b,
-                       lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True), world, rank)
+                       lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True, gated=True), world, rank)
 
     def _update_rest(self):
         b, n = self._main_range()[1], self.optimizer.flat_param.numel()
@@ -634,9 +648,13 @@ class FusedSAMStep:
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
 
     def flush(self):
+        """Apply a pending deferred table update now (checkpoint, evaluation, tests, switching plans).  The device-side
+        gate is cleared afterwards, so the deferred pass at the start of the next step (baked into its CUDA graph) is a
+        no-op instead of a momentum-only update on a zero gradient."""
         if self.pending_main:
             with torch.cuda.device(self.dev):
                 self._update_main()
+                self.optimizer.clear_gate()
             self.pending_main = False
 
     def _deferred_update(self):
@@ -677,24 +695,26 @@ class FusedSAMStep:
                 self.eager_runs += 1
                 self._whole_step()
             elif self.world_size == 1:
-                if self.graphs is None:
+                mode = bool(self.model.training)
+                if mode not in self.graphs:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         self._whole_step()
-                    self.graphs = (g,)
-                self.graphs[0].replay()
+                    self.graphs[mode] = (g,)
+                self.graphs[mode][0].replay()
             else:
-                if self.graphs is None:
+                mode = bool(self.model.training)
+                if mode not in self.graphs:
                     gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gf):
                         _critical(self, self._launch_front)
                     with torch.cuda.graph(gb):
                         _critical(self, self._launch_back)
-                    self.graphs = (gf, gb)
+                    self.graphs[mode] = (gf, gb)
                 main, upd = self._deferred_update()
-                self.graphs[0].replay()
+                self.graphs[mode][0].replay()
                 main.wait_stream(upd)
-                self.graphs[1].replay()
+                self.graphs[mode][1].replay()
                 self._update_rest()
             self.pending_main = True
         return self.loss[0]

@@ -33,16 +33,19 @@ def default_opt(**overrides):
 class RGBTrainer:
     """Stage-1 step: ``step(rays_o, rays_d, gt_rgb) -> loss`` (device tensors), with optional DDP-style sharding."""
 
-    def __init__(self, model, lr=1e-2, iters=20000, world_size=1, fused_step=True, use_graph=True):
+    def __init__(self, model, lr=1e-2, iters=20000, world_size=1, fused_step=True, use_graph=True, ema_decay=None):
         self.model = model.train()
         self.world_size = world_size
         self.global_step = 0
         self.fused_step, self.use_graph = bool(fused_step), bool(use_graph)
         self._plans = {}                                  # ray count -> FusedRGBStep (static buffers + CUDA graphs)
+        self._checked_counts = set()
         params = [p for p in model.parameters() if p.requires_grad]
         # Adam(eps=1e-15) + LambdaLR 0.1**min(iter/iters,1)  (main.py:296,312-313) on flat buffers; the flat
-        # gradient doubles as the all-reduce bucket and is cleared by the optimizer kernel
-        self.optimizer = FusedAdam(params, lr=lr, eps=1e-15, decay_iters=iters)
+        # gradient doubles as the all-reduce bucket and is cleared by the optimizer kernel; ema_decay=0.95 is what the
+        # reference's Trainer is built with (main.py:316)
+        self.optimizer = FusedAdam(params, lr=lr, eps=1e-15, decay_iters=iters, ema_decay=ema_decay)
+        self._prop_range = self.optimizer.range_of([*model.prop_encoders.parameters(), *model.prop_mlp.parameters()])
 
     def loss(self, rays_o, rays_d, gt_rgb, update_proposal=True, perturb=True):
         out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=perturb,
@@ -76,6 +79,7 @@ class RGBTrainer:
                 plan.flush()
 
     def step(self, rays_o, rays_d, gt_rgb):
+        _check_equal_shards(self, rays_o.shape[0])
         plan = self.plan(rays_o.shape[0])
         for other in self._plans.values():                # a pending update of another ray count's plan comes first
             if other is not None and other is not plan:
@@ -91,31 +95,52 @@ class RGBTrainer:
         rays_o, rays_d, gt_rgb = (t.to(dev, non_blocking=True) for t in (rays_o, rays_d, gt_rgb))
         loss, _ = self.loss(rays_o, rays_d, gt_rgb, update_proposal)
         loss.backward()                                   # accumulates into the (pre-zeroed) flat gradient
+        # steps that do not train the proposal networks leave their range out of the exchange and the update (the
+        # reference's Adam skips parameters whose .grad is None), see FusedRGBStep._update_rest
+        lo, hi = self._prop_range
+        stop = self.optimizer.flat_param.numel() if (update_proposal or hi != self.optimizer.flat_param.numel()) else lo
         if self.world_size > 1:
-            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
-        self.optimizer.step(grad_scale=1.0 / self.world_size, zero_grad=True)
+            dist.all_reduce(self.optimizer.flat_grad[:stop], op=dist.ReduceOp.SUM)
+        self.optimizer.schedule()
+        self.optimizer.apply(0, stop, grad_scale=1.0 / self.world_size, zero_grad=True)
         return loss.detach()
+
+
+def _check_equal_shards(trainer, n_rays):
+    """The data-parallel gradient is (sum of per-rank means) / world: the global-batch mean only when every rank
+    renders the same number of rays.  Checked once per ray count."""
+    if trainer.world_size == 1 or n_rays in trainer._checked_counts:
+        return
+    dev = trainer.optimizer.flat_param.device
+    t = torch.tensor([n_rays, -n_rays], device=dev, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if int(t[0]) != -int(t[1]):
+        raise RuntimeError(f"ray shards differ across ranks ({-int(t[1])}..{int(t[0])} rays): pad or drop rays so that "
+                           "every rank renders the same count (the gradient is averaged with equal rank weights)")
+    trainer._checked_counts.add(n_rays)
 
 
 class SAMTrainer:
     """Stage-2 step on frozen stage-1 parameters: render the [h,w] low-resolution rays' 256-d feature map and
     regress a target feature map (nerf/utils.py:1095-1106; the ViT-H target is replaced by a given tensor)."""
 
-    def __init__(self, model, lr=1e-2, iters=5000, world_size=1, use_graph=True, fused_step=True):
+    def __init__(self, model, lr=1e-2, iters=5000, world_size=1, use_graph=True, fused_step=True, ema_decay=None):
         assert model.opt.with_sam
         self.model = model.train()
         self.world_size = world_size
+        self._checked_counts = set()
         self.use_graph = bool(use_graph)
         self.fused_step = bool(fused_step)
         self._graphs = {}                                 # (n_rays, h, w, target shape) -> captured step
         self._plans = {}                                  # same key -> FusedSAMStep (hand-scheduled step) or None
-        trainable = set()
-        for m in (model.s_grid, model.samvit_mlp):
-            trainable.update(id(p) for p in m.parameters())
-        for p in model.parameters():                      # main.py:255-262: freeze what stage 1 trained
-            p.requires_grad_(id(p) in trainable)
+        if all(p.requires_grad for p in model.parameters()):
+            trainable = set()                             # no warm start applied: freeze what stage 1 trains, as
+            for m in (model.s_grid, model.samvit_mlp):    # checkpoint.warm_start (main.py:255-262) would from its keys
+                trainable.update(id(p) for p in m.parameters())
+            for p in model.parameters():
+                p.requires_grad_(id(p) in trainable)
         self.optimizer = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=lr, eps=1e-15,
-                                   decay_iters=iters)
+                                   decay_iters=iters, ema_decay=ema_decay)
 
     def _forward_backward(self, rays_o, rays_d, target, h, w):
         out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=False, update_proposal=False,
@@ -134,6 +159,7 @@ class SAMTrainer:
         per input shape it is captured into a CUDA graph and replayed (static input buffers), which removes the
         ~150 host-side launches that otherwise dominate this 4096-ray step."""
         dev = self.optimizer.flat_param.device
+        _check_equal_shards(self, rays_o.shape[0])
         key = (tuple(rays_o.shape), h, w, tuple(target.shape))
         plan = self.plan(rays_o.shape[0], h, w, tuple(target.shape))
         for other in self._plans.values():                # a pending table update of another shape's plan comes first
@@ -193,34 +219,47 @@ class SAMTrainer:
                 plan.flush()
 
 
-_FRAME_PLANS = {}
+_MAX_FRAME_PLANS = 4          # ray counts kept per model (static buffers + one CUDA graph each)
 
 
 @torch.no_grad()
 def render_frame(model, rays_o, rays_d, feat_rays_o=None, feat_rays_d=None, h=64, w=64, fused=True):
     """Interactive frame (nerf/utils.py:1647-1712): full-resolution RGB + depth, plus the low-resolution 256-d SAM
     feature map when feature rays are given.  The RGB pass is ONE CUDA-graph replay of the hand-scheduled forward
-    (``FusedRGBFrame``) when the model has the reference's shapes, else the staged renderer (renderer.py:185-219)."""
+    (``FusedRGBFrame``) when the model has the reference's shapes, else the staged renderer (renderer.py:185-219).
+    Runs in eval mode (aabb_infer, no jitter) and restores the caller's mode; the plans live on the model object
+    (least-recently-used bound), so they die with it."""
+    was_training = model.training
     model.eval()
-    plan = None
-    if fused and rays_o.is_cuda and getattr(model, "tc_head", False):
-        from .step import FusedRGBFrame, UnsupportedConfig
-        key = (id(model), rays_o.shape[0])
-        if key not in _FRAME_PLANS:
-            try:
-                _FRAME_PLANS[key] = FusedRGBFrame(model, rays_o.shape[0])
-            except UnsupportedConfig:
-                _FRAME_PLANS[key] = None
-        plan = _FRAME_PLANS[key]
-    if plan is not None:
-        out = plan(rays_o, rays_d)
-    else:
-        out = model.render(rays_o, rays_d, staged=True, bg_color=1, perturb=False)
-    res = {"image": out["image"], "depth": out["depth"]}
-    if feat_rays_o is not None:
-        f = model.render(feat_rays_o, feat_rays_d, staged=False, bg_color=1, perturb=False, return_feats=1, H=h, W=w)
-        res["samvit"] = f["samvit"]
-    return res
+    try:
+        plan = None
+        if fused and rays_o.is_cuda and getattr(model, "tc_head", False):
+            from .step import FusedRGBFrame, UnsupportedConfig
+            plans = model.__dict__.setdefault("_frame_plans", {})
+            key = int(rays_o.shape[0])
+            if key in plans:
+                plans[key] = plans.pop(key)                   # most recently used last
+            else:
+                try:
+                    plans[key] = FusedRGBFrame(model, key)
+                except UnsupportedConfig:
+                    plans[key] = None
+                while len(plans) > _MAX_FRAME_PLANS:
+                    plans.pop(next(iter(plans)))
+            plan = plans[key]
+        if plan is not None:
+            out = plan(rays_o, rays_d)
+        else:
+            out = model.render(rays_o, rays_d, staged=True, bg_color=1, perturb=False)
+        res = {"image": out["image"], "depth": out["depth"]}
+        if "n_alive" in out:
+            res["n_alive"] = out["n_alive"]
+        if feat_rays_o is not None:
+            f = model.render(feat_rays_o, feat_rays_d, staged=False, bg_color=1, perturb=False, return_feats=1, H=h, W=w)
+            res["samvit"] = f["samvit"]
+        return res
+    finally:
+        model.train(was_training)
 
 
 from .parallel import gather_frame, shard_rays  # noqa: E402,F401  (re-exported: sharding helpers live in parallel.py)

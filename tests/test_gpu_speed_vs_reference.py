@@ -101,6 +101,34 @@ def test_grid_encode_not_slower_than_reference_kernel(cuda, ref_ext, flush, name
         tp.grad = None
         state["y"].backward(grad, retain_graph=True)
 
+    # values first (BASELINE.json north_star): forward bit-exact in fp32 / 1e-2 in fp16 against the UNMODIFIED reference
+    # kernel at the full size; scatter 1e-4 relative (atomic order) in fp32 / 1e-2 in fp16
+    y_ref = _ref_forward(ext, x, table, enc.offsets, S, H)
+    g_ref = _ref_backward(ext, grad, x, table, enc.offsets, S, H)
+    ours_fwd()
+    ours_bwd()
+    y_our, g_our = state["y"].detach(), tp.grad.detach()
+    assert y_our.dtype == y_ref.dtype and g_our.dtype == g_ref.dtype
+    if dtype == torch.float32:
+        assert torch.equal(y_our, y_ref), f"{name}: forward differs from the reference kernel in " \
+                                          f"{int((y_our != y_ref).sum())} of {y_ref.numel()} values"
+        rel = ((g_our.double() - g_ref.double()).norm() / g_ref.double().norm()).item()
+        assert rel < 1e-4, f"{name}: scatter relative L2 error {rel:.3e}"
+        torch.testing.assert_close(g_our, g_ref, rtol=1e-4, atol=1e-4 * float(g_ref.abs().max()))
+    else:
+        torch.testing.assert_close(y_our.float(), y_ref.float(), rtol=1e-2, atol=1e-2 * float(y_ref.float().abs().max()))
+        # half-precision atomics round after every addition, in both implementations: measure each against the fp32
+        # scatter of the same gradient and require ours to be within 1e-2, or at least no worse than the reference's own
+        t32 = table.float().requires_grad_(True)
+        grid_encode(x, t32, enc.offsets, enc.per_level_scale, H, False, 0, False, 0, None).backward(grad.float())
+        exact = t32.grad.double()
+        rel = ((g_our.double() - exact).norm() / exact.norm()).item()
+        rel_ref = ((g_ref.double() - exact).norm() / exact.norm()).item()
+        _record(f"parity/{name}/reference_scatter_rel_l2", rel_ref)
+        assert rel < max(1e-2, 1.25 * rel_ref), f"{name}: fp16 scatter error {rel:.3e} (reference kernel: {rel_ref:.3e})"
+    _record(f"parity/{name}", {"B": B, "forward_bit_exact": bool(dtype == torch.float32), "scatter_rel_l2": rel})
+    tp.grad = None
+
     t_ref_f = _timeit(lambda: _ref_forward(ext, x, table, enc.offsets, S, H), flush)
     t_ref_b = _timeit(lambda: _ref_backward(ext, grad, x, table, enc.offsets, S, H), flush)
     t_our_f = _timeit(ours_fwd, flush)
@@ -154,7 +182,7 @@ def test_rgb_training_step_not_slower_than_reference_gpu_path(cuda, ref_ext, flu
 
     torch.manual_seed(0)
     ref = R.NeRFNetworkRef(grid_cls=_ref_grid_cls(ext)).to(cuda).train()
-    opt = torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)      # main.py:296
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2, eps=1e-15)      # main.py:296 (torch's default betas)
 
     def ref_step():
         opt.zero_grad(set_to_none=False)
