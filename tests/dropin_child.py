@@ -31,10 +31,20 @@ def main():
     ap.add_argument("--hw", type=int, default=16)
     args = ap.parse_args()
 
-    # the reference's packages come first; the shim directory only contributes _gridencoder / _shencoder / _freqencoder
-    # (+ the sanerf_b200 binding they call); its same-named mirrors (gridencoder/, nerf/, ...) are shadowed
-    sys.path[:0] = [REF_PY, PKG, ROOT]
     import torch
+
+    # From THIS repository the child takes only the three compiled-backend names (+ the sanerf_b200 ctypes binding they
+    # call): they are imported first, then the shim directory leaves the module path again, so that ``gridencoder``,
+    # ``shencoder``, ``freqencoder``, ``encoding``, ``activation`` and ``nerf`` can only be the reference's files.
+    sys.path.insert(0, PKG)
+    import _freqencoder  # noqa: F401
+    import _gridencoder  # noqa: F401
+    import _shencoder  # noqa: F401
+    sys.path.remove(PKG)
+    for name in [m for m in sys.modules if m.split(".")[0] in ("gridencoder", "shencoder", "freqencoder", "nerf",
+                                                               "encoding", "activation")]:
+        raise AssertionError(f"{name} imported too early")
+    sys.path[:0] = [REF_PY, ROOT]
 
     from oracle import build_ref
     from oracle import render_torch as R

@@ -53,7 +53,7 @@ def _assert_grads_vs_oracle(model, ref, names=None):
         got, exp = p.grad.detach().double(), ref_p[name].grad.detach().double()
         assert float(exp.abs().max()) > 0, name
         rel = ((got - exp).norm() / exp.norm()).item()
-        assert rel < (5e-3 if name.endswith("embeddings") else 2e-3), f"{name}: relative L2 error {rel:.3e}"
+        assert rel < (5e-3 if name.endswith("embeddings") else 3e-3), f"{name}: relative L2 error {rel:.3e}"
 
 
 def test_rgb_step_8192_rays_matches_autograd_and_oracle(cuda):
@@ -164,12 +164,14 @@ def test_deferred_update_is_idempotent_after_flush(cuda):
         if i % 2 == 0:
             ta.flush()                         # e.g. a checkpoint / evaluation between steps
     ta.flush(); tb.flush()
+    # (Adam with eps = 1e-15 amplifies atomic-order noise of near-zero gradients: 1.2e-3 measured after these six steps
+    # for two correct runs; a momentum-only pass moves every touched entry by ~lr = 1e-2, i.e. ||diff|| / ||table|| ~ 7e-2)
     for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
-        assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-4, n
-    # and the optimizer state: a spurious pass would have decayed exp_avg / exp_avg_sq of the main table
+        assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 5e-3, n
+    # and the optimizer state: a spurious pass would have decayed exp_avg of the main table by 0.9 per flush
     a, b = ta.optimizer.ranges[id(model_a.grid.embeddings)]
     ma, mb = ta.optimizer.exp_avg[a:b], tb.optimizer.exp_avg[a:b]
-    assert ((ma - mb).norm() / mb.norm()).item() < 1e-4
+    assert ((ma - mb).norm() / mb.norm()).item() < 2e-2
 
 
 def test_proposal_networks_do_not_move_without_gradient(cuda):

@@ -63,7 +63,7 @@ def test_fused_step_graph_replay_equals_eager(cuda):
         assert torch.isfinite(la)
         torch.testing.assert_close(la, lb, rtol=2e-4, atol=1e-6)
     pa.flush(); pb.flush()          # the main-table update of the last step is deferred to the next one
-    assert True in pa.graphs and int(ta.optimizer.step_count) == 4
+    assert (True, True) in pa.graphs and int(ta.optimizer.step_count) == 4
     for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
 
@@ -105,7 +105,7 @@ def test_fused_frame_equals_staged_render(cuda, with_sam):
         torch.testing.assert_close(out["image"], ref["image"], rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(out["depth"], ref["depth"], rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(out["weights_sum"], ref["weights_sum"], rtol=1e-5, atol=1e-6)
-    assert plan.graph is not None
+    assert False in plan.graph                 # captured in eval mode (aabb_infer)
     res = render_frame(model, o, d, o[:64] if with_sam else None, d[:64] if with_sam else None, 8, 8)
     torch.testing.assert_close(res["image"], ref["image"], rtol=1e-5, atol=1e-6)
     if with_sam:
@@ -222,6 +222,6 @@ def test_fused_sam_step_graph_replay_equals_autograd_steps(cuda):
         la, lb = ta.step(o, d, target, h, w).clone(), tb.step(o, d, target, h, w).clone()
         torch.testing.assert_close(la, lb, rtol=2e-4, atol=1e-6)
     ta.flush()
-    assert ta._plans[(h * w, h, w, tuple(target.shape))].graphs is not None
+    assert True in ta._plans[(h * w, h, w, tuple(target.shape))].graphs
     for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
