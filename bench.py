@@ -1,16 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the Segment-Anything-NeRF render hot path on B200 (contract: see the task statement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload rgb|sam|frame]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|rgb|sam|frame|cfg1|cfg5]
 
-One "step" of the default workload (BASELINE.json configs[1]) is one stage-1 RGB training step:
-8192 synthetic rays per GPU, 128/64/32 proposal/final samples (2^18 final samples), random-init tables of
-the reference's shapes, forward + backward + gradient all-reduce (N>1) + Adam.  `value` is whole-job
-rays/s with the rays already resident in HBM; `e2e` is the same step driven from pinned HOST buffers
-through the public API (H2D copy of rays + targets and D2H read of the loss inside the timed region).
+The headline line is BASELINE.json configs[1]: one stage-1 RGB training step = 8192 synthetic rays per GPU, 128/64/32
+proposal/final samples (2^18 final samples), random-init tables of the reference's shapes, forward + backward + gradient
+exchange (N>1) + Adam + EMA.  `value` is whole-job rays/s with the rays already resident in HBM; `e2e` is the same step
+driven from pinned HOST buffers through the public API (H2D copy of rays + targets and D2H read of the loss inside the timed
+region).  The same JSON line carries, under `workloads`, the other halves of BASELINE's metric measured in the same run:
 
-`--impl reference` times the reference's own algorithm for this path restated in pure torch
-(oracle/render_torch.py — the "pure-torch reference path" of BASELINE.json) on the box's host cores.
+  sam    configs[2]: stage-2 SAM feature-field step, 4096 rays (64x64) per GPU, [1,256,64,64] target (rays/s)
+  frame  configs[3]: 512x512 RGB + depth + 64x64x256 SAM feature map per frame (frames/s), rows sharded over the ranks;
+         with early ray termination (t_thresh 1e-4) beside the reference's behaviour (no termination)
+  cfg1   configs[0]: 4096 rays x 64 samples, main grid encode -> 64-wide MLP -> trunc_exp -> C=3 composite, fwd + bwd,
+         with the oracle (pure-torch reference path) on the host cores on the SAME shape beside it (N=1 only)
+  cfg5   configs[4]: T=2^22 fp16 table, 2^20 samples per GPU: encode / scatter / composite roofline fractions and the
+         whole step (gather -> composite -> scatter -> reduce-scatter + sharded Adam + all-gather)
+
+plus `gpu_reference` (N=1): the UNMODIFIED reference CUDA extensions (oracle/_ref) + the torch step of the reference on the
+same GPU in the same run — a reported baseline — and, for N>1, `grad_equiv`: N-rank averaged gradients against one rank
+on the concatenated batch.
+
+`--impl reference` times the reference's own algorithm for this path restated in pure torch (oracle/render_torch.py — the
+"pure-torch reference path" of BASELINE.json) on the box's host cores, on the same config (8192 rays per step).
 """
 from __future__ import annotations
 
@@ -21,7 +33,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,6 +47,16 @@ import torch  # noqa: E402
 METRIC = "train rays/s (RGB fwd+bwd+Adam step)"
 N_RAYS = 8192                     # steady-state rays per step: 2^18 points / 32 final samples
 NUM_STEPS = (128, 64, 32)
+EMA_DECAY = 0.95                  # main.py:316
+
+
+def rgb_config(world):
+    """The workload description both arms print verbatim (the driver compares them)."""
+    return {"workload": "configs[1]: stage-1 RGB training step, 8192 rays/GPU x (128,64,32) samples (2^18 final samples), "
+                        "L16 T2^19 F2 main grid + 2 L5 T2^17 proposal grids, fwd+bwd+grad exchange+Adam+EMA(0.95), "
+                        "random-init tables",
+            "rays_per_gpu_per_step": N_RAYS, "samples": list(NUM_STEPS), "optimizer": "Adam(eps=1e-15)+LambdaLR+EMA(0.95)",
+            "l2": "flushed (256 MiB write) between timed iterations", "parallelism": f"ray-sharded data parallel x{world}"}
 
 
 def load_peaks():
@@ -48,7 +69,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks/throttle reasons sampled every 100 ms while the timed regions run."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -64,7 +85,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                          "-lms", "100", "-i", str(self.gpu_index)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -73,7 +94,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -106,28 +127,43 @@ def synthetic_rays(n, device, seed):
     return o.to(device), d.to(device), rgb.to(device)
 
 
-# ----------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
-    """Reference arm: the pure-torch restatement of the reference path on the host cores (rank 0 only)."""
-    if rank != 0:
-        return
+# ============================================================================================== reference arm (CPU)
+def _oracle_rgb_step(n_rays, ema=True):
+    """The oracle's stage-1 step on the host cores: fwd + bwd + Adam (+ EMA), nerf/utils.py:897-930, 1811-1836, 1862."""
     from oracle import render_torch as R
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    n_rays = args.ref_rays
     model = R.NeRFNetworkRef().train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-2, eps=1e-15)
+    params = list(model.parameters())
+    shadow = [p.detach().clone() for p in params] if ema else None
     o, d, rgb = synthetic_rays(n_rays, "cpu", 1234)
+    t = [0]
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad(set_to_none=True)
         loss, _ = model.rgb_loss(o, d, rgb, update_proposal=True, perturb=True)
         loss.backward()
         opt.step()
-        return float(loss)
+        if shadow is not None:
+            t[0] += 1
+            decay = min(EMA_DECAY, (1 + t[0]) / (10 + t[0]))
+            with torch.no_grad():
+                torch._foreach_sub_(shadow, torch._foreach_mul(torch._foreach_sub(shadow, params), 1.0 - decay))
+        return loss.detach()
 
+    return step
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the pure-torch restatement of the reference path on the host cores (rank 0 only), on the SAME
+    config as our arm: 8192 rays per step."""
+    if rank != 0:
+        return
+    n_rays = args.ref_rays
+    step = _oracle_rgb_step(n_rays)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -135,14 +171,15 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     value = n_rays * args.steps / dt
-    sample = f"{n_rays} rays/step x {args.steps} steps of the same RGB training step (128/64/32 samples, same tables)"
+    sample = (f"{n_rays} rays/step x {args.steps} steps of the same RGB training step (oracle/render_torch.py on "
+              f"{torch.get_num_threads()} host threads, fp32, {dt:.1f} s of CPU work)")
+    config = rgb_config(world)
+    if n_rays != N_RAYS:
+        config["rays_per_gpu_per_step"] = n_rays
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "configs[1]: stage-1 RGB training step, 8192 rays x (128,64,32) samples, L16 T2^19 F2 "
-                               "main grid + 2 proposal grids, fwd+bwd+Adam", "rays_per_step": n_rays,
-                   "device": "cpu", "threads": torch.get_num_threads()},
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -152,23 +189,8 @@ def run_reference(args, rank, world):
 
 
 def cpu_baseline_sample(budget_s=20.0):
-    """Bounded sample of the same workload through the oracle port on the host cores (rank 0, N=1 only)."""
-    from oracle import render_torch as R
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    n_rays = 512
-    model = R.NeRFNetworkRef().train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-2, eps=1e-15)
-    o, d, rgb = synthetic_rays(n_rays, "cpu", 1234)
-
-    def step():
-        opt.zero_grad(set_to_none=False)
-        loss, _ = model.rgb_loss(o, d, rgb, update_proposal=True, perturb=True)
-        loss.backward()
-        opt.step()
-
+    """Bounded sample of the same workload (8192 rays per step) through the oracle port on the host cores."""
+    step = _oracle_rgb_step(N_RAYS)
     step()  # warm-up
     t0 = time.perf_counter()
     n = 0
@@ -176,90 +198,103 @@ def cpu_baseline_sample(budget_s=20.0):
         step()
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n_rays * n / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} steps x {n_rays} rays of the same RGB training step (oracle/render_torch.py, fp32, "
+    return {"value": N_RAYS * n / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps x {N_RAYS} rays of the same RGB training step (oracle/render_torch.py, fp32, "
                       f"{dt:.1f} s of CPU work)"}
 
 
-# ----------------------------------------------------------------------------------------------
-# dram__bytes_read.sum + dram__bytes_write.sum of one head_forward_kernel launch inside the training step
-# (ncu --set full, profiles/r1_head_forward_ncu.md); the 50 MB table is L2-resident, so this is far below the
-# algorithmic bytes
-HEAD_FWD_TRAFFIC = 236.4e6      # profiles/r1i_launch_summary.md (ncu --set full): 86.2 MB read + 150.2 MB written
+# ============================================================================================== our arm
+class Ctx:
+    """Per-process state shared by the workloads: device, ranks, the L2-flush buffer, timing helpers."""
+
+    def __init__(self, args, rank, world, local_rank):
+        self.args, self.rank, self.world = args, rank, world
+        self.dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, device=self.dev, dtype=torch.float32)   # > 126 MB L2
+        self.peak, self.peak_src = load_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, step_fn, n_steps, watch=None, pred=None):
+        """n_steps calls bracketed by barrier + synchronize; per-step CUDA events around each call (the L2 flush between
+        them is outside the events); returns (sum of step times in ms, MAX over ranks; launches counted; per-step ms)."""
+        from sanerf_b200 import _lib
+        evs = []
+        _lib.stats.reset(watch, pred)
+        self.barrier()
+        for i in range(n_steps):
+            self.flush.fill_(float(i))                                  # evict L2 between timed iterations
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step_fn(i)
+            e.record()
+            evs.append((s, e))
+        self.barrier()
+        per = [s.elapsed_time(e) for s, e in evs]
+        t = torch.tensor([sum(per)], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.stats.count, per
+
+    def roofline(self, alg_bytes, avg_ms, desc, traffic=None, **extra):
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "kernel": desc, "achieved": achieved, "peak": self.peak, "peak_source": self.peak_src,
+             "unit": "GB/s", "frac": achieved / self.peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+             "avg_launch_ms": avg_ms}
+        r.update(extra)
+        return r
 
 
-def algorithmic_bytes_encode(B, L, C, D=3, table_bytes=4, out_bytes=4):
-    """per sample 4*D + L*2^D*C*s_p + L*C*s_o."""
-    return B * (4 * D + L * (1 << D) * C * table_bytes + L * C * out_bytes)
+def _span_table(spans):
+    """[(entry name, launch info, count, mean ms)] from LaunchStats spans, one row per distinct (name, info)."""
+    acc = {}
+    for ms, info in spans:
+        key = (info["name"], tuple(sorted((k, v) for k, v in info.items() if k != "name")))
+        c, s = acc.get(key, (0, 0.0))
+        acc[key] = (c + 1, s + ms)
+    return [(name, dict(kv), c, s / c) for (name, kv), (c, s) in acc.items()]
 
 
-# name -> (C-ABI entry watched, predicate on the launch info, algorithmic bytes per launch (SURVEY §8 d4), description,
-#          DRAM traffic per launch from the committed `ncu --set full` capture (profiles/), or None)
+def _span_ms(table, name, **match):
+    for nm, info, _, ms in table:
+        if nm == name and all(info.get(k) == v for k, v in match.items()):
+            return ms
+    return None
+
+
 B_FINAL = N_RAYS * NUM_STEPS[2]
-ROOFLINE_KERNELS = {
-    "head_forward": ("field_head_forward", lambda i: i.get("B") == B_FINAL,
-                     B_FINAL * (12 + 16 * 8 * 8 + 64 + 640),
-                     "head_forward_kernel (final level: hash-grid gather L16 F2 T2^19 + 32-64-64-16 MLP on tcgen05, "
-                     "B=262144): 12 B in + 1024 B gathered + 64 B out + 640 B saved activations per sample",
-                     HEAD_FWD_TRAFFIC),
-    "head_backward": ("field_head_backward", lambda i: i.get("B") == B_FINAL, B_FINAL * (640 + 64 + 128),
-                      "head_backward_kernel (MLP data + weight gradients on tcgen05, B=262144): 640 B saved activations "
-                      "+ 64 B in + 128 B out per sample", None),
-    "main_backward": ("grid_encode_backward", lambda i: i.get("L") == 16 and i.get("B") == B_FINAL,
-                      algorithmic_bytes_encode(B_FINAL, 16, 2),
-                      "grid_backward_kernel<float,3,2,4,2> (main grid L16 F2 T2^19, B=262144): 1164 B/sample", None),
-    "prop0_forward": ("prop_density_forward", lambda i: i.get("B") == N_RAYS * NUM_STEPS[0],
-                      N_RAYS * NUM_STEPS[0] * (12 + 5 * 8 * 8 + 4 + 40),
-                      "prop_forward_kernel<5> (proposal level 0: encode L5 F2 + MLP + trunc_exp fused, B=1048576): "
-                      "12 B in + 320 B gathered + 4 B out + 40 B saved per sample", None),
-    "prop0_backward": ("prop_density_backward", lambda i: i.get("B") == N_RAYS * NUM_STEPS[0],
-                       N_RAYS * NUM_STEPS[0] * (12 + 4 + 40 + 5 * 8 * 8),
-                       "prop_backward_kernel<5> (proposal level 0 backward: MLP recompute + warp-aggregated scatter, "
-                       "B=1048576): 56 B in + 320 B reduced per sample", None),
-}
+# ncu --set full of one head_forward_kernel launch inside the training step (profiles/): dram__bytes_read.sum +
+# dram__bytes_write.sum, and lts__t_bytes.sum (L2 traffic); the 50 MB table is L2-resident, so DRAM is far below the
+# algorithmic bytes
+HEAD_FWD_NCU = {"dram_bytes": 236.4e6, "lts_bytes": None, "source": "profiles/r1i_launch_summary.md"}
+_ncu_path = os.path.join(ROOT, "profiles", "r2_head_forward_ncu.json")
+if os.path.exists(_ncu_path):
+    with open(_ncu_path) as _f:
+        HEAD_FWD_NCU = json.load(_f)
 
 
-def run_ours(args, rank, world, local_rank):
+def bench_rgb(ctx):
+    """configs[1] — the headline line."""
     import torch.distributed as dist
 
     from nerf.network import NeRFNetwork
     from sanerf_b200 import _lib
     from sanerf_b200.train import RGBTrainer, default_opt
 
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    _lib.load()
+    args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
     torch.manual_seed(0)                      # identical replicas on every rank
     model = NeRFNetwork(default_opt()).to(dev)
-    trainer = RGBTrainer(model, lr=1e-2, iters=20000, world_size=world)
+    trainer = RGBTrainer(model, lr=1e-2, iters=20000, world_size=world, ema_decay=EMA_DECAY)
 
     n_sets = 4                                 # rotate over a few synthetic ray batches
     dev_sets = [synthetic_rays(N_RAYS, dev, 1234 + rank * 100 + i) for i in range(n_sets)]
     host_sets = [tuple(t.cpu().pin_memory() for t in s) for s in dev_sets]
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)   # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed_loop(step_fn, n_steps, watch=None, pred=None):
-        evs = []
-        _lib.stats.reset(watch, pred)
-        barrier()
-        for i in range(n_steps):
-            flush.fill_(float(i))                                  # evict L2 between timed iterations
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            step_fn(i)
-            e.record()
-            evs.append((s, e))
-        barrier()
-        total_ms = sum(s.elapsed_time(e) for s, e in evs)
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _lib.stats.count
 
     def step_device(i):
         o, d, rgb = dev_sets[i % n_sets]
@@ -273,174 +308,202 @@ def run_ours(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step_device(i)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
-    total_ms, _ = timed_loop(step_device, args.steps)            # CUDA-graph replays: one launch per step on the host side
+    total_ms, _, per_step = ctx.timed(step_device, args.steps)    # CUDA-graph replays: one launch per step on the host side
     clocks = sampler.stop() if rank == 0 else {}
-    # dominant kernel of the step, picked from the ncu launch list (profiles/): see ROOFLINE_KERNELS.  Kernels inside a
-    # graph cannot be bracketed by events, so the SAME step is replayed eagerly (same buffers, same kernels, same L2
-    # flush) right after the timed region with CUDA events around the watched launches on the launching stream.
-    watch_name, pred, alg_bytes, watch_desc, traffic = ROOFLINE_KERNELS[args.roofline_kernel]
-    plan = trainer.plan(N_RAYS)
-    if plan is not None:
-        plan.use_graph = False
-    _, launches_eager = timed_loop(step_device, max(3, min(args.steps, 10)), watch_name, pred)
-    n_eager = max(3, min(args.steps, 10))
-    launches = (launches_eager // n_eager) * args.steps          # C-ABI kernels per step x timed steps
-    if plan is not None:
-        plan.use_graph = True
-    spans = _lib.stats.durations_ms()
     if args.no_e2e:
         e2e_ms = float("nan")
     else:
         for i in range(min(3, args.warmup)):
             step_e2e(i)
-        e2e_ms, _ = timed_loop(step_e2e, args.steps)
+        e2e_ms, _, _ = ctx.timed(step_e2e, args.steps)
+    # Per-kernel times: kernels inside a graph cannot be bracketed by events, so the SAME step is replayed eagerly (same
+    # buffers, same kernels, same L2 flush) right after the timed region with CUDA events around every C-ABI launch on
+    # its launching stream.
+    plan = trainer.plan(N_RAYS)
+    n_eager = max(3, min(args.steps, 10))
+    if plan is not None:
+        plan.use_graph = False
+    _, launches_eager, _ = ctx.timed(step_device, n_eager, "*", None)
+    if plan is not None:
+        plan.use_graph = True
+    table = _span_table(_lib.stats.durations_ms())
+    launches = (launches_eager // n_eager) * args.steps           # C-ABI kernels per step x timed steps
 
-    if rank != 0:
-        return
-    ms_per_step = total_ms / args.steps
-    value = world * N_RAYS * args.steps / (total_ms / 1e3)
-    e2e_value = world * N_RAYS * args.steps / (e2e_ms / 1e3)
-    peak, peak_src = load_peaks()
-    roofline = None
-    if spans:
-        alg = alg_bytes
-        avg_ms = sum(ms for ms, _ in spans) / len(spans)
-        achieved = alg / (avg_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": watch_desc,
-                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
-                    "avg_launch_ms": avg_ms, "launches_timed": len(spans),
-                    "timing": "CUDA events around the kernel's launches in an eager replay of the same step after the "
-                              "timed region (the timed region itself replays a CUDA graph)"}
+    kernels = {}
+    saved = 640                                # bytes/sample head_forward keeps for the backward (enc 128 + h1 256 + h2 256)
+    specs = {
+        # name: (entry, match, strict algorithmic bytes per launch (unfused inputs/outputs only), extra bytes)
+        "head_forward": ("field_head_forward", dict(B=B_FINAL), B_FINAL * (12 + 1024 + 64), B_FINAL * saved),
+        "head_backward": ("field_head_backward", dict(B=B_FINAL), B_FINAL * (64 + 128), B_FINAL * saved),
+        "main_scatter": ("grid_encode_backward", dict(B=B_FINAL, L=16), B_FINAL * (12 + 128 + 1024), 0),
+        "prop0_forward": ("prop_density_forward", dict(B=N_RAYS * NUM_STEPS[0]), N_RAYS * NUM_STEPS[0] * (12 + 320 + 4),
+                          N_RAYS * NUM_STEPS[0] * 40),
+        "prop0_backward": ("prop_density_backward", dict(B=N_RAYS * NUM_STEPS[0]), N_RAYS * NUM_STEPS[0] * (12 + 4 + 320),
+                           N_RAYS * NUM_STEPS[0] * 40),
+        "prop1_forward": ("prop_density_forward", dict(B=N_RAYS * NUM_STEPS[1]), N_RAYS * NUM_STEPS[1] * (12 + 320 + 4),
+                          N_RAYS * NUM_STEPS[1] * 40),
+        "head_composite_forward": ("head_composite_forward", dict(N=N_RAYS), N_RAYS * (32 * (64 + 8) + 4 * 18), 0),
+        "head_composite_backward": ("head_composite_backward", dict(N=N_RAYS), N_RAYS * (32 * (64 + 8 + 64) + 4 * 18), 0),
+    }
+    for name, (entry, match, strict, extra) in specs.items():
+        ms = _span_ms(table, entry, **match)
+        if ms:
+            kernels[name] = {"avg_ms": ms, "frac_strict": strict / (ms * 1e-3) / 1e9 / ctx.peak,
+                             "frac_with_saved": (strict + extra) / (ms * 1e-3) / 1e9 / ctx.peak}
+
     line = {
-        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "configs[1]: stage-1 RGB training step, 8192 rays/GPU x (128,64,32) samples "
-                               "(2^18 final samples), L16 T2^19 F2 main grid + 2 L5 T2^17 proposal grids, "
-                               "fwd+bwd+grad all-reduce+Adam, random-init tables",
-                   "rays_per_gpu_per_step": N_RAYS, "l2": "flushed (256 MiB write) between timed iterations",
-                   "execution": "hand-scheduled step replayed as one CUDA graph per step" if plan is not None else "autograd",
-                   "parallelism": f"ray-sharded data parallel x{world}"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
+        "metric": METRIC, "value": world * N_RAYS * args.steps / (total_ms / 1e3), "unit": "rays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": rgb_config(world),
+        "execution": ("hand-scheduled step replayed as one CUDA graph per step" if plan is not None else "autograd"),
+        "ms_per_step_median": statistics.median(per_step), "clocks": clocks,
+        "e2e": {"value": world * N_RAYS * args.steps / (e2e_ms / 1e3), "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": 3 * N_RAYS * 3 * 4, "d2h_bytes_per_step": 4, "last_loss": last_loss[0]},
         "gpu_launches": launches,
-        "roofline": roofline,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample()
-    print(json.dumps(line), flush=True)
+    hf = kernels.get("head_forward")
+    if hf:
+        strict = specs["head_forward"][2]
+        line["roofline"] = ctx.roofline(
+            strict, hf["avg_ms"],
+            "head_forward_kernel (final level: hash-grid gather L16 F2 T2^19 + 32-64-64-16 MLP on tcgen05, B=262144), "
+            "graded on its unfused algorithmic inputs/outputs only (SURVEY §8 d4): 12 B in + 1024 B gathered + 64 B out "
+            "per sample", traffic=HEAD_FWD_NCU.get("dram_bytes"),
+            frac_strict=hf["frac_strict"], frac_with_saved_activations=hf["frac_with_saved"],
+            saved_bytes_per_sample=saved, lts_bytes=HEAD_FWD_NCU.get("lts_bytes"), ncu_source=HEAD_FWD_NCU.get("source"),
+            launches_timed=n_eager,
+            timing="CUDA events around the kernel's launches in an eager replay of the same step after the timed region "
+                   "(the timed region itself replays a CUDA graph)")
+    line["kernels"] = kernels
+    trainer.flush()
+    return line, trainer, dev_sets
 
 
-def _timed(step_fn, n_steps, dev, world, flush):
+def grad_equiv(ctx, trainer, dev_sets):
+    """N ranks, each on its own 8192 rays, gradients summed over NVLink and divided by N  ==  ONE rank on the
+    concatenated N x 8192 rays (SURVEY §4 tier iv).  No jitter; max over parameter tensors of the relative L2 error."""
     import torch.distributed as dist
-    evs = []
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    for i in range(n_steps):
-        flush.fill_(float(i))                                      # evict L2 between timed iterations
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(); step_fn(i); e.record()
-        evs.append((s, e))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+
+    from sanerf_b200.step import FusedRGBStep
+    world, dev = ctx.world, ctx.dev
+    trainer.flush()
+    opt = trainer.optimizer
+    opt.zero_grad()
+    plan = trainer.plan(N_RAYS)
+    perturb, plan.perturb = plan.perturb, False
+    o, d, rgb = dev_sets[0]
+    plan.gradients_only(o, d, rgb, update_proposal=True)
+    multi = opt.flat_grad.clone()
+    dist.all_reduce(multi, op=dist.ReduceOp.SUM)
+    multi /= world
+    plan.perturb = perturb
+    opt.zero_grad()
+    # the concatenated batch on this rank alone
+    parts = [[torch.empty_like(t) for _ in range(world)] for t in (o, d, rgb)]
+    for lst, t in zip(parts, (o, d, rgb)):
+        dist.all_gather(lst, t.contiguous())
+    O, D, RGB = (torch.cat(lst, 0) for lst in parts)
+    big = FusedRGBStep(trainer.model, opt, world * N_RAYS, world_size=1, use_graph=False, perturb=False)
+    big.gradients_only(O, D, RGB, update_proposal=True)
+    single = opt.flat_grad.clone()
+    opt.zero_grad()
+    del big
+    worst, per = 0.0, {}
+    for name, p in trainer.model.named_parameters():
+        if not p.requires_grad:
+            continue
+        a, _ = opt.ranges[id(p)]
+        n = p.numel()
+        rel = ((multi[a:a + n].double() - single[a:a + n].double()).norm() / single[a:a + n].double().norm().clamp_min(1e-30)).item()
+        per[name] = rel
+        worst = max(worst, rel)
+    t = torch.tensor([worst], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"max_rel_l2": float(t.item()), "tol": 1e-4, "ok": bool(float(t.item()) <= 1e-4), "ranks": world,
+            "rays_per_rank": N_RAYS, "what": "N-rank all-reduced mean gradient vs one rank on the concatenated batch, per "
+                                             "parameter tensor, no jitter", "per_tensor": per}
 
 
-def run_sam(args, rank, world, local_rank):
+def bench_sam(ctx):
     """configs[2]: stage-2 SAM feature-field training step, 4096 rays (64x64) per GPU, synthetic [1,256,64,64] target."""
     from nerf.network import NeRFNetwork
     from sanerf_b200 import _lib
     from sanerf_b200.train import SAMTrainer, default_opt
 
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    _lib.load()
+    args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
     torch.manual_seed(0)
     model = NeRFNetwork(default_opt(with_sam=True)).to(dev)
-    trainer = SAMTrainer(model, world_size=world)
+    trainer = SAMTrainer(model, world_size=world, ema_decay=EMA_DECAY)
     n = 4096
     sets = [synthetic_rays(n, dev, 1234 + rank * 100 + i)[:2] for i in range(4)]
     g = torch.Generator(device="cpu").manual_seed(7 + rank)
     target = torch.randn(1, 256, 64, 64, generator=g)
     host = [tuple(t.cpu().pin_memory() for t in s) for s in sets]
     target_dev, target_host = target.to(dev), target.pin_memory()
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
     last = [0.0]
     for i in range(args.warmup):
         trainer.step(*sets[i % 4], target_dev, 64, 64)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms = _timed(lambda i: trainer.step(*sets[i % 4], target_dev, 64, 64), args.steps, dev, world, flush)
+    ms, _, per = ctx.timed(lambda i: trainer.step(*sets[i % 4], target_dev, 64, 64), args.steps)
 
     def e2e(i):
         last[0] = trainer.step(*host[i % 4], target_host, 64, 64).item()
-    e2e_ms = _timed(e2e, args.steps, dev, world, flush)
-    clocks = sampler.stop() if rank == 0 else {}
-    # roofline of the dominant kernel (profiles/r1i_sam_step.md: the s_grid scatter): the same step replayed eagerly
-    # with CUDA events around its launches, as in run_ours
+    e2e_ms, _, _ = ctx.timed(e2e, args.steps)
     plan = trainer.plan(n, 64, 64, tuple(target.shape))
-    roofline, launches = None, None
+    roofline, launches, kernels = None, None, {}
     if plan is not None:
         trainer.flush()
         plan.use_graph = False
         n_eager = max(3, min(args.steps, 10))
-        _lib.stats.reset("ray_features_backward", None)
-        _timed(lambda i: trainer.step(*sets[i % 4], target_dev, 64, 64), n_eager, dev, world, flush)
-        launches = (_lib.stats.count // n_eager) * args.steps
-        spans = [ms_ for ms_, _ in _lib.stats.durations_ms()]
+        _, cnt, _ = ctx.timed(lambda i: trainer.step(*sets[i % 4], target_dev, 64, 64), n_eager, "*", None)
+        launches = (cnt // n_eager) * args.steps
         plan.use_graph = True
-        if spans:
-            peak, peak_src = load_peaks()
-            alg = n * 32 * (16 + 16 * 8 * 8 * 4) + n * 128 * 4
-            avg = sum(spans) / len(spans)
-            roofline = {"bound": "hbm", "kernel": "ray_features_backward_kernel<8> (s_grid L16 F8 T2^19 scatter with the factorised "
-                        "gradient w_i * g_ray, 4096 rays x 32 samples): 16 B in + 4096 B of reductions per sample + 512 B per ray",
-                        "achieved": alg / avg / 1e6, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                        "frac": alg / avg / 1e6 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
-                        "avg_launch_ms": avg, "launches_timed": len(spans)}
-    if rank != 0:
-        return
-    print(json.dumps({
+        table = _span_table(_lib.stats.durations_ms())
+        alg = n * 32 * (16 + 16 * 8 * 8 * 4) + n * 128 * 4
+        for nm in ("ray_features_backward", "ray_features_forward"):
+            t = _span_ms(table, nm)
+            if t:
+                kernels[nm] = {"avg_ms": t, "frac_strict": alg / (t * 1e-3) / 1e9 / ctx.peak}
+        if "ray_features_backward" in kernels:
+            roofline = ctx.roofline(alg, kernels["ray_features_backward"]["avg_ms"],
+                                    "ray_features_backward_kernel<8> (s_grid L16 F8 T2^19 scatter with the factorised "
+                                    "gradient w_i * g_ray, 4096 rays x 32 samples): 16 B in + 4096 B of reductions per sample "
+                                    "+ 512 B per ray", launches_timed=n_eager)
+        trainer.flush()
+    return {
         "metric": "train rays/s (SAM feature fwd+bwd+Adam step)", "value": world * n * args.steps / (ms / 1e3), "unit": "rays/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "ms_per_step_median": statistics.median(per),
+        "higher_is_better": True, "scaling": "weak", "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "configs[2]: stage-2 SAM feature-field step, 4096 rays (64x64) per GPU x (128,64,32) samples, s_grid "
-                               "L16 F8 T2^19 + samvit_mlp (163->256x5, LayerNorm), frozen stage-1 field, [1,256,64,64] target",
-                   "execution": "hand-scheduled step (FusedSAMStep) replayed as one CUDA graph per step" if world == 1 else
-                                "hand-scheduled step: two CUDA graphs around the eager NCCL reduce-scatter / all-gather",
-                   "l2": "flushed between timed iterations",
-                   "parallelism": f"ray-sharded data parallel x{world}"},
-        "clocks": clocks,
+                               "L16 F8 T2^19 + samvit_mlp (163->256x5, LayerNorm), frozen stage-1 field, [1,256,64,64] target, "
+                               "Adam+EMA(0.95)",
+                   "l2": "flushed between timed iterations", "parallelism": f"ray-sharded data parallel x{world}"},
         "e2e": {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": 2 * n * 3 * 4 + 256 * 64 * 64 * 4, "d2h_bytes_per_step": 4, "last_loss": last[0]},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None}), flush=True)
+        "gpu_launches": launches, "roofline": roofline, "kernels": kernels}
 
 
-def run_frame(args, rank, world, local_rank):
-    """configs[3]: 512x512 RGB + depth + 64x64x256 SAM feature map; image rows are sharded over the ranks, one final gather."""
-    import numpy as np
+def bench_frame(ctx):
+    """configs[3]: 512x512 RGB + depth + 64x64x256 SAM feature map; image rows are sharded over the ranks, one final gather.
+    Measured without early termination (the reference never terminates: --T_thresh is declared, main.py:71-72, and never
+    read) and with t_thresh = 1e-4, with the truncation error of the latter against the former."""
     from nerf.network import NeRFNetwork
     from nerf.utils import get_rays
-    from sanerf_b200 import _lib
     from sanerf_b200.parallel import gather_frame, shard_rays
     from sanerf_b200.train import default_opt, render_frame
 
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    _lib.load()
+    args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
     torch.manual_seed(0)
     model = NeRFNetwork(default_opt(with_sam=True)).to(dev).eval()
+    with torch.no_grad():   # a field with structure (the +-1e-4 random init renders a uniform fog in which no ray terminates early)
+        for enc in (model.grid, *model.prop_encoders):
+            offs = enc.offsets.tolist()
+            for l in range(len(offs) - 1):
+                enc.embeddings[offs[l]:offs[l + 1]].uniform_(-1.0, 1.0)
+        for lin in (*model.grid_mlp.net, *[m for p in model.prop_mlp for m in p.net]):
+            lin.weight.mul_(2.0)
     H = W = 512
     intr = np.array([0.5 * H / np.tan(np.radians(30)), 0.5 * H / np.tan(np.radians(30)), W / 2, H / 2], dtype=np.float32)
     intr_f = intr / 8
@@ -450,45 +513,202 @@ def run_frame(args, rank, world, local_rank):
     fa, fb = shard_rays(64 * 64, rank, world)
     pix = torch.arange(a, b, device=dev)
     fpix = torch.arange(fa, fb, device=dev)
+    coords = torch.stack([pix // W, pix % W], -1)
+    fcoords = torch.stack([fpix // 64, fpix % 64], -1)
     img_host = torch.empty(H * W, 3).pin_memory()
     feat_host = torch.empty(64, 64, 256).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    keep = {}
 
     def frame(pose, copy_back):
         pose = pose.to(dev, non_blocking=True)
-        r = get_rays(pose, intr, H, W, b - a, coords=torch.stack([pix // W, pix % W], -1))
-        f = get_rays(pose, intr_f, 64, 64, fb - fa, coords=torch.stack([fpix // 64, fpix % 64], -1))
+        r = get_rays(pose, intr, H, W, b - a, coords=coords)
+        f = get_rays(pose, intr_f, 64, 64, fb - fa, coords=fcoords)
         out = render_frame(model, r["rays_o"], r["rays_d"], f["rays_o"], f["rays_d"], fb - fa, 1)
         image = gather_frame(out["image"], H * W, rank, world)
         feats = gather_frame(out["samvit"].reshape(fb - fa, 256), 64 * 64, rank, world)
+        keep["image"], keep["alive"] = image, out.get("n_alive")
         if copy_back and rank == 0:
             img_host.copy_(image, non_blocking=True)
             feat_host.copy_(feats.view(64, 64, 256), non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     pose_dev = pose_host.to(dev)
-    for _ in range(args.warmup):
-        frame(pose_dev, False)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms = _timed(lambda i: frame(pose_dev, False), args.steps, dev, world, flush)
-    e2e_ms = _timed(lambda i: frame(pose_host, True), args.steps, dev, world, flush)
-    clocks = sampler.stop() if rank == 0 else {}
-    if rank != 0:
-        return
-    print(json.dumps({
-        "metric": "512x512 RGB + 256-d SAM feature render FPS", "value": args.steps / (ms / 1e3), "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+    res = {}
+    for label, thresh in (("no_termination", 0.0), ("early_termination", 1e-4)):
+        model.t_thresh = thresh
+        model.__dict__.pop("_frame_plans", None)                      # the captured graphs bake the threshold in
+        for _ in range(max(3, args.warmup)):
+            frame(pose_dev, False)
+        ms, _, per = ctx.timed(lambda i: frame(pose_dev, False), args.steps)
+        e2e_ms, _, _ = ctx.timed(lambda i: frame(pose_host, True), args.steps)
+        res[label] = {"t_thresh": thresh, "fps": args.steps / (ms / 1e3), "ms_per_frame": ms / args.steps,
+                      "ms_per_frame_median": statistics.median(per), "e2e_fps": args.steps / (e2e_ms / 1e3),
+                      "e2e_ms_per_frame": e2e_ms / args.steps}
+        res[label]["_image"] = keep["image"].clone()
+        if keep.get("alive") is not None:
+            res[label]["mean_samples_alive_of_32"] = float(keep["alive"].float().mean().item())
+    err = (res["early_termination"].pop("_image") - res["no_termination"].pop("_image")).abs().max().item()
+    res["early_termination"]["max_abs_rgb_error_vs_no_termination"] = err
+    model.t_thresh = 0.0
+    base = res["no_termination"]
+    return {
+        "metric": "512x512 RGB + 256-d SAM feature render FPS", "value": base["fps"], "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
+        "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "configs[3]: 512x512 RGB + depth (262144 rays x (128,64,32) samples) + 64x64x256 SAM feature map, "
-                               "random-init field; pose -> rays -> render -> gather",
+                               "structured random field; pose -> rays -> render -> gather",
                    "execution": "hand-scheduled forward replayed as one CUDA graph + autograd-free feature pass",
                    "l2": "flushed between timed frames", "parallelism": f"image rows sharded x{world}, one final all_gather"},
-        "clocks": clocks,
-        "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
+        "e2e": {"value": base["e2e_fps"], "unit": "frames/s", "ms_per_step": base["e2e_ms_per_frame"],
                 "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 3 * 4 + 64 * 64 * 256 * 4},
-        "gpu_launches": None, "roofline": None, "cpu_baseline": None}), flush=True)
+        "no_termination": base, "early_termination": res["early_termination"]}
+
+
+def bench_cfg1(ctx):
+    """configs[0]: 4096 rays x 64 samples (B = 262,144), main grid L16 T2^19 F2 -> 64-wide MLP (32-64-64-16: density logit
+    + RGB + 12 spare) -> trunc_exp -> C = 3 composite, forward + backward to the table and the MLP; the oracle (pure-torch
+    reference path) runs the SAME shape on the host cores beside it."""
+    from activation import trunc_exp
+    from nerf.network import NeRFNetwork
+    from sanerf_b200 import fused
+    from sanerf_b200.ops import composite
+    from sanerf_b200.train import default_opt
+
+    args, dev = ctx.args, ctx.dev
+    N, T = 4096, 64
+    torch.manual_seed(0)
+    model = NeRFNetwork(default_opt()).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x01 = torch.rand(N, T, 3, generator=g)
+    bins = torch.sort(torch.rand(N, T + 1, generator=g), dim=-1).values * 4 + 0.2
+    target = torch.rand(N, 3, generator=g)
+    xd, bd, td = x01.to(dev), bins.to(dev), target.to(dev)
+    deltas, ts = (bd[:, 1:] - bd[:, :-1]).contiguous(), ((bd[:, 1:] + bd[:, :-1]) / 2).contiguous()
+    params = [model.grid.embeddings, *model.grid_mlp.parameters()]
+
+    def step(i):
+        for p in params:
+            p.grad = None
+        head = fused.field_head(xd, model.grid, model.grid_mlp)                       # [N,T,16] (tcgen05)
+        sigma = trunc_exp(head[..., 0])
+        out = composite(sigma, deltas, ts, head[..., 1:4], last_sample_opaque=True)[3]
+        loss = (out - td).square().mean()
+        loss.backward()
+        return loss
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    ms, _, per = ctx.timed(step, args.steps)
+    res = {"metric": "rays/s (encode + MLP + composite, fwd+bwd)", "value": N * args.steps / (ms / 1e3), "unit": "rays/s",
+           "ms_per_step": ms / args.steps, "ms_per_step_median": statistics.median(per),
+           "config": {"workload": "configs[0]: 4096 rays x 64 samples, hash grid L16 T2^19 F2, 64-wide MLP, RGB+density composite "
+                                  "fp32, fwd+bwd (autograd over the C-ABI operators)"}}
+    if ctx.world == 1 and not args.no_cpu_baseline:
+        from oracle import render_torch as R
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        ref = R.NeRFNetworkRef()
+        deltas_c, ts_c = bins[:, 1:] - bins[:, :-1], (bins[:, 1:] + bins[:, :-1]) / 2
+        rp = [ref.grid.embeddings, *ref.grid_mlp.parameters()]
+
+        def cpu_step():
+            for p in rp:
+                p.grad = None
+            h = ref.grid_mlp(ref.grid(x01 * 2 - 1, bound=1))
+            sigma = R.trunc_exp(h[..., 0])
+            out = R.composite(sigma, deltas_c, ts_c, h[..., 1:4])[3]
+            (out - target).square().mean().backward()
+
+        cpu_step()
+        t0, n = time.perf_counter(), 0
+        while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 20):
+            cpu_step(); n += 1
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": N * n / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{n} iterations of the SAME shape (4096 x 64) through oracle/render_torch.py, {dt:.1f} s"}
+    return res
+
+
+def bench_cfg5(ctx):
+    from sanerf_b200.large import LargeSceneStep
+    args = ctx.args
+    step = LargeSceneStep(ctx.dev, world_size=ctx.world, rank=ctx.rank)
+    for i in range(max(3, args.warmup)):
+        step(i)
+    ms, _, per = ctx.timed(step, args.steps)
+    B = step.B
+    kernels = step.kernel_times(ctx)                                       # eager replay with events per kernel
+    return {"metric": "samples/s (T=2^22 fp16 table: gather + composite + scatter + sharded Adam)",
+            "value": ctx.world * B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": ctx.world,
+            "ms_per_step": ms / args.steps, "ms_per_step_median": statistics.median(per), "scaling": "weak",
+            "config": {"workload": "configs[4]: hash table L16 F2 T2^22 fp16 (42.6 M rows, 170 MB), 2^20 samples per GPU "
+                                   "(8192 rays x 128), encode -> C=32 composite -> scatter -> reduce-scatter + sharded Adam "
+                                   "(fp32 master) + all-gather"},
+            "kernels": kernels}
+
+
+def bench_gpu_reference(ctx):
+    """REPORTED BASELINE, not the product: the rebuilt, unmodified reference CUDA extensions + the torch step of the
+    reference (autograd, cuBLAS nn.Linear, torch.optim.Adam, EMA) on the same GPU, same rays, same timing rules."""
+    from oracle import ref_gpu
+    try:
+        step = ref_gpu.reference_rgb_step(ctx.dev, ema_decay=EMA_DECAY)
+    except (FileNotFoundError, ImportError, OSError) as e:
+        return {"unavailable": str(e)[:200]}
+    sets = [synthetic_rays(N_RAYS, ctx.dev, 1234 + i) for i in range(4)]
+    for i in range(3):
+        step(*sets[i % 4])
+    n = max(5, min(ctx.args.steps, 10))
+    ms, _, per = ctx.timed(lambda i: step(*sets[i % 4]), n)
+    return {"value": N_RAYS * n / (ms / 1e3), "unit": "rays/s", "ms_per_step": ms / n, "steps": n,
+            "kind": "unmodified reference CUDA extensions rebuilt for sm_100 (oracle/_ref) + the reference's torch step "
+                    "(oracle/render_torch.py on the GPU: torch glue, cuBLAS MLPs, autograd, torch.optim.Adam, EMA)",
+            "config": rgb_config(1)["workload"]}
+
+
+def run_ours(args, rank, world, local_rank):
+    from sanerf_b200 import _lib
+    _lib.load()                                   # fails loudly when the CUDA library is missing: no fallback
+    ctx = Ctx(args, rank, world, local_rank)
+    which = args.workload
+    single = {"sam": bench_sam, "frame": bench_frame, "cfg1": bench_cfg1, "cfg5": bench_cfg5}
+    if which in single:                           # targeted runs (profiling): that workload's line alone
+        line = single[which](ctx)
+        line.setdefault("n_gpus", world); line.setdefault("steps", args.steps); line["warmup"] = args.warmup
+        line.setdefault("vs_baseline", None)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
+    line, trainer, dev_sets = bench_rgb(ctx)
+    if world > 1:
+        try:
+            line["grad_equiv"] = grad_equiv(ctx, trainer, dev_sets)
+        except Exception as e:  # noqa: BLE001
+            line["grad_equiv"] = {"error": repr(e)[:300]}
+    del trainer
+    torch.cuda.empty_cache()
+    if which == "all":
+        line["workloads"] = {}
+        order = [("sam", bench_sam), ("frame", bench_frame), ("cfg5", bench_cfg5)]
+        if world == 1:
+            order.insert(2, ("cfg1", bench_cfg1))
+        for name, fn in order:
+            try:
+                line["workloads"][name] = fn(ctx)
+            except Exception as e:  # noqa: BLE001   (a failing side workload must not lose the headline line)
+                line["workloads"][name] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+        if world == 1 and not args.no_gpu_reference:
+            try:
+                line["gpu_reference"] = bench_gpu_reference(ctx)
+                if "value" in line["gpu_reference"]:
+                    line["gpu_reference"]["speedup_of_ours"] = line["value"] / line["gpu_reference"]["value"]
+            except Exception as e:  # noqa: BLE001
+                line["gpu_reference"] = {"error": repr(e)[:300]}
+    if world == 1 and not args.no_cpu_baseline and rank == 0:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -497,12 +717,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--ref-rays", type=int, default=N_RAYS, help="rays per step of the CPU reference arm (default: same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
-    ap.add_argument("--roofline-kernel", default="head_forward", choices=sorted(ROOFLINE_KERNELS))
-    ap.add_argument("--workload", default="rgb", choices=["rgb", "sam", "frame"],
-                    help="rgb = BASELINE configs[1] (the headline); sam = configs[2]; frame = configs[3]")
+    ap.add_argument("--workload", default="all", choices=["all", "rgb", "sam", "frame", "cfg1", "cfg5"],
+                    help="all = the headline RGB line (configs[1]) carrying the other configs under 'workloads'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -517,7 +737,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        {"rgb": run_ours, "sam": run_sam, "frame": run_frame}[args.workload](args, rank, world, local_rank)
+        run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

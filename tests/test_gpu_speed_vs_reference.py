@@ -19,6 +19,9 @@ import torch
 from gridencoder import GridEncoder
 from gridencoder.grid import grid_encode
 from oracle import render_torch as R
+from oracle.ref_gpu import ref_backward as _ref_backward
+from oracle.ref_gpu import ref_forward as _ref_forward
+from oracle.ref_gpu import ref_grid_cls as _ref_grid_cls
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -50,25 +53,6 @@ def _timeit(fn, flush, n=10, warm=3):
 @pytest.fixture(scope="module")
 def flush(cuda):
     return torch.empty(256 * 1024 * 1024 // 4, device=cuda)
-
-
-def _ref_forward(ext, x, table, offsets, S, H):
-    """grid.py:27-69: [L,B,C] output, kernel, permute(1,0,2).reshape copy."""
-    B, D = x.shape
-    L, C = offsets.shape[0] - 1, table.shape[1]
-    out = torch.empty(L, B, C, device=x.device, dtype=table.dtype)
-    ext.grid_encode_forward(x, table, offsets, out, B, D, C, L, L, S, H, None, 0, False, 0)
-    return out.permute(1, 0, 2).reshape(B, L * C)
-
-
-def _ref_backward(ext, grad, x, table, offsets, S, H):
-    """grid.py:74-95: permuted contiguous gradient copy, zero-filled gradient table, scatter kernel."""
-    B, D = x.shape
-    L, C = offsets.shape[0] - 1, table.shape[1]
-    g = grad.view(B, L, C).permute(1, 0, 2).contiguous()
-    gt = torch.zeros_like(table)
-    ext.grid_encode_backward(g, x, table, offsets, gt, B, D, C, L, L, S, H, None, None, 0, False, 0)
-    return gt
 
 
 GRIDS = {
@@ -139,33 +123,6 @@ def test_grid_encode_not_slower_than_reference_kernel(cuda, ref_ext, flush, name
     # 10 % slack for run-to-run timing noise (the F = 8 scatter sits on the same L2 reduction bound in both implementations)
     assert t_our_f <= 1.1 * t_ref_f, (t_our_f, t_ref_f)
     assert t_our_b <= 1.1 * t_ref_b, (t_our_b, t_ref_b)
-
-
-class _RefGridFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, table, offsets, S, H, ext):
-        ctx.save_for_backward(x, table, offsets)
-        ctx.cfg = (S, H, ext)
-        return _ref_forward(ext, x, table, offsets, S, H)
-
-    @staticmethod
-    def backward(ctx, grad):
-        x, table, offsets = ctx.saved_tensors
-        S, H, ext = ctx.cfg
-        return None, _ref_backward(ext, grad.contiguous(), x, table, offsets, S, H), None, None, None, None
-
-
-def _ref_grid_cls(ext):
-    class RefExtGridEncoder(R.GridEncoderRef):
-        """GridEncoder of the reference (grid.py:102-168) on the rebuilt reference kernels."""
-
-        def forward(self, inputs, bound=1, max_level=None):
-            x = ((inputs + bound) / (2 * bound)).reshape(-1, self.input_dim).contiguous()
-            out = _RefGridFn.apply(x, self.embeddings, self.offsets, float(np.log2(self.per_level_scale)),
-                                   int(self.base_resolution), ext)
-            return out.view(list(inputs.shape[:-1]) + [self.output_dim])
-
-    return RefExtGridEncoder
 
 
 def test_rgb_training_step_not_slower_than_reference_gpu_path(cuda, ref_ext, flush):
