@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 18
+#define SANERF_ABI_VERSION 19
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -333,6 +333,13 @@ SANERF_API int sanerf_adam_schedule(int32_t* step, float* dyn, float lr0, float 
 SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint64_t n,
                      const float* dyn, float beta1, float beta2, float eps, float grad_scale,
                      int zero_grad, const int32_t* gate, float* ema, void* stream);
+/* Half-precision table with an fp32 master copy (BASELINE configs[4], T = 2^22 fp16 parameters; the reference reaches
+ * half tables through grid.py:43-46): grads16 [n] half (the scatter target / its reduce-scattered sum), master /
+ * exp_avg / exp_avg_sq [n] fp32; the updated parameters are written to master AND, rounded, to params16 in one pass.
+ * n % 8 == 0, 16-byte aligned buffers. */
+SANERF_API int sanerf_adam_step_half(float* master, void* params16, void* grads16, float* exp_avg, float* exp_avg_sq,
+                          uint64_t n, const float* dyn, float beta1, float beta2, float eps, float grad_scale,
+                          int zero_grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Field head on the tensor cores (tcgen05 / TMEM), fused with the hash-grid gather:

@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams 
     pdl_begin();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t level0 = blockIdx.y * G;
-    // fp32 tables with few values per cell: merge consecutive samples of a ray that share a cell before the
-    // reductions are issued (grid_common.cuh: warp_run_reduce).  Needs warp-uniform control flow: no early exits.
-    constexpr bool kAggregate = (sizeof(T) == 4) && ((1u << D) * CH <= 16u) && (CH == C);
+    // Tables with few values per cell: merge consecutive samples of a ray that share a cell before the reductions are
+    // issued (grid_common.cuh: warp_run_reduce; sums are kept in fp32 and, for half tables, rounded ONCE per run instead
+    // of once per sample).  Needs warp-uniform control flow: no early exits.  Without it the 4096 rows of level 0 take
+    // every sample's eight updates one by one: 360 us of the 977 us cfg5 scatter (T = 2^22 fp16, 2^20 samples).
+    constexpr bool kAggregate = ((1u << D) * CH <= 16u) && (CH == C);
     const uint32_t lane = threadIdx.x & 31u;
 
     float x[D];
@@ -92,12 +94,18 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams 
                         const uint32_t r0 = corner_row<D>(geo, cell, k), r1 = corner_row<D>(geo, cell, k + 1);
                         if ((r0 ^ r1) == 1u) {
                             const bool lo_first = r0 < r1;
-                            float* dst = reinterpret_cast<float*>(slice) + (size_t)(lo_first ? r0 : r1) * 2;
-                            red_add_v4_f32(dst, lo_first ? v[2 * k] : v[2 * k + 2], lo_first ? v[2 * k + 1] : v[2 * k + 3],
-                                           lo_first ? v[2 * k + 2] : v[2 * k], lo_first ? v[2 * k + 3] : v[2 * k + 1]);
+                            const float a0 = lo_first ? v[2 * k] : v[2 * k + 2], a1 = lo_first ? v[2 * k + 1] : v[2 * k + 3];
+                            const float b0 = lo_first ? v[2 * k + 2] : v[2 * k], b1 = lo_first ? v[2 * k + 3] : v[2 * k + 1];
+                            if constexpr (sizeof(T) == 4) {
+                                red_add_v4_f32(reinterpret_cast<float*>(slice) + (size_t)(lo_first ? r0 : r1) * 2, a0, a1, b0, b1);
+                            } else {                         // two 4-byte rows in one aligned 8-byte slot
+                                red_add_v2_f16x2(reinterpret_cast<__half*>(slice) + (size_t)(lo_first ? r0 : r1) * 2,
+                                                 __floats2half2_rn(a0, a1), __floats2half2_rn(b0, b1));
+                            }
                         } else {
-                            red_add_v2_f32(reinterpret_cast<float*>(slice) + (size_t)r0 * 2, v[2 * k], v[2 * k + 1]);
-                            red_add_v2_f32(reinterpret_cast<float*>(slice) + (size_t)r1 * 2, v[2 * k + 2], v[2 * k + 3]);
+                            float u0[2] = {v[2 * k], v[2 * k + 1]}, u1[2] = {v[2 * k + 2], v[2 * k + 3]};
+                            RowIO<T, 2>::red(slice + (size_t)r0 * 2, u0);
+                            RowIO<T, 2>::red(slice + (size_t)r1 * 2, u1);
                         }
                     }
                 } else {

@@ -224,6 +224,57 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
     }
 }
 
+// Adam for a HALF-precision table with an fp32 master copy (BASELINE configs[4]: T = 2^22 fp16 parameters): the gradient
+// arrives in half (the scatter's red.global.add.f16x2 target, or the reduce-scattered sum of them), the moments and the
+// master parameters stay fp32, and the half table the gather kernels read is rewritten in the same pass.  8 elements per
+// thread and trip: one 16-byte access per half array, two per fp32 array.
+__global__ void __launch_bounds__(256) adam_step_half_kernel(float* __restrict__ p, __half* __restrict__ p16, __half* __restrict__ g16,
+                                                             float* __restrict__ m, float* __restrict__ v, size_t n8,
+                                                             const float* __restrict__ dyn, float beta1, float beta2, float eps,
+                                                             float grad_scale, int zero_grad) {
+    pdl_begin();
+    const float lr = __ldg(dyn), bc1 = __ldg(dyn + 1), bc2 = __ldg(dyn + 2);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        uint4 graw = __ldcs(reinterpret_cast<const uint4*>(g16) + i);
+        const __half2* gh = reinterpret_cast<const __half2*>(&graw);
+        float4 pp[2], mm[2], vv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            pp[h] = __ldcs(reinterpret_cast<float4*>(p) + 2 * i + h);
+            mm[h] = __ldcs(reinterpret_cast<float4*>(m) + 2 * i + h);
+            vv[h] = __ldcs(reinterpret_cast<float4*>(v) + 2 * i + h);
+        }
+        float* pf = reinterpret_cast<float*>(pp);
+        float* mf = reinterpret_cast<float*>(mm);
+        float* vf = reinterpret_cast<float*>(vv);
+        uint4 praw;
+        __half2* ph = reinterpret_cast<__half2*>(&praw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 g2 = __half22float2(gh[j]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 2 * j + e;
+                const float gg = (e ? g2.y : g2.x) * grad_scale;
+                mf[k] = beta1 * mf[k] + (1.0f - beta1) * gg;
+                vf[k] = beta2 * vf[k] + (1.0f - beta2) * gg * gg;
+                pf[k] -= step_size * mf[k] / (sqrtf(vf[k]) * inv_sqrt_bc2 + eps);
+            }
+            ph[j] = __floats2half2_rn(pf[2 * j], pf[2 * j + 1]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            __stcs(reinterpret_cast<float4*>(p) + 2 * i + h, pp[h]);
+            __stcs(reinterpret_cast<float4*>(m) + 2 * i + h, mm[h]);
+            __stcs(reinterpret_cast<float4*>(v) + 2 * i + h, vv[h]);
+        }
+        reinterpret_cast<uint4*>(p16)[i] = praw;               // the table the next forward gathers from: keep it cacheable
+        if (zero_grad) __stcs(reinterpret_cast<uint4*>(g16) + i, make_uint4(0u, 0u, 0u, 0u));
+    }
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -278,4 +329,20 @@ extern "C" int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
     SANERF_LAUNCH(adam_step_kernel, (uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream), 
         params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad, gate, ema);
     return check_launch("adam_step_kernel");
+}
+
+extern "C" int sanerf_adam_step_half(float* master, void* params16, void* grads16, float* exp_avg, float* exp_avg_sq,
+                                     uint64_t n, const float* dyn, float beta1, float beta2, float eps, float grad_scale,
+                                     int zero_grad, void* stream) {
+    if (n == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(master); SANERF_REQUIRE_PTR(params16); SANERF_REQUIRE_PTR(grads16);
+    SANERF_REQUIRE_PTR(exp_avg); SANERF_REQUIRE_PTR(exp_avg_sq); SANERF_REQUIRE_PTR(dyn);
+    const uintptr_t align = (uintptr_t)master | (uintptr_t)params16 | (uintptr_t)grads16 | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq;
+    if ((align & 15u) || (n & 7u)) return fail(SANERF_ERR_MISALIGNED, "adam_step_half: 16-byte aligned buffers and n % 8 == 0");
+    const size_t n8 = (size_t)n / 8;
+    const size_t blocks = div_up(div_up(n8, (size_t)256), (size_t)4);
+    SANERF_LAUNCH(adam_step_half_kernel, (uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream), master,
+                  static_cast<__half*>(params16), static_cast<__half*>(grads16), exp_avg, exp_avg_sq, n8, dyn, beta1, beta2,
+                  eps, grad_scale, zero_grad);
+    return check_launch("adam_step_half_kernel");
 }
