@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 19
+#define SANERF_ABI_VERSION 20
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -340,6 +340,27 @@ SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
 SANERF_API int sanerf_adam_step_half(float* master, void* params16, void* grads16, float* exp_avg, float* exp_avg_sq,
                           uint64_t n, const float* dyn, float beta1, float beta2, float eps, float grad_scale,
                           int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel update fused with its exchange over NVLink / NVSwitch peer memory (csrc/symm_adam.cu): replaces the
+ * gradient all-reduce of DistributedDataParallel + torch.optim.Adam on every rank (main.py:296).
+ * All `world` ranks of one node call it with the same range; param / grad are this rank's flat buffers, which live in
+ * symmetric memory: *_mc = their multicast (NVLS) addresses or NULL, *_peers = HOST arrays [world] of every rank's
+ * unicast address of the same buffers (index = rank), flag_peers = HOST array [world] of the symmetric flag arrays
+ * (uint32 [128][8], zero-initialised once), epoch = this rank's uint32 [128] (zero-initialised once), error = uint32 [1]
+ * set to 1 if a peer never arrived (bounded spin, the kernel then returns instead of hanging).
+ * Per call: barrier; rank r sums the gradient of slice r of [start, stop) over all ranks (multimem.ld_reduce or peer
+ * loads), applies Adam (grad_scale, typically 1/world; optional EMA as in sanerf_adam_step) to its slice of
+ * exp_avg / exp_avg_sq / ema, writes the new parameters into EVERY rank's buffer and clears that slice of every rank's
+ * gradient; barrier.  Afterwards all ranks hold bit-identical parameters and a zero gradient in [start, stop);
+ * optimizer state and EMA are valid only for the rank's own slice.  gate as in sanerf_adam_step.  start, stop: multiples
+ * of 4.  blocks <= 128 and small enough to be co-resident (the blocks of one index wait for each other across ranks).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
+                          void* param_mc, void* grad_mc, const uint64_t* param_peers, const uint64_t* grad_peers,
+                          const uint64_t* flag_peers, uint32_t* epoch, uint32_t* error, uint64_t start, uint64_t stop,
+                          uint32_t world, uint32_t rank, const float* dyn, float beta1, float beta2, float eps,
+                          float grad_scale, const int32_t* gate, uint32_t blocks, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Field head on the tensor cores (tcgen05 / TMEM), fused with the hash-grid gather:

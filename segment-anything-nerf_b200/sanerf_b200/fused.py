@@ -571,15 +571,23 @@ class FusedAdam:
     step's CUDA graph finds nothing to do instead of moving the parameters by momentum on a zero gradient.
     """
 
-    def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000, ema_decay=None):
+    def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000, ema_decay=None, world_size=1):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
         # every slot is a multiple of 32 elements: views stay 16-byte aligned and any range of whole slots splits into
         # 2 / 4 / 8 equal, 16-byte-aligned shards (reduce-scatter + sharded update + all-gather, sanerf_b200/step.py)
         sizes = [(p.numel() + 31) // 32 * 32 for p in self.params]
         total = sum(sizes)
-        self.flat_param = torch.zeros(total, device=dev)
-        self.flat_grad = torch.zeros(total, device=dev)
+        # multi-GPU: parameters and gradients live in symmetric memory, so that the update kernel of every rank can read
+        # the peers' gradients and write the peers' parameters over NVLink (sanerf_b200/symm.py, csrc/symm_adam.cu)
+        from . import symm as _symm
+        self.symm = _symm.SymmetricState(total, dev) if _symm.enabled(world_size) else None
+        self.sharded = {}                                   # (start, stop) -> (lo, hi): ranges whose m / v / EMA are rank-sharded
+        if self.symm is not None:
+            self.flat_param, self.flat_grad = self.symm.param, self.symm.grad
+        else:
+            self.flat_param = torch.zeros(total, device=dev)
+            self.flat_grad = torch.zeros(total, device=dev)
         self.exp_avg = torch.zeros(total, device=dev)
         self.exp_avg_sq = torch.zeros(total, device=dev)
         off = 0
@@ -641,6 +649,29 @@ class FusedAdam:
                                       None if self.ema is None else self.ema.data_ptr() + off, _lib.current_stream(dev))
         _lib.check(rc, "adam_step")
 
+    def apply_symm(self, start, stop, gated=False, blocks=None):
+        """Multi-GPU form of ``apply``: ONE kernel sums the gradient of this rank's slice of [start, stop) over all ranks
+        through NVLink / NVSwitch, updates the slice (1/world scaling, EMA) and writes the new parameters into every rank's
+        buffer, clearing the gradient everywhere (csrc/symm_adam.cu).  Collective: every rank must call it."""
+        from . import symm as _symm
+        n = stop - start
+        if blocks is None:                                  # ~2 float4 per thread and trip; small ranges need few blocks
+            blocks = max(1, min(64, (n // 4 + 512 * 8 - 1) // (512 * 8)))
+        self.symm.launch(self, start, stop, 1.0 / self.symm.world, gated, blocks)
+        self.sharded[(start, stop)] = _symm.slice_bounds(start, stop, self.symm.world, self.symm.rank)
+
+    def gather_sharded_state(self):
+        """Ranges updated rank-sharded (``apply_symm`` / the NCCL reduce-scatter form) keep exp_avg / exp_avg_sq / EMA
+        only for the rank's own slice: make them whole on every rank (checkpoints, EMA evaluation).  Collective."""
+        import torch.distributed as dist
+        bufs = [self.exp_avg, self.exp_avg_sq] + ([self.ema] if self.ema is not None else [])
+        for (a, b), (lo, hi) in self.sharded.items():
+            for buf in bufs:
+                tmp = torch.zeros(b - a, device=buf.device)
+                tmp[lo - a:hi - a] = buf[lo:hi]
+                dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+                buf[a:b] = tmp
+
     def clear_gate(self):
         self.gate.zero_()
 
@@ -656,6 +687,8 @@ class FusedAdam:
     def ema_copy_to(self):
         if self.ema is None:
             raise RuntimeError("FusedAdam was built without ema_decay")
+        if self.sharded:
+            self.gather_sharded_state()
         self.flat_param.copy_(self.ema)
 
     def ema_restore(self):
@@ -668,6 +701,8 @@ class FusedAdam:
         """Same layout as ``torch_ema.ExponentialMovingAverage.state_dict()`` over the trainable parameters."""
         if self.ema is None:
             raise RuntimeError("FusedAdam was built without ema_decay")
+        if self.sharded:
+            self.gather_sharded_state()
         shadow = [self.ema[a:a + p.numel()].view_as(p).clone() for p, (a, _) in ((p, self.ranges[id(p)]) for p in self.params)]
         return {"decay": self.ema_decay, "num_updates": int(self.step_count.item()), "shadow_params": shadow,
                 "collected_params": None}

@@ -111,7 +111,10 @@ class FusedRGBStep:
         self.update_stream = torch.cuda.Stream(dev, priority=_update_priority(world_size))
         self.critical_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_CRIT_PRIO", -1)))
         self.distort_done = torch.cuda.Event()
-        self.one_graph = os.environ.get("SANERF_ONE_GRAPH", "0") == "1"     # multi-GPU: capture the NCCL exchange as well
+        # multi-GPU: with the fused symmetric-memory update there is no NCCL call in the step, and the whole step is ONE
+        # graph per rank (no host launches between its phases); with the NCCL exchange (SANERF_SYMM=0) the forward /
+        # backward halves are two graphs around the eager collectives unless SANERF_ONE_GRAPH=1 captures them as well
+        self.one_graph = optimizer.symm is not None or os.environ.get("SANERF_ONE_GRAPH", "0") == "1"
         self.pending_main = False
         self.sharded_update = True
         self.graphs = {}
@@ -293,6 +296,9 @@ class FusedRGBStep:
         if self.world_size == 1:
             opt.apply(a, b, grad_scale=1.0, zero_grad=True, gated=True)
             return
+        if opt.symm is not None:                           # reduce + Adam + broadcast in ONE kernel over NVLink peer memory
+            opt.apply_symm(a, b, gated=True)
+            return
         world, rank = self.world_size, dist.get_rank()
         if os.environ.get("SANERF_DBG_SKIP_MAIN_NCCL"):    # timing diagnostics only (tools/ab_nccl_g8.sh): wrong gradients
             lo, hi = shard_bounds(a, b, world, rank)
@@ -304,6 +310,7 @@ class FusedRGBStep:
             opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True, gated=True)
             return
         from .parallel import sharded_update
+        opt.sharded[(a, b)] = shard_bounds(a, b, world, rank)
         sharded_update(opt.flat_param, opt.flat_grad, a, b,
                        lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True, gated=True), world, rank)
 
@@ -317,6 +324,9 @@ class FusedRGBStep:
         assert a == 0, "the main table is expected to lead the flat parameter buffer"
         if not update_proposal:
             n = self.prop_range[0]
+        if self.optimizer.symm is not None:
+            self.optimizer.apply_symm(b, n)
+            return
         if self.world_size > 1 and not os.environ.get("SANERF_DBG_SKIP_TAIL_NCCL"):
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
@@ -632,17 +642,24 @@ class FusedSAMStep:
         if self.world_size == 1:
             opt.apply(a, b, grad_scale=1.0, zero_grad=True, gated=True)
             return
+        if opt.symm is not None:
+            opt.apply_symm(a, b, gated=True)
+            return
         world, rank = self.world_size, dist.get_rank()
         if not self.sharded_update:
             dist.all_reduce(opt.flat_grad[a:b], op=dist.ReduceOp.SUM)
             opt.apply(a, b, grad_scale=1.0 / world, zero_grad=True, gated=True)
             return
         from .parallel import sharded_update
+        opt.sharded[(a, b)] = shard_bounds(a, b, world, rank)
         sharded_update(opt.flat_param, opt.flat_grad, a, b,
                        lambda lo, hi: opt.apply(lo, hi, grad_scale=1.0 / world, zero_grad=True, gated=True), world, rank)
 
     def _update_rest(self):
         b, n = self._main_range()[1], self.optimizer.flat_param.numel()
+        if self.optimizer.symm is not None:
+            self.optimizer.apply_symm(b, n)
+            return
         if self.world_size > 1:
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
         self.optimizer.apply(b, n, grad_scale=1.0 / self.world_size, zero_grad=True)
@@ -694,7 +711,7 @@ class FusedSAMStep:
             if not self.use_graph or self.eager_runs < 1:
                 self.eager_runs += 1
                 self._whole_step()
-            elif self.world_size == 1:
+            elif self.world_size == 1 or self.optimizer.symm is not None:
                 mode = bool(self.model.training)
                 if mode not in self.graphs:
                     g = torch.cuda.CUDAGraph()

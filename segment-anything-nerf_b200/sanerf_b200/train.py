@@ -44,7 +44,7 @@ class RGBTrainer:
         # Adam(eps=1e-15) + LambdaLR 0.1**min(iter/iters,1)  (main.py:296,312-313) on flat buffers; the flat
         # gradient doubles as the all-reduce bucket and is cleared by the optimizer kernel; ema_decay=0.95 is what the
         # reference's Trainer is built with (main.py:316)
-        self.optimizer = FusedAdam(params, lr=lr, eps=1e-15, decay_iters=iters, ema_decay=ema_decay)
+        self.optimizer = FusedAdam(params, lr=lr, eps=1e-15, decay_iters=iters, ema_decay=ema_decay, world_size=world_size)
         self._prop_range = self.optimizer.range_of([*model.prop_encoders.parameters(), *model.prop_mlp.parameters()])
 
     def loss(self, rays_o, rays_d, gt_rgb, update_proposal=True, perturb=True):
@@ -140,7 +140,7 @@ class SAMTrainer:
             for p in model.parameters():
                 p.requires_grad_(id(p) in trainable)
         self.optimizer = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=lr, eps=1e-15,
-                                   decay_iters=iters, ema_decay=ema_decay)
+                                   decay_iters=iters, ema_decay=ema_decay, world_size=world_size)
 
     def _forward_backward(self, rays_o, rays_d, target, h, w):
         out = self.model.render(rays_o, rays_d, staged=False, bg_color=1, perturb=False, update_proposal=False,
