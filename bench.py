@@ -378,53 +378,81 @@ def bench_rgb(ctx):
             timing="CUDA events around the kernel's launches in an eager replay of the same step after the timed region "
                    "(the timed region itself replays a CUDA graph)")
     line["kernels"] = kernels
+    line["launch_table_ms"] = {nm + "".join(f" {k}={v}" for k, v in sorted(info.items())): round(ms, 5)
+                               for nm, info, _, ms in sorted(table, key=lambda r: -r[3])}
+    if world > 1:
+        symm = trainer.optimizer.symm
+        line["exchange"] = ("fused symmetric-memory kernel (reduce + Adam + EMA + broadcast over NVLink, "
+                            f"multicast={'yes' if symm.multicast() else 'no'}), whole step = one CUDA graph per rank"
+                            if symm is not None else "NCCL reduce-scatter / all-gather + all-reduce (eager, between two graphs)")
+        if symm is not None:
+            symm.check()
     trainer.flush()
     return line, trainer, dev_sets
 
 
-def grad_equiv(ctx, trainer, dev_sets):
+def grad_equiv(ctx, dev_sets):
     """N ranks, each on its own 8192 rays, gradients summed over NVLink and divided by N  ==  ONE rank on the
-    concatenated N x 8192 rays (SURVEY §4 tier iv).  No jitter; max over parameter tensors of the relative L2 error."""
+    concatenated N x 8192 rays (SURVEY §4 tier iv).  No jitter; max over parameter tensors of the relative L2 error.
+
+    Evaluated on a FRESH model with smooth, non-trivial tables (the tests' field): the bench's own model, after a few dozen
+    optimizer steps towards random RGB targets, has a field-head gradient that is a cancelling sum of terms ~1e6 times its
+    norm, and two evaluations of the SAME batch on ONE GPU then differ by 0.4 relative (tools/dbg_equiv.py) — a
+    conditioning property of that synthetic state, reported below as ``noise_floor`` for this model."""
     import torch.distributed as dist
 
+    from nerf.network import NeRFNetwork
     from sanerf_b200.step import FusedRGBStep
+    from sanerf_b200.train import RGBTrainer, default_opt
     world, dev = ctx.world, ctx.dev
-    trainer.flush()
+    torch.manual_seed(1)
+    model = NeRFNetwork(default_opt()).to(dev)
+    with torch.no_grad():
+        for enc in (model.grid, *model.prop_encoders):
+            offs = enc.offsets.tolist()
+            for l in range(len(offs) - 1):
+                enc.embeddings[offs[l]:offs[l + 1]].uniform_(-0.5, 0.5).mul_(1.0 / enc.per_level_scale ** l)
+    trainer = RGBTrainer(model, world_size=world)
     opt = trainer.optimizer
-    opt.zero_grad()
     plan = trainer.plan(N_RAYS)
-    perturb, plan.perturb = plan.perturb, False
+    plan.perturb = False
     o, d, rgb = dev_sets[0]
-    plan.gradients_only(o, d, rgb, update_proposal=True)
-    multi = opt.flat_grad.clone()
+
+    def grads(pl, *rays):
+        opt.zero_grad()
+        pl.gradients_only(*rays, update_proposal=True)
+        g = opt.flat_grad.clone()
+        opt.zero_grad()
+        return g
+
+    local = grads(plan, o, d, rgb)
+    again = grads(plan, o, d, rgb)
+    multi = local.clone()
     dist.all_reduce(multi, op=dist.ReduceOp.SUM)
     multi /= world
-    plan.perturb = perturb
-    opt.zero_grad()
-    # the concatenated batch on this rank alone
     parts = [[torch.empty_like(t) for _ in range(world)] for t in (o, d, rgb)]
     for lst, t in zip(parts, (o, d, rgb)):
         dist.all_gather(lst, t.contiguous())
     O, D, RGB = (torch.cat(lst, 0) for lst in parts)
-    big = FusedRGBStep(trainer.model, opt, world * N_RAYS, world_size=1, use_graph=False, perturb=False)
-    big.gradients_only(O, D, RGB, update_proposal=True)
-    single = opt.flat_grad.clone()
-    opt.zero_grad()
+    big = FusedRGBStep(model, opt, world * N_RAYS, world_size=1, use_graph=False, perturb=False)
+    single = grads(big, O, D, RGB)
     del big
-    worst, per = 0.0, {}
-    for name, p in trainer.model.named_parameters():
-        if not p.requires_grad:
-            continue
+    worst, floor, per = 0.0, 0.0, {}
+    for name, p in model.named_parameters():
         a, _ = opt.ranges[id(p)]
-        n = p.numel()
-        rel = ((multi[a:a + n].double() - single[a:a + n].double()).norm() / single[a:a + n].double().norm().clamp_min(1e-30)).item()
+        s = slice(a, a + p.numel())
+        den = single[s].double().norm().clamp_min(1e-30)
+        rel = ((multi[s].double() - single[s].double()).norm() / den).item()
+        floor = max(floor, ((local[s].double() - again[s].double()).norm() / local[s].double().norm().clamp_min(1e-30)).item())
         per[name] = rel
         worst = max(worst, rel)
-    t = torch.tensor([worst], device=dev, dtype=torch.float64)
+    t = torch.tensor([worst, floor], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"max_rel_l2": float(t.item()), "tol": 1e-4, "ok": bool(float(t.item()) <= 1e-4), "ranks": world,
-            "rays_per_rank": N_RAYS, "what": "N-rank all-reduced mean gradient vs one rank on the concatenated batch, per "
-                                             "parameter tensor, no jitter", "per_tensor": per}
+    return {"max_rel_l2": float(t[0].item()), "tol": 1e-4, "ok": bool(float(t[0].item()) <= 1e-4), "ranks": world,
+            "rays_per_rank": N_RAYS, "noise_floor": float(t[1].item()),
+            "what": "N-rank all-reduced mean gradient vs one rank on the concatenated batch, per parameter tensor, no jitter, "
+                    "fresh model with smooth tables; noise_floor = the same batch evaluated twice on one rank (atomic order)",
+            "per_tensor": per}
 
 
 def bench_sam(ctx):
@@ -682,7 +710,7 @@ def run_ours(args, rank, world, local_rank):
     line, trainer, dev_sets = bench_rgb(ctx)
     if world > 1:
         try:
-            line["grad_equiv"] = grad_equiv(ctx, trainer, dev_sets)
+            line["grad_equiv"] = grad_equiv(ctx, dev_sets)
         except Exception as e:  # noqa: BLE001
             line["grad_equiv"] = {"error": repr(e)[:300]}
     del trainer

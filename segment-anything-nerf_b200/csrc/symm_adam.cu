@@ -109,35 +109,56 @@ __global__ void __launch_bounds__(symm::kThreads) symm_adam_kernel(const SymmAda
         vv = p.beta2 * vv + (1.0f - p.beta2) * gg * gg;
         pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + p.eps);
     };
-    for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
-        float4 g;
-        if (p.grad_mc != nullptr) {
-            g = multimem_ld_reduce_f4(p.grad_mc + 4 * i);
-        } else {
-            g = zero;
-            for (uint32_t w = 0; w < p.world; ++w) {
-                const float4 t = __ldcs(reinterpret_cast<const float4*>(p.grad_peer[w]) + i);
-                g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    // kU independent 16-byte pieces per thread and trip: the switch-side reduction has a latency of microseconds, so the
+    // bytes in flight per SM, not the instruction rate, set the throughput of a slice
+    constexpr uint32_t kU = 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += kU * stride) {
+        float4 g[kU], pp[kU], mm[kU], vv[kU];
+#pragma unroll
+        for (uint32_t u = 0; u < kU; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i >= hi) break;
+            if (p.grad_mc != nullptr) {
+                g[u] = multimem_ld_reduce_f4(p.grad_mc + 4 * i);
+            } else {
+                g[u] = zero;
+                for (uint32_t w = 0; w < p.world; ++w) {
+                    const float4 t = __ldcs(reinterpret_cast<const float4*>(p.grad_peer[w]) + i);
+                    g[u].x += t.x; g[u].y += t.y; g[u].z += t.z; g[u].w += t.w;
+                }
             }
         }
-        float4 pp = __ldcs(reinterpret_cast<const float4*>(p.param) + i);
-        float4 mm = __ldcs(reinterpret_cast<const float4*>(p.exp_avg) + i);
-        float4 vv = __ldcs(reinterpret_cast<const float4*>(p.exp_avg_sq) + i);
-        upd(pp.x, g.x, mm.x, vv.x); upd(pp.y, g.y, mm.y, vv.y); upd(pp.z, g.z, mm.z, vv.z); upd(pp.w, g.w, mm.w, vv.w);
-        __stcs(reinterpret_cast<float4*>(p.exp_avg) + i, mm);
-        __stcs(reinterpret_cast<float4*>(p.exp_avg_sq) + i, vv);
-        if (p.ema != nullptr) {
-            float4 e = __ldcs(reinterpret_cast<const float4*>(p.ema) + i);
-            e.x -= ema_w * (e.x - pp.x); e.y -= ema_w * (e.y - pp.y); e.z -= ema_w * (e.z - pp.z); e.w -= ema_w * (e.w - pp.w);
-            __stcs(reinterpret_cast<float4*>(p.ema) + i, e);
+#pragma unroll
+        for (uint32_t u = 0; u < kU; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i >= hi) break;
+            pp[u] = __ldcs(reinterpret_cast<const float4*>(p.param) + i);
+            mm[u] = __ldcs(reinterpret_cast<const float4*>(p.exp_avg) + i);
+            vv[u] = __ldcs(reinterpret_cast<const float4*>(p.exp_avg_sq) + i);
         }
-        if (p.param_mc != nullptr) {
-            multimem_st_f4(p.param_mc + 4 * i, pp);
-            multimem_st_f4(p.grad_mc + 4 * i, zero);
-        } else {
-            for (uint32_t w = 0; w < p.world; ++w) {
-                reinterpret_cast<float4*>(p.param_peer[w])[i] = pp;
-                reinterpret_cast<float4*>(p.grad_peer[w])[i] = zero;
+#pragma unroll
+        for (uint32_t u = 0; u < kU; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i >= hi) break;
+            upd(pp[u].x, g[u].x, mm[u].x, vv[u].x); upd(pp[u].y, g[u].y, mm[u].y, vv[u].y);
+            upd(pp[u].z, g[u].z, mm[u].z, vv[u].z); upd(pp[u].w, g[u].w, mm[u].w, vv[u].w);
+            __stcs(reinterpret_cast<float4*>(p.exp_avg) + i, mm[u]);
+            __stcs(reinterpret_cast<float4*>(p.exp_avg_sq) + i, vv[u]);
+            if (p.ema != nullptr) {
+                float4 e = __ldcs(reinterpret_cast<const float4*>(p.ema) + i);
+                e.x -= ema_w * (e.x - pp[u].x); e.y -= ema_w * (e.y - pp[u].y);
+                e.z -= ema_w * (e.z - pp[u].z); e.w -= ema_w * (e.w - pp[u].w);
+                __stcs(reinterpret_cast<float4*>(p.ema) + i, e);
+            }
+            if (p.param_mc != nullptr) {
+                multimem_st_f4(p.param_mc + 4 * i, pp[u]);
+                multimem_st_f4(p.grad_mc + 4 * i, zero);
+            } else {
+                for (uint32_t w = 0; w < p.world; ++w) {
+                    reinterpret_cast<float4*>(p.param_peer[w])[i] = pp[u];
+                    reinterpret_cast<float4*>(p.grad_peer[w])[i] = zero;
+                }
             }
         }
     }
