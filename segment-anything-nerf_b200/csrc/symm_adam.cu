@@ -18,7 +18,8 @@
 // Cross-rank barrier: block b of rank r writes a monotonically increasing epoch into slot [b][r] of every peer's flag
 // array (st.release.sys) and waits until its own slots [b][*] reached the epoch (ld.acquire.sys).  Blocks only ever wait
 // for the SAME block index of the peers, and the grid is small enough to be co-resident, so progress needs nothing but
-// every rank launching the kernel.  A bounded spin (about 4 s) raises an error flag instead of hanging the GPU.
+// every rank launching the kernel.  Calls that may run concurrently (the deferred table update beside the next step's
+// front, the two tail ranges beside the hash-grid scatter) use different CHANNELS = disjoint slot ranges.  A bounded spin (about 4 s) raises an error flag instead of hanging the GPU.
 #include "common.cuh"
 
 namespace sanerf {
@@ -27,6 +28,7 @@ namespace symm {
 constexpr uint32_t kThreads = 512;
 constexpr uint32_t kMaxWorld = 8;
 constexpr uint32_t kMaxBlocks = 128;
+constexpr uint32_t kChannels = 4, kChannelBlocks = kMaxBlocks / kChannels;   // concurrent calls use disjoint flag slots
 }  // namespace symm
 
 struct SymmAdamParams {
@@ -46,7 +48,7 @@ struct SymmAdamParams {
     const int32_t* gate;     // or NULL
     uint64_t start, stop;    // flat range, multiples of 4
     float beta1, beta2, eps, grad_scale;
-    uint32_t world, rank;
+    uint32_t world, rank, slot0;   // slot0: first flag / epoch slot of this call's channel
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -76,8 +78,8 @@ __device__ __forceinline__ void rank_barrier(const SymmAdamParams& p, uint32_t& 
     epoch_reg += 1u;
     if (threadIdx.x < p.world) {
         const uint32_t peer = threadIdx.x;
-        st_release_sys(p.flags_peer[peer] + blockIdx.x * symm::kMaxWorld + p.rank, epoch_reg);
-        const uint32_t* mine = p.flags_peer[p.rank] + blockIdx.x * symm::kMaxWorld + peer;
+        st_release_sys(p.flags_peer[peer] + (p.slot0 + blockIdx.x) * symm::kMaxWorld + p.rank, epoch_reg);
+        const uint32_t* mine = p.flags_peer[p.rank] + (p.slot0 + blockIdx.x) * symm::kMaxWorld + peer;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(mine) - epoch_reg) < 0) {
             if (clock64() - t0 > 8000000000ll) {          // ~4 s at 1.9 GHz: a peer never arrived
@@ -92,7 +94,7 @@ __device__ __forceinline__ void rank_barrier(const SymmAdamParams& p, uint32_t& 
 __global__ void __launch_bounds__(symm::kThreads) symm_adam_kernel(const SymmAdamParams p) {
     pdl_begin();
     if (p.gate != nullptr && *p.gate == 0) return;          // same value on every rank: all skip together
-    uint32_t epoch_reg = p.epoch[blockIdx.x];
+    uint32_t epoch_reg = p.epoch[p.slot0 + blockIdx.x];
     rank_barrier(p, epoch_reg);                              // every rank's gradient is complete
 
     const uint64_t n4 = (p.stop - p.start) / 4;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(symm::kThreads) symm_adam_kernel(const SymmAda
         }
     }
     rank_barrier(p, epoch_reg);                              // every rank holds the new parameters and a cleared gradient
-    if (threadIdx.x == 0) p.epoch[blockIdx.x] = epoch_reg;
+    if (threadIdx.x == 0) p.epoch[p.slot0 + blockIdx.x] = epoch_reg;
 }
 
 }  // namespace sanerf
@@ -174,7 +176,7 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
                                      void* grad_mc, const uint64_t* param_peers, const uint64_t* grad_peers,
                                      const uint64_t* flag_peers, uint32_t* epoch, uint32_t* error, uint64_t start, uint64_t stop,
                                      uint32_t world, uint32_t rank, const float* dyn, float beta1, float beta2, float eps,
-                                     float grad_scale, const int32_t* gate, uint32_t blocks, void* stream) {
+                                     float grad_scale, const int32_t* gate, uint32_t blocks, uint32_t channel, void* stream) {
     if (stop <= start) return SANERF_OK;
     SANERF_REQUIRE_PTR(param); SANERF_REQUIRE_PTR(grad); SANERF_REQUIRE_PTR(exp_avg); SANERF_REQUIRE_PTR(exp_avg_sq);
     SANERF_REQUIRE_PTR(flag_peers); SANERF_REQUIRE_PTR(epoch); SANERF_REQUIRE_PTR(error); SANERF_REQUIRE_PTR(dyn);
@@ -183,7 +185,8 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
     if ((param_mc == nullptr) != (grad_mc == nullptr)) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: both multicast addresses or none");
     if (param_mc == nullptr && (param_peers == nullptr || grad_peers == nullptr))
         return fail(SANERF_ERR_INVALID_ARG, "symm_adam: peer addresses are required without multicast addresses");
-    if (blocks == 0 || blocks > symm::kMaxBlocks) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: 1..128 blocks");
+    if (channel >= symm::kChannels || blocks == 0 || blocks > symm::kChannelBlocks)
+        return fail(SANERF_ERR_INVALID_ARG, "symm_adam: channel 0..3, 1..32 blocks");
     SymmAdamParams p{};
     p.param = param; p.grad = grad; p.exp_avg = exp_avg; p.exp_avg_sq = exp_avg_sq; p.ema = ema;
     p.param_mc = static_cast<float*>(param_mc); p.grad_mc = static_cast<float*>(grad_mc);
@@ -194,6 +197,7 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
     }
     p.epoch = epoch; p.error = error; p.dyn = dyn; p.gate = gate; p.start = start; p.stop = stop;
     p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale; p.world = world; p.rank = rank;
+    p.slot0 = channel * symm::kChannelBlocks;
     SANERF_LAUNCH(symm_adam_kernel, blocks, symm::kThreads, 0, static_cast<cudaStream_t>(stream), p);
     return check_launch("symm_adam_kernel");
 }

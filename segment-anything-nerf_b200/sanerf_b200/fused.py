@@ -649,15 +649,16 @@ class FusedAdam:
                                       None if self.ema is None else self.ema.data_ptr() + off, _lib.current_stream(dev))
         _lib.check(rc, "adam_step")
 
-    def apply_symm(self, start, stop, gated=False, blocks=None):
+    def apply_symm(self, start, stop, gated=False, blocks=None, channel=0):
         """Multi-GPU form of ``apply``: ONE kernel sums the gradient of this rank's slice of [start, stop) over all ranks
         through NVLink / NVSwitch, updates the slice (1/world scaling, EMA) and writes the new parameters into every rank's
-        buffer, clearing the gradient everywhere (csrc/symm_adam.cu).  Collective: every rank must call it."""
+        buffer, clearing the gradient everywhere (csrc/symm_adam.cu).  Collective: every rank must call it.  Calls that
+        may overlap in time (different streams) must use different ``channel``s (0..3)."""
         from . import symm as _symm
         n = stop - start
-        if blocks is None:                                  # ~2 float4 per thread and trip; small ranges need few blocks
-            blocks = max(1, min(64, (n // 4 + 512 * 8 - 1) // (512 * 8)))
-        self.symm.launch(self, start, stop, 1.0 / self.symm.world, gated, blocks)
+        if blocks is None:                                  # a slice of n / world: 8 float4 per thread; at most one channel's slots
+            blocks = max(1, min(_symm.CHANNEL_BLOCKS, (n // (4 * self.symm.world) + 512 * 8 - 1) // (512 * 8)))
+        self.symm.launch(self, start, stop, 1.0 / self.symm.world, gated, blocks, channel)
         self.sharded[(start, stop)] = _symm.slice_bounds(start, stop, self.symm.world, self.symm.rank)
 
     def gather_sharded_state(self):

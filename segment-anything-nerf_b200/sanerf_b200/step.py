@@ -111,6 +111,9 @@ class FusedRGBStep:
         self.update_stream = torch.cuda.Stream(dev, priority=_update_priority(world_size))
         self.critical_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_CRIT_PRIO", -1)))
         self.distort_done = torch.cuda.Event()
+        self.view_done = torch.cuda.Event()
+        self.tail_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_SIDE_PRIO", 0)))
+        self.fuse_tail = os.environ.get("SANERF_FUSE_TAIL", "1") == "1"      # multi-GPU: tail exchanges beside the backward
         # multi-GPU: with the fused symmetric-memory update there is no NCCL call in the step, and the whole step is ONE
         # graph per rank (no host launches between its phases); with the NCCL exchange (SANERF_SYMM=0) the forward /
         # backward halves are two graphs around the eager collectives unless SANERF_ONE_GRAPH=1 captures them as well
@@ -173,8 +176,12 @@ class FusedRGBStep:
                                                          L["enc"].data_ptr() if update_proposal else None, st)
                 check(rc, "prop_density_forward")
 
-    def _launch_back(self, update_proposal):
-        """Final level forward, losses, backward of everything."""
+    def _launch_back(self, update_proposal, fuse_updates=False):
+        """Final level forward, losses, backward of everything.  ``fuse_updates`` (multi-GPU with the symmetric-memory
+        exchange): the small parameter ranges are exchanged + updated as soon as their gradients are complete, on side
+        branches BESIDE the rest of the backward — [view_mlp, proposal networks] after the view head and the proposal
+        branch, grid_mlp after the field-head backward, both while the hash-grid scatter (the last ~100 us of the step)
+        still runs — so that no exchange, barrier wait or optimizer launch is left at the end of the step."""
         m, lib, N = self.model, _lib.load(), self.N
         st = _lib.current_stream(self.dev)
         span, check = _lib.stats.span, _lib.check
@@ -204,10 +211,12 @@ class FusedRGBStep:
         main = torch.cuda.current_stream(self.dev)
         have_gw2 = lam_d > 0
         side = self.side_stream
-        if lam_p > 0 or have_gw2:
+        fuse_updates = fuse_updates and self.optimizer.symm is not None
+        forked = lam_p > 0 or have_gw2 or fuse_updates
+        if forked:
             side.wait_stream(main)
         if self.perturb:                                   # next step's jitter ([N, T+1] uniforms per level, reference order)
-            with torch.cuda.stream(side if (lam_p > 0 or have_gw2) else main):
+            with torch.cuda.stream(side if forked else main):
                 self.noise_flat.uniform_()
         if have_gw2:                                       # distortion loss: concurrent with the view head on the main stream
             with torch.cuda.stream(side):
@@ -254,6 +263,13 @@ class FusedRGBStep:
                                       self.g_geo_sum.data_ptr(), self.g_ws.data_ptr(), v1.grad.data_ptr(), v2.grad.data_ptr(),
                                       v3.grad.data_ptr(), st)
         check(rc, "view_head")
+        if fuse_updates:                                   # [view_mlp, proposal networks]: complete after view_head + the side branch
+            self.view_done.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(self.view_done)
+                b1 = self.optimizer.ranges[id(m.grid_mlp.net[-1].weight)][1]
+                n = self.optimizer.flat_param.numel() if update_proposal else self.prop_range[0]
+                self.optimizer.apply_symm(b1, n, channel=2)
         # ---------------- backward: final level
         if have_gw2:
             main.wait_event(self.distort_done)
@@ -269,13 +285,21 @@ class FusedRGBStep:
                                                 0.0, 0, None, w1.grad.data_ptr(), w2.grad.data_ptr(), w3.grad.data_ptr(),
                                                 self.precision, st)
         check(rc, "field_head_backward")
+        if fuse_updates:                                   # grid_mlp: complete now; exchanged beside the scatter
+            tail = self.tail_stream
+            tail.wait_stream(main)
+            with torch.cuda.stream(tail):
+                a1 = self._main_range()[1]
+                self.optimizer.apply_symm(a1, self.optimizer.ranges[id(m.grid_mlp.net[-1].weight)][1], channel=1)
         with span("grid_encode_backward", B=B, L=16, C=2, D=3, half=False):
             rc = lib.sanerf_grid_encode_backward(self.g_enc.data_ptr(), L["x01"].data_ptr(), g.embeddings.data_ptr(),
                                                  g.offsets.data_ptr(), g.embeddings.grad.data_ptr(), B, 3, 2, 16, 16, S, H, None,
                                                  None, 0, 0, 0, _lib.SANERF_F32, _lib.LAYOUT_BLC, st)
         check(rc, "grid_encode_backward")
-        if lam_p > 0 or have_gw2:
+        if forked:
             main.wait_stream(self.side_stream)            # join
+        if fuse_updates:
+            main.wait_stream(self.tail_stream)
 
     # ---- optimizer.  The main hash table is 89 % of the parameters and nothing before the final level's field head reads
     # it, so its Adam update (and, multi-GPU, the all-reduce of its gradient) is DEFERRED to the start of the next step,
@@ -369,8 +393,10 @@ class FusedRGBStep:
         # deferred main-table exchange another 74 us (tools/ab_nccl_g8.sh: 1.054 / 0.980 / 0.979 / 0.914 ms), but MOVING the
         # tail reduction beside the hash-grid scatter (a third graph for the scatter, NCCL on the update stream) changes
         # nothing: 1.0528 vs 1.0556 ms at 8 GPUs, 0.950 vs 0.949 at 2 - what the collectives absorb is rank skew.)
-        self._launch_back(update_proposal)
-        self._update_rest(update_proposal)
+        fuse = self.fuse_tail and self.optimizer.symm is not None
+        self._launch_back(update_proposal, fuse_updates=fuse)
+        if not fuse:
+            self._update_rest(update_proposal)
 
     def _graphs(self, update_proposal):
         """Single GPU: the whole step is one graph.  Multi-GPU: the forward / backward halves are two graphs and the
