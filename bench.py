@@ -708,7 +708,7 @@ def run_ours(args, rank, world, local_rank):
             print(json.dumps(line), flush=True)
         return
     line, trainer, dev_sets = bench_rgb(ctx)
-    if world > 1:
+    if world > 1 and not args.no_grad_equiv:
         try:
             line["grad_equiv"] = grad_equiv(ctx, dev_sets)
         except Exception as e:  # noqa: BLE001
@@ -749,6 +749,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
+    ap.add_argument("--no-grad-equiv", action="store_true", help="tuning runs only: skip the N-rank gradient check")
     ap.add_argument("--workload", default="all", choices=["all", "rgb", "sam", "frame", "cfg1", "cfg5"],
                     help="all = the headline RGB line (configs[1]) carrying the other configs under 'workloads'")
     args = ap.parse_args()

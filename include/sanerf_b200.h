@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 21
+#define SANERF_ABI_VERSION 22
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -351,17 +351,18 @@ SANERF_API int sanerf_adam_step_half(float* master, void* params16, void* grads1
  * set to 1 if a peer never arrived (bounded spin, the kernel then returns instead of hanging).
  * Per call: barrier; rank r sums the gradient of slice r of [start, stop) over all ranks (multimem.ld_reduce or peer
  * loads), applies Adam (grad_scale, typically 1/world; optional EMA as in sanerf_adam_step) to its slice of
- * exp_avg / exp_avg_sq / ema, writes the new parameters into EVERY rank's buffer and clears that slice of every rank's
- * gradient; barrier.  Afterwards all ranks hold bit-identical parameters and a zero gradient in [start, stop);
+ * exp_avg / exp_avg_sq / ema and writes the new parameters into EVERY rank's buffer; barrier; every rank clears its own
+ * gradient range.  Afterwards all ranks hold bit-identical parameters and a zero gradient in [start, stop);
  * optimizer state and EMA are valid only for the rank's own slice.  gate as in sanerf_adam_step.  start, stop: multiples
- * of 4.  blocks <= 32 (co-resident: the blocks of one index wait for each other across ranks); channel 0..3 selects a
- * disjoint quarter of the flag / epoch slots, so that calls running concurrently on different streams do not share any.
+ * of 4.  The blocks of one index wait for each other across ranks, so the grid must be co-resident: channel 0 (<= 64
+ * blocks), 1 or 2 (<= 32 blocks each) select disjoint flag / epoch slots, so that calls running concurrently on different
+ * streams do not share any.  threads: 32..512 per block (a small footprint leaves the SMs to the kernels it runs beside).
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
                           void* param_mc, void* grad_mc, const uint64_t* param_peers, const uint64_t* grad_peers,
                           const uint64_t* flag_peers, uint32_t* epoch, uint32_t* error, uint64_t start, uint64_t stop,
                           uint32_t world, uint32_t rank, const float* dyn, float beta1, float beta2, float eps,
-                          float grad_scale, const int32_t* gate, uint32_t blocks, uint32_t channel, void* stream);
+                          float grad_scale, const int32_t* gate, uint32_t blocks, uint32_t threads, uint32_t channel, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Field head on the tensor cores (tcgen05 / TMEM), fused with the hash-grid gather:

@@ -4,8 +4,7 @@
 //                                                         switch, or peer loads)
 //                                                        Adam (+ EMA) on the slice with the summed gradient
 //                                                        broadcast the new parameters     (multimem.st, or peer stores)
-//                                                        clear the slice of every rank's gradient
-//               barrier
+//               barrier  ->  clear the local gradient range
 //
 // It replaces the exchange the reference gets from DistributedDataParallel + torch.optim.Adam (one
 // all-reduce of the gradient bucket, then identical full-size Adam passes on every rank) and this repository's own NCCL
@@ -28,7 +27,10 @@ namespace symm {
 constexpr uint32_t kThreads = 512;
 constexpr uint32_t kMaxWorld = 8;
 constexpr uint32_t kMaxBlocks = 128;
-constexpr uint32_t kChannels = 4, kChannelBlocks = kMaxBlocks / kChannels;   // concurrent calls use disjoint flag slots
+// concurrent calls use disjoint flag slots: channel 0 (the deferred table update) owns 64, channels 1 and 2 own 32 each
+constexpr uint32_t kChannels = 3;
+__host__ __device__ constexpr uint32_t channel_slot0(uint32_t c) { return c == 0 ? 0u : 32u + 32u * c; }
+__host__ __device__ constexpr uint32_t channel_blocks(uint32_t c) { return c == 0 ? 64u : 32u; }
 }  // namespace symm
 
 struct SymmAdamParams {
@@ -111,16 +113,16 @@ __global__ void __launch_bounds__(symm::kThreads) symm_adam_kernel(const SymmAda
         vv = p.beta2 * vv + (1.0f - p.beta2) * gg * gg;
         pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + p.eps);
     };
-    // kU independent 16-byte pieces per thread and trip: the switch-side reduction has a latency of microseconds, so the
-    // bytes in flight per SM, not the instruction rate, set the throughput of a slice
+    // The switch-side reduction has a latency of several microseconds, so the bytes in flight, not the instruction rate,
+    // set the throughput of a slice: kU independent 16-byte reductions per thread, and the NEXT trip's reductions are
+    // issued before the current trip is processed (software pipeline), so the link never drains between trips.
     constexpr uint32_t kU = 4;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i0 = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += kU * stride) {
-        float4 g[kU], pp[kU], mm[kU], vv[kU];
+    auto fetch = [&](uint64_t i0, float4 (&g)[kU]) {
 #pragma unroll
         for (uint32_t u = 0; u < kU; ++u) {
             const uint64_t i = i0 + u * stride;
-            if (i >= hi) break;
+            if (i >= hi) { g[u] = zero; continue; }
             if (p.grad_mc != nullptr) {
                 g[u] = multimem_ld_reduce_f4(p.grad_mc + 4 * i);
             } else {
@@ -131,41 +133,45 @@ __global__ void __launch_bounds__(symm::kThreads) symm_adam_kernel(const SymmAda
                 }
             }
         }
+    };
+    float4 g[kU], gn[kU];
+    uint64_t i0 = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 < hi) fetch(i0, g);
+    for (; i0 < hi; i0 += kU * stride) {
+        const uint64_t inext = i0 + kU * stride;
+        if (inext < hi) fetch(inext, gn);
 #pragma unroll
         for (uint32_t u = 0; u < kU; ++u) {
             const uint64_t i = i0 + u * stride;
             if (i >= hi) break;
-            pp[u] = __ldcs(reinterpret_cast<const float4*>(p.param) + i);
-            mm[u] = __ldcs(reinterpret_cast<const float4*>(p.exp_avg) + i);
-            vv[u] = __ldcs(reinterpret_cast<const float4*>(p.exp_avg_sq) + i);
-        }
-#pragma unroll
-        for (uint32_t u = 0; u < kU; ++u) {
-            const uint64_t i = i0 + u * stride;
-            if (i >= hi) break;
-            upd(pp[u].x, g[u].x, mm[u].x, vv[u].x); upd(pp[u].y, g[u].y, mm[u].y, vv[u].y);
-            upd(pp[u].z, g[u].z, mm[u].z, vv[u].z); upd(pp[u].w, g[u].w, mm[u].w, vv[u].w);
-            __stcs(reinterpret_cast<float4*>(p.exp_avg) + i, mm[u]);
-            __stcs(reinterpret_cast<float4*>(p.exp_avg_sq) + i, vv[u]);
+            float4 pp = __ldcs(reinterpret_cast<const float4*>(p.param) + i);
+            float4 mm = __ldcs(reinterpret_cast<const float4*>(p.exp_avg) + i);
+            float4 vv = __ldcs(reinterpret_cast<const float4*>(p.exp_avg_sq) + i);
+            upd(pp.x, g[u].x, mm.x, vv.x); upd(pp.y, g[u].y, mm.y, vv.y);
+            upd(pp.z, g[u].z, mm.z, vv.z); upd(pp.w, g[u].w, mm.w, vv.w);
+            __stcs(reinterpret_cast<float4*>(p.exp_avg) + i, mm);
+            __stcs(reinterpret_cast<float4*>(p.exp_avg_sq) + i, vv);
             if (p.ema != nullptr) {
                 float4 e = __ldcs(reinterpret_cast<const float4*>(p.ema) + i);
-                e.x -= ema_w * (e.x - pp[u].x); e.y -= ema_w * (e.y - pp[u].y);
-                e.z -= ema_w * (e.z - pp[u].z); e.w -= ema_w * (e.w - pp[u].w);
+                e.x -= ema_w * (e.x - pp.x); e.y -= ema_w * (e.y - pp.y);
+                e.z -= ema_w * (e.z - pp.z); e.w -= ema_w * (e.w - pp.w);
                 __stcs(reinterpret_cast<float4*>(p.ema) + i, e);
             }
             if (p.param_mc != nullptr) {
-                multimem_st_f4(p.param_mc + 4 * i, pp[u]);
-                multimem_st_f4(p.grad_mc + 4 * i, zero);
+                multimem_st_f4(p.param_mc + 4 * i, pp);
             } else {
-                for (uint32_t w = 0; w < p.world; ++w) {
-                    reinterpret_cast<float4*>(p.param_peer[w])[i] = pp[u];
-                    reinterpret_cast<float4*>(p.grad_peer[w])[i] = zero;
-                }
+                for (uint32_t w = 0; w < p.world; ++w) reinterpret_cast<float4*>(p.param_peer[w])[i] = pp;
             }
         }
+#pragma unroll
+        for (uint32_t u = 0; u < kU; ++u) g[u] = gn[u];
     }
-    rank_barrier(p, epoch_reg);                              // every rank holds the new parameters and a cleared gradient
+    rank_barrier(p, epoch_reg);                              // every rank holds the new parameters; nobody reads gradients any more
     if (threadIdx.x == 0) p.epoch[p.slot0 + blockIdx.x] = epoch_reg;
+    // every slice of this rank's gradient has been consumed by its owner: clear the whole local range (local stores; sending
+    // zeros to the peers instead would cost the link as many bytes as the parameters)
+    for (uint64_t i = p.start / 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride)
+        __stcs(reinterpret_cast<float4*>(p.grad) + i, zero);
 }
 
 }  // namespace sanerf
@@ -176,7 +182,7 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
                                      void* grad_mc, const uint64_t* param_peers, const uint64_t* grad_peers,
                                      const uint64_t* flag_peers, uint32_t* epoch, uint32_t* error, uint64_t start, uint64_t stop,
                                      uint32_t world, uint32_t rank, const float* dyn, float beta1, float beta2, float eps,
-                                     float grad_scale, const int32_t* gate, uint32_t blocks, uint32_t channel, void* stream) {
+                                     float grad_scale, const int32_t* gate, uint32_t blocks, uint32_t threads, uint32_t channel, void* stream) {
     if (stop <= start) return SANERF_OK;
     SANERF_REQUIRE_PTR(param); SANERF_REQUIRE_PTR(grad); SANERF_REQUIRE_PTR(exp_avg); SANERF_REQUIRE_PTR(exp_avg_sq);
     SANERF_REQUIRE_PTR(flag_peers); SANERF_REQUIRE_PTR(epoch); SANERF_REQUIRE_PTR(error); SANERF_REQUIRE_PTR(dyn);
@@ -185,8 +191,9 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
     if ((param_mc == nullptr) != (grad_mc == nullptr)) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: both multicast addresses or none");
     if (param_mc == nullptr && (param_peers == nullptr || grad_peers == nullptr))
         return fail(SANERF_ERR_INVALID_ARG, "symm_adam: peer addresses are required without multicast addresses");
-    if (channel >= symm::kChannels || blocks == 0 || blocks > symm::kChannelBlocks)
-        return fail(SANERF_ERR_INVALID_ARG, "symm_adam: channel 0..3, 1..32 blocks");
+    if (channel >= symm::kChannels || blocks == 0 || blocks > symm::channel_blocks(channel))
+        return fail(SANERF_ERR_INVALID_ARG, "symm_adam: channel 0 (<= 64 blocks), 1 or 2 (<= 32 blocks)");
+    if (threads == 0 || threads > symm::kThreads || (threads & 31u)) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: threads 32..512");
     SymmAdamParams p{};
     p.param = param; p.grad = grad; p.exp_avg = exp_avg; p.exp_avg_sq = exp_avg_sq; p.ema = ema;
     p.param_mc = static_cast<float*>(param_mc); p.grad_mc = static_cast<float*>(grad_mc);
@@ -197,7 +204,7 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
     }
     p.epoch = epoch; p.error = error; p.dyn = dyn; p.gate = gate; p.start = start; p.stop = stop;
     p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale; p.world = world; p.rank = rank;
-    p.slot0 = channel * symm::kChannelBlocks;
-    SANERF_LAUNCH(symm_adam_kernel, blocks, symm::kThreads, 0, static_cast<cudaStream_t>(stream), p);
+    p.slot0 = symm::channel_slot0(channel);
+    SANERF_LAUNCH(symm_adam_kernel, blocks, threads, 0, static_cast<cudaStream_t>(stream), p);
     return check_launch("symm_adam_kernel");
 }

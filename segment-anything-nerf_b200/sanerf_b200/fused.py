@@ -656,9 +656,12 @@ class FusedAdam:
         may overlap in time (different streams) must use different ``channel``s (0..3)."""
         from . import symm as _symm
         n = stop - start
-        if blocks is None:                                  # a slice of n / world: 8 float4 per thread; at most one channel's slots
-            blocks = max(1, min(_symm.CHANNEL_BLOCKS, (n // (4 * self.symm.world) + 512 * 8 - 1) // (512 * 8)))
-        self.symm.launch(self, start, stop, 1.0 / self.symm.world, gated, blocks, channel)
+        import os
+        threads = int(os.environ.get("SANERF_SYMM_THREADS", 512))
+        if blocks is None:                                  # a slice of n / world: ~8 float4 per thread; at most the channel's slots
+            cap = min(_symm.CHANNEL_BLOCKS[channel], int(os.environ.get("SANERF_SYMM_BLOCKS", 32)))
+            blocks = max(1, min(cap, (n // (4 * self.symm.world) + threads * 8 - 1) // (threads * 8)))
+        self.symm.launch(self, start, stop, 1.0 / self.symm.world, gated, blocks, threads, channel)
         self.sharded[(start, stop)] = _symm.slice_bounds(start, stop, self.symm.world, self.symm.rank)
 
     def gather_sharded_state(self):

@@ -19,7 +19,8 @@ import torch.distributed as dist
 
 from . import _lib
 
-MAX_BLOCKS, MAX_WORLD, CHANNEL_BLOCKS = 128, 8, 32
+MAX_BLOCKS, MAX_WORLD = 128, 8
+CHANNEL_BLOCKS = {0: 64, 1: 32, 2: 32}
 
 
 def enabled(world_size):
@@ -66,7 +67,7 @@ class SymmetricState:
     def multicast(self):
         return bool(self.param_mc)
 
-    def launch(self, opt, start, stop, grad_scale, gated, blocks, channel=0):
+    def launch(self, opt, start, stop, grad_scale, gated, blocks, threads=256, channel=0):
         """Fused reduce + Adam(+EMA) + broadcast of the flat range [start, stop) on the current stream."""
         lib = _lib.load()
         dev = opt.flat_param.device
@@ -76,7 +77,7 @@ class SymmetricState:
                 None if opt.ema is None else opt.ema.data_ptr(), self.param_mc or None, self.grad_mc or None,
                 self.param_peers, self.grad_peers, self.flag_peers, self.epoch.data_ptr(), self.error.data_ptr(),
                 int(start), int(stop), self.world, self.rank, opt.dyn.data_ptr(), opt.betas[0], opt.betas[1], opt.eps,
-                float(grad_scale), opt.gate.data_ptr() if gated else None, int(blocks), int(channel), _lib.current_stream(dev))
+                float(grad_scale), opt.gate.data_ptr() if gated else None, int(blocks), int(threads), int(channel), _lib.current_stream(dev))
         _lib.check(rc, "symm_adam_step")
 
     def check(self):
