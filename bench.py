@@ -382,8 +382,8 @@ def bench_rgb(ctx):
                                for nm, info, _, ms in sorted(table, key=lambda r: -r[3])}
     if world > 1:
         symm = trainer.optimizer.symm
-        line["exchange"] = ("fused symmetric-memory kernel (reduce + Adam + EMA + broadcast over NVLink, "
-                            f"multicast={'yes' if symm.multicast() else 'no'}), whole step = one CUDA graph per rank"
+        line["exchange"] = ("fused symmetric-memory kernel (reduce + Adam + EMA + broadcast over NVLink; "
+                            f"{symm.describe() if symm is not None else ''}), whole step = one CUDA graph per rank"
                             if symm is not None else "NCCL reduce-scatter / all-gather + all-reduce (eager, between two graphs)")
         if symm is not None:
             symm.check()

@@ -345,18 +345,18 @@ SANERF_API int sanerf_adam_step_half(float* master, void* params16, void* grads1
  * Data-parallel update fused with its exchange over NVLink / NVSwitch peer memory (csrc/symm_adam.cu): replaces the
  * gradient all-reduce of DistributedDataParallel + torch.optim.Adam on every rank (main.py:296).
  * All `world` ranks of one node call it with the same range; param / grad are this rank's flat buffers, which live in
- * symmetric memory: *_mc = their multicast (NVLS) addresses or NULL, *_peers = HOST arrays [world] of every rank's
+ * symmetric memory: *_mc = their multicast (NVLS) addresses or NULL (independently: NULL selects the peer addresses), *_peers = HOST arrays [world] of every rank's
  * unicast address of the same buffers (index = rank), flag_peers = HOST array [world] of the symmetric flag arrays
- * (uint32 [128][8], zero-initialised once), epoch = this rank's uint32 [128] (zero-initialised once), error = uint32 [1]
+ * (uint32 [256][8], zero-initialised once), epoch = this rank's uint32 [256] (zero-initialised once), error = uint32 [1]
  * set to 1 if a peer never arrived (bounded spin, the kernel then returns instead of hanging).
  * Per call: barrier; rank r sums the gradient of slice r of [start, stop) over all ranks (multimem.ld_reduce or peer
  * loads), applies Adam (grad_scale, typically 1/world; optional EMA as in sanerf_adam_step) to its slice of
  * exp_avg / exp_avg_sq / ema and writes the new parameters into EVERY rank's buffer; barrier; every rank clears its own
  * gradient range.  Afterwards all ranks hold bit-identical parameters and a zero gradient in [start, stop);
  * optimizer state and EMA are valid only for the rank's own slice.  gate as in sanerf_adam_step.  start, stop: multiples
- * of 4.  The blocks of one index wait for each other across ranks, so the grid must be co-resident: channel 0 (<= 64
+ * of 4.  The blocks of one index wait for each other across ranks, so the grid must be co-resident: channel 0 (<= 160
  * blocks), 1 or 2 (<= 32 blocks each) select disjoint flag / epoch slots, so that calls running concurrently on different
- * streams do not share any.  threads: 32..512 per block (a small footprint leaves the SMs to the kernels it runs beside).
+ * streams do not share any.  threads: 32..1024 per block.  world: 2, 4 or 8.
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
                           void* param_mc, void* grad_mc, const uint64_t* param_peers, const uint64_t* grad_peers,

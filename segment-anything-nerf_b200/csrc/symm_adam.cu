@@ -24,13 +24,14 @@
 namespace sanerf {
 
 namespace symm {
-constexpr uint32_t kThreads = 512;
+constexpr uint32_t kThreads = 1024;
 constexpr uint32_t kMaxWorld = 8;
-constexpr uint32_t kMaxBlocks = 128;
-// concurrent calls use disjoint flag slots: channel 0 (the deferred table update) owns 64, channels 1 and 2 own 32 each
+constexpr uint32_t kMaxBlocks = 256;
+// concurrent calls use disjoint flag slots: channel 0 (the deferred table update) owns 160 (one block per SM), channels 1
+// and 2 own 32 each
 constexpr uint32_t kChannels = 3;
-__host__ __device__ constexpr uint32_t channel_slot0(uint32_t c) { return c == 0 ? 0u : 32u + 32u * c; }
-__host__ __device__ constexpr uint32_t channel_blocks(uint32_t c) { return c == 0 ? 64u : 32u; }
+__host__ __device__ constexpr uint32_t channel_slot0(uint32_t c) { return c == 0 ? 0u : 128u + 32u * c; }
+__host__ __device__ constexpr uint32_t channel_blocks(uint32_t c) { return c == 0 ? 160u : 32u; }
 }  // namespace symm
 
 struct SymmAdamParams {
@@ -61,14 +62,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// (ptxas emits LDGMC...STRONG.SYS for every semantics of multimem.ld_reduce; a thread then has ONE such reduction in
+// flight, ~2.6 us each through the switch: 25 MB per rank took 255 us on 32 x 512 threads and twice that on half the
+// threads, whatever the unrolling.  Plain peer loads (grad_mc == NULL) have no such limit and are the default.)
 __device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
     float4 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    asm volatile("multimem.ld_reduce.weak.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc));       // no memory clobber: loads may be hoisted together
     return v;
 }
 __device__ __forceinline__ void multimem_st_f4(float* mc, float4 v) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
 
@@ -93,7 +97,8 @@ __device__ __forceinline__ void rank_barrier(const SymmAdamParams& p, uint32_t& 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(symm::kThreads) symm_adam_kernel(const SymmAdamParams p) {
+template <uint32_t WORLD>
+__global__ void __launch_bounds__(symm::kThreads, 1) symm_adam_kernel(const SymmAdamParams p) {
     pdl_begin();
     if (p.gate != nullptr && *p.gate == 0) return;          // same value on every rank: all skip together
     uint32_t epoch_reg = p.epoch[p.slot0 + blockIdx.x];
@@ -113,58 +118,68 @@ __global__ void __launch_bounds__(symm::kThreads) symm_adam_kernel(const SymmAda
         vv = p.beta2 * vv + (1.0f - p.beta2) * gg * gg;
         pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + p.eps);
     };
-    // The switch-side reduction has a latency of several microseconds, so the bytes in flight, not the instruction rate,
-    // set the throughput of a slice: kU independent 16-byte reductions per thread, and the NEXT trip's reductions are
-    // issued before the current trip is processed (software pipeline), so the link never drains between trips.
-    constexpr uint32_t kU = 4;
+    // Remote reads have a latency of microseconds: every load of a trip is issued before the first use (kU pieces x
+    // WORLD peers of plain loads, or kU in-switch reductions), and the kernel is launched WIDE and SHORT (one block of up
+    // to 1024 threads per SM) rather than narrow and long: ptxas emits LDGMC...STRONG.SYS for multimem.ld_reduce and a
+    // thread gets one of them back every ~2.6 us, so the slice time is (elements per thread) x 2.6 us.
+    constexpr uint32_t kU = 2;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    auto fetch = [&](uint64_t i0, float4 (&g)[kU]) {
+    for (uint64_t i0 = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += kU * stride) {
+        float4 g[kU], pp[kU], mm[kU], vv[kU], ee[kU];
+        if (p.grad_mc != nullptr) {
 #pragma unroll
-        for (uint32_t u = 0; u < kU; ++u) {
-            const uint64_t i = i0 + u * stride;
-            if (i >= hi) { g[u] = zero; continue; }
-            if (p.grad_mc != nullptr) {
-                g[u] = multimem_ld_reduce_f4(p.grad_mc + 4 * i);
-            } else {
-                g[u] = zero;
-                for (uint32_t w = 0; w < p.world; ++w) {
-                    const float4 t = __ldcs(reinterpret_cast<const float4*>(p.grad_peer[w]) + i);
-                    g[u].x += t.x; g[u].y += t.y; g[u].z += t.z; g[u].w += t.w;
+            for (uint32_t u = 0; u < kU; ++u) {
+                const uint64_t i = i0 + u * stride;
+                g[u] = (i < hi) ? multimem_ld_reduce_f4(p.grad_mc + 4 * i) : zero;
+            }
+        } else {
+            float4 t[kU][WORLD];
+#pragma unroll
+            for (uint32_t u = 0; u < kU; ++u) {
+                const uint64_t i = i0 + u * stride;
+#pragma unroll
+                for (uint32_t w = 0; w < WORLD; ++w)
+                    t[u][w] = (i < hi) ? __ldcs(reinterpret_cast<const float4*>(p.grad_peer[w]) + i) : zero;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < kU; ++u) {
+                g[u] = t[u][0];
+#pragma unroll
+                for (uint32_t w = 1; w < WORLD; ++w) {
+                    g[u].x += t[u][w].x; g[u].y += t[u][w].y; g[u].z += t[u][w].z; g[u].w += t[u][w].w;
                 }
             }
         }
-    };
-    float4 g[kU], gn[kU];
-    uint64_t i0 = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i0 < hi) fetch(i0, g);
-    for (; i0 < hi; i0 += kU * stride) {
-        const uint64_t inext = i0 + kU * stride;
-        if (inext < hi) fetch(inext, gn);
 #pragma unroll
         for (uint32_t u = 0; u < kU; ++u) {
             const uint64_t i = i0 + u * stride;
             if (i >= hi) break;
-            float4 pp = __ldcs(reinterpret_cast<const float4*>(p.param) + i);
-            float4 mm = __ldcs(reinterpret_cast<const float4*>(p.exp_avg) + i);
-            float4 vv = __ldcs(reinterpret_cast<const float4*>(p.exp_avg_sq) + i);
-            upd(pp.x, g[u].x, mm.x, vv.x); upd(pp.y, g[u].y, mm.y, vv.y);
-            upd(pp.z, g[u].z, mm.z, vv.z); upd(pp.w, g[u].w, mm.w, vv.w);
-            __stcs(reinterpret_cast<float4*>(p.exp_avg) + i, mm);
-            __stcs(reinterpret_cast<float4*>(p.exp_avg_sq) + i, vv);
+            pp[u] = __ldcs(reinterpret_cast<const float4*>(p.param) + i);
+            mm[u] = __ldcs(reinterpret_cast<const float4*>(p.exp_avg) + i);
+            vv[u] = __ldcs(reinterpret_cast<const float4*>(p.exp_avg_sq) + i);
+            if (p.ema != nullptr) ee[u] = __ldcs(reinterpret_cast<const float4*>(p.ema) + i);
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < kU; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i >= hi) break;
+            upd(pp[u].x, g[u].x, mm[u].x, vv[u].x); upd(pp[u].y, g[u].y, mm[u].y, vv[u].y);
+            upd(pp[u].z, g[u].z, mm[u].z, vv[u].z); upd(pp[u].w, g[u].w, mm[u].w, vv[u].w);
+            __stcs(reinterpret_cast<float4*>(p.exp_avg) + i, mm[u]);
+            __stcs(reinterpret_cast<float4*>(p.exp_avg_sq) + i, vv[u]);
             if (p.ema != nullptr) {
-                float4 e = __ldcs(reinterpret_cast<const float4*>(p.ema) + i);
-                e.x -= ema_w * (e.x - pp.x); e.y -= ema_w * (e.y - pp.y);
-                e.z -= ema_w * (e.z - pp.z); e.w -= ema_w * (e.w - pp.w);
+                float4 e = ee[u];
+                e.x -= ema_w * (e.x - pp[u].x); e.y -= ema_w * (e.y - pp[u].y);
+                e.z -= ema_w * (e.z - pp[u].z); e.w -= ema_w * (e.w - pp[u].w);
                 __stcs(reinterpret_cast<float4*>(p.ema) + i, e);
             }
             if (p.param_mc != nullptr) {
-                multimem_st_f4(p.param_mc + 4 * i, pp);
+                multimem_st_f4(p.param_mc + 4 * i, pp[u]);
             } else {
-                for (uint32_t w = 0; w < p.world; ++w) reinterpret_cast<float4*>(p.param_peer[w])[i] = pp;
+#pragma unroll
+                for (uint32_t w = 0; w < WORLD; ++w) reinterpret_cast<float4*>(p.param_peer[w])[i] = pp[u];
             }
         }
-#pragma unroll
-        for (uint32_t u = 0; u < kU; ++u) g[u] = gn[u];
     }
     rank_barrier(p, epoch_reg);                              // every rank holds the new parameters; nobody reads gradients any more
     if (threadIdx.x == 0) p.epoch[p.slot0 + blockIdx.x] = epoch_reg;
@@ -186,14 +201,13 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
     if (stop <= start) return SANERF_OK;
     SANERF_REQUIRE_PTR(param); SANERF_REQUIRE_PTR(grad); SANERF_REQUIRE_PTR(exp_avg); SANERF_REQUIRE_PTR(exp_avg_sq);
     SANERF_REQUIRE_PTR(flag_peers); SANERF_REQUIRE_PTR(epoch); SANERF_REQUIRE_PTR(error); SANERF_REQUIRE_PTR(dyn);
-    if (world < 2 || world > symm::kMaxWorld || rank >= world) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: world must be 2..8");
+    if (world < 2 || world > symm::kMaxWorld || rank >= world) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: world must be 2, 4 or 8");
     if ((start | stop) & 3u) return fail(SANERF_ERR_MISALIGNED, "symm_adam: range bounds must be multiples of 4 elements");
-    if ((param_mc == nullptr) != (grad_mc == nullptr)) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: both multicast addresses or none");
-    if (param_mc == nullptr && (param_peers == nullptr || grad_peers == nullptr))
-        return fail(SANERF_ERR_INVALID_ARG, "symm_adam: peer addresses are required without multicast addresses");
+    if ((param_mc == nullptr && param_peers == nullptr) || (grad_mc == nullptr && grad_peers == nullptr))
+        return fail(SANERF_ERR_INVALID_ARG, "symm_adam: each buffer needs its multicast address or its peer addresses");
     if (channel >= symm::kChannels || blocks == 0 || blocks > symm::channel_blocks(channel))
-        return fail(SANERF_ERR_INVALID_ARG, "symm_adam: channel 0 (<= 64 blocks), 1 or 2 (<= 32 blocks)");
-    if (threads == 0 || threads > symm::kThreads || (threads & 31u)) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: threads 32..512");
+        return fail(SANERF_ERR_INVALID_ARG, "symm_adam: channel 0 (<= 160 blocks), 1 or 2 (<= 32 blocks)");
+    if (threads == 0 || threads > symm::kThreads || (threads & 31u)) return fail(SANERF_ERR_INVALID_ARG, "symm_adam: threads 32..1024");
     SymmAdamParams p{};
     p.param = param; p.grad = grad; p.exp_avg = exp_avg; p.exp_avg_sq = exp_avg_sq; p.ema = ema;
     p.param_mc = static_cast<float*>(param_mc); p.grad_mc = static_cast<float*>(grad_mc);
@@ -205,6 +219,12 @@ extern "C" int sanerf_symm_adam_step(float* param, float* grad, float* exp_avg, 
     p.epoch = epoch; p.error = error; p.dyn = dyn; p.gate = gate; p.start = start; p.stop = stop;
     p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale; p.world = world; p.rank = rank;
     p.slot0 = symm::channel_slot0(channel);
-    SANERF_LAUNCH(symm_adam_kernel, blocks, threads, 0, static_cast<cudaStream_t>(stream), p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (world) {
+        case 2: SANERF_LAUNCH(symm_adam_kernel<2>, blocks, threads, 0, st, p); break;
+        case 4: SANERF_LAUNCH(symm_adam_kernel<4>, blocks, threads, 0, st, p); break;
+        case 8: SANERF_LAUNCH(symm_adam_kernel<8>, blocks, threads, 0, st, p); break;
+        default: return fail(SANERF_ERR_INVALID_ARG, "symm_adam: world must be 2, 4 or 8");
+    }
     return check_launch("symm_adam_kernel");
 }

@@ -657,10 +657,10 @@ class FusedAdam:
         from . import symm as _symm
         n = stop - start
         import os
-        threads = int(os.environ.get("SANERF_SYMM_THREADS", 512))
-        if blocks is None:                                  # a slice of n / world: ~8 float4 per thread; at most the channel's slots
-            cap = min(_symm.CHANNEL_BLOCKS[channel], int(os.environ.get("SANERF_SYMM_BLOCKS", 32)))
-            blocks = max(1, min(cap, (n // (4 * self.symm.world) + threads * 8 - 1) // (threads * 8)))
+        threads = int(os.environ.get("SANERF_SYMM_THREADS", 1024))
+        if blocks is None:                                  # wide and short: a slice of n / world at ~4 float4 per thread
+            cap = min(_symm.CHANNEL_BLOCKS[channel], int(os.environ.get("SANERF_SYMM_BLOCKS", 148)))
+            blocks = max(1, min(cap, (n // (4 * self.symm.world) + threads * 4 - 1) // (threads * 4)))
         self.symm.launch(self, start, stop, 1.0 / self.symm.world, gated, blocks, threads, channel)
         self.sharded[(start, stop)] = _symm.slice_bounds(start, stop, self.symm.world, self.symm.rank)
 

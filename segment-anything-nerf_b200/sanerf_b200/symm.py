@@ -19,12 +19,12 @@ import torch.distributed as dist
 
 from . import _lib
 
-MAX_BLOCKS, MAX_WORLD = 128, 8
-CHANNEL_BLOCKS = {0: 64, 1: 32, 2: 32}
+MAX_BLOCKS, MAX_WORLD = 256, 8
+CHANNEL_BLOCKS = {0: 160, 1: 32, 2: 32}
 
 
 def enabled(world_size):
-    return world_size > 1 and os.environ.get("SANERF_SYMM", "1") != "0" and dist.is_initialized() \
+    return world_size in (2, 4, 8) and os.environ.get("SANERF_SYMM", "1") != "0" and dist.is_initialized() \
         and dist.get_backend() == "nccl"
 
 
@@ -35,8 +35,8 @@ class SymmetricState:
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if not 2 <= self.world <= MAX_WORLD:
-            raise RuntimeError(f"the fused symmetric-memory update supports 2..{MAX_WORLD} ranks of one node")
+        if self.world not in (2, 4, 8):
+            raise RuntimeError("the fused symmetric-memory update supports 2, 4 or 8 ranks of one node")
         try:
             symm_mem.enable_symm_mem_for_group(group.group_name)
         except Exception:  # noqa: BLE001  (newer torch enables every group implicitly)
@@ -52,8 +52,10 @@ class SymmetricState:
         use_mc = os.environ.get("SANERF_SYMM_MULTICAST", "1") != "0"
         self.param_mc = int(hp.multicast_ptr) if (use_mc and hp.has_multicast_support) else 0
         self.grad_mc = int(hg.multicast_ptr) if (use_mc and hg.has_multicast_support) else 0
-        if not (self.param_mc and self.grad_mc):
-            self.param_mc = self.grad_mc = 0
+        # gradient reduction: peer loads by default (many in flight per thread); "multimem" = in-switch reduction
+        # (multimem.ld_reduce), measured slower: one strong system-scope reduction in flight per thread
+        if os.environ.get("SANERF_SYMM_REDUCE", "p2p") != "multimem":
+            self.grad_mc = 0
         arr = ctypes.c_uint64 * self.world
         self.param_peers = arr(*[int(p) for p in hp.buffer_ptrs])
         self.grad_peers = arr(*[int(p) for p in hg.buffer_ptrs])
@@ -66,6 +68,10 @@ class SymmetricState:
 
     def multicast(self):
         return bool(self.param_mc)
+
+    def describe(self):
+        return (f"gradient reduction: {'multimem.ld_reduce (NVLS)' if self.grad_mc else 'peer loads over NVLink'}; parameter "
+                f"broadcast: {'multimem.st (NVLS)' if self.param_mc else 'peer stores'}")
 
     def launch(self, opt, start, stop, grad_scale, gated, blocks, threads=256, channel=0):
         """Fused reduce + Adam(+EMA) + broadcast of the flat range [start, stop) on the current stream."""
