@@ -62,9 +62,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// (ptxas emits LDGMC...STRONG.SYS for every semantics of multimem.ld_reduce; a thread then has ONE such reduction in
-// flight, ~2.6 us each through the switch: 25 MB per rank took 255 us on 32 x 512 threads and twice that on half the
-// threads, whatever the unrolling.  Plain peer loads (grad_mc == NULL) have no such limit and are the default.)
+// (ptxas emits LDGMC...STRONG.SYS for every semantics of multimem.ld_reduce, and a thread gets such a reduction back
+// every ~2.6 us: on 32 x 512 threads a 25 MB slice took 255 us, and twice that on half the threads, whatever the
+// unrolling - hence the wide launch below.)
 __device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
     float4 v;
     asm volatile("multimem.ld_reduce.weak.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"

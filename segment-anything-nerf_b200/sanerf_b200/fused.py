@@ -659,7 +659,7 @@ class FusedAdam:
         import os
         threads = int(os.environ.get("SANERF_SYMM_THREADS", 1024))
         if blocks is None:                                  # wide and short: a slice of n / world at ~4 float4 per thread
-            cap = min(_symm.CHANNEL_BLOCKS[channel], int(os.environ.get("SANERF_SYMM_BLOCKS", 148)))
+            cap = min(_symm.CHANNEL_BLOCKS[channel], int(os.environ.get("SANERF_SYMM_BLOCKS", 64)))
             blocks = max(1, min(cap, (n // (4 * self.symm.world) + threads * 4 - 1) // (threads * 4)))
         self.symm.launch(self, start, stop, 1.0 / self.symm.world, gated, blocks, threads, channel)
         self.sharded[(start, stop)] = _symm.slice_bounds(start, stop, self.symm.world, self.symm.rank)

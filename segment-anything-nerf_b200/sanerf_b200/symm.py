@@ -52,9 +52,10 @@ class SymmetricState:
         use_mc = os.environ.get("SANERF_SYMM_MULTICAST", "1") != "0"
         self.param_mc = int(hp.multicast_ptr) if (use_mc and hp.has_multicast_support) else 0
         self.grad_mc = int(hg.multicast_ptr) if (use_mc and hg.has_multicast_support) else 0
-        # gradient reduction: peer loads by default (many in flight per thread); "multimem" = in-switch reduction
-        # (multimem.ld_reduce), measured slower: one strong system-scope reduction in flight per thread
-        if os.environ.get("SANERF_SYMM_REDUCE", "p2p") != "multimem":
+        # gradient reduction: in-switch (multimem.ld_reduce, NVLS) by default; SANERF_SYMM_REDUCE=p2p reads every peer's
+        # slice with plain loads instead.  8 GPUs, RGB step, ms/step: multimem 0.931, p2p 0.977, NCCL exchange 1.050
+        # (profiles/r2_symm_sweep.md); at 2 GPUs the two are equal within noise.
+        if os.environ.get("SANERF_SYMM_REDUCE", "multimem") != "multimem":
             self.grad_mc = 0
         arr = ctypes.c_uint64 * self.world
         self.param_peers = arr(*[int(p) for p in hp.buffer_ptrs])
