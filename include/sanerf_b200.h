@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 22
+#define SANERF_ABI_VERSION 23
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -340,6 +340,15 @@ SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
 SANERF_API int sanerf_adam_step_half(float* master, void* params16, void* grads16, float* exp_avg, float* exp_avg_sq,
                           uint64_t n, const float* dyn, float beta1, float beta2, float eps, float grad_scale,
                           int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Uniform [0,1) jitter for the samplers (renderer.py:269 `torch.rand_like(bins)`, :101 `torch.rand_like(u)`): out f32 [n]
+ * filled with Philox4x32-10 numbers; state = uint32 [2] on the device, zero-initialised once, {call number, block
+ * arrival count}: the call number advances by one per launch, so a replayed CUDA graph draws fresh numbers.  Optionally
+ * clears zero[0..zero_n) (the step's loss accumulator) in the same launch.
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_uniform_fill(float* out, uint64_t n, uint64_t seed, uint32_t* state, float* zero, uint32_t zero_n,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-parallel update fused with its exchange over NVLink / NVSwitch peer memory (csrc/symm_adam.cu): replaces the

@@ -275,6 +275,56 @@ __global__ void __launch_bounds__(256) adam_step_half_kernel(float* __restrict__
     }
 }
 
+// ---- uniform jitter for the samplers (renderer.py:269 and :101: torch.rand_like, [N, T+1] per level) -----------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (element index / 4, call number), key = seed: 4 uniforms in [0,1) per
+// counter.  The call number lives on the device and advances by one per launch, so a captured CUDA graph draws fresh
+// numbers at every replay (the stream torch's generator would have produced is not reproduced: the reference has no seed
+// contract for the jitter, and parity tests feed the very buffer this kernel fills to the oracle).
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+
+__global__ void __launch_bounds__(256) uniform_fill_kernel(float* __restrict__ out, size_t n, uint64_t seed,
+                                                           uint32_t* __restrict__ call_counter, float* __restrict__ zero_a,
+                                                           uint32_t zero_n) {
+    pdl_begin();
+    const uint32_t call = *call_counter;
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 < zero_n) zero_a[i4] = 0.0f;                      // optional: clear a small accumulator (the step's loss) as well
+    if (i4 * 4 < n) {
+        uint32_t c[4] = {(uint32_t)i4, (uint32_t)(i4 >> 32), call, 0x5a4e5246u};
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            philox_round(c, k0, k1);
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        float u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = (float)(c[j] >> 8) * (1.0f / 16777216.0f);    // 24 bits: [0, 1)
+        if (i4 * 4 + 3 < n) {
+            reinterpret_cast<float4*>(out)[i4] = make_float4(u[0], u[1], u[2], u[3]);
+        } else {
+            for (size_t j = 0; i4 * 4 + j < n; ++j) out[i4 * 4 + j] = u[j];
+        }
+    }
+    __syncthreads();
+    // the last block to finish advances the call counter: every thread of every block has read it by then
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(call_counter + 1, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        call_counter[1] = 0u;
+        call_counter[0] = call + 1u;
+    }
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -345,4 +395,16 @@ extern "C" int sanerf_adam_step_half(float* master, void* params16, void* grads1
                   static_cast<__half*>(params16), static_cast<__half*>(grads16), exp_avg, exp_avg_sq, n8, dyn, beta1, beta2,
                   eps, grad_scale, zero_grad);
     return check_launch("adam_step_half_kernel");
+}
+
+extern "C" int sanerf_uniform_fill(float* out, uint64_t n, uint64_t seed, uint32_t* state, float* zero, uint32_t zero_n,
+                                   void* stream) {
+    if (n == 0 && zero_n == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(out); SANERF_REQUIRE_PTR(state);
+    if ((uintptr_t)out & 15u) return fail(SANERF_ERR_MISALIGNED, "uniform_fill: out must be 16-byte aligned");
+    const size_t n4 = div_up((size_t)n, (size_t)4);
+    const size_t work = n4 > zero_n ? n4 : (size_t)zero_n;
+    SANERF_LAUNCH(uniform_fill_kernel, (uint32_t)div_up(work, (size_t)256), 256, 0, static_cast<cudaStream_t>(stream), out,
+                  (size_t)n, seed, state, zero, zero_n);
+    return check_launch("uniform_fill_kernel");
 }

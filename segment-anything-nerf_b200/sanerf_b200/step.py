@@ -83,7 +83,10 @@ class FusedRGBStep:
         f32 = dict(device=dev, dtype=torch.float32)
         self.rays_o, self.rays_d, self.gt = (torch.zeros(N, 3, **f32) for _ in range(3))
         sizes = [N * (t + 1) for t in self.steps]
-        self.noise_flat = torch.rand(sum(sizes), **f32)
+        self.noise_flat = torch.rand(sum(sizes), **f32)       # first step's jitter; later steps: sanerf_uniform_fill (Philox)
+        self.rng_state = torch.zeros(4, device=dev, dtype=torch.int32)      # {call number, arrivals} of the jitter and of clear_loss
+        rank = dist.get_rank() if (world_size > 1 and dist.is_initialized()) else 0
+        self.seed = (int(torch.initial_seed()) ^ (rank * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF    # ranks draw different jitter
         self.noise, off = [], 0
         for t, n in zip(self.steps, sizes):
             self.noise.append(self.noise_flat[off:off + n].view(N, t + 1))
@@ -131,6 +134,13 @@ class FusedRGBStep:
         if self.prop_range[1] != optimizer.flat_param.numel():
             raise UnsupportedConfig("FusedRGBStep expects the proposal networks at the tail of the flat parameter buffer")
 
+    def _clear_loss(self):
+        """loss <- 0 with the library's own kernel (no torch fill inside the captured step)."""
+        with _lib.stats.span("clear_loss"):
+            rc = _lib.load().sanerf_uniform_fill(self.loss.data_ptr(), 0, 0, self.rng_state.data_ptr() + 8, self.loss.data_ptr(), 1,
+                                                 _lib.current_stream(self.dev))
+        _lib.check(rc, "clear_loss")
+
     # ------------------------------------------------------------------------------------------------------
     def _launch(self, update_proposal):
         """Enqueue forward + backward on the current stream (eagerly, or under CUDA-graph capture)."""
@@ -144,7 +154,7 @@ class FusedRGBStep:
         span, check, ptr = _lib.stats.span, _lib.check, _lib.ptr
         aabb = m.aabb_train if m.training else m.aabb_infer
         bound, contract, min_near = float(m.bound), int(bool(m.opt.contract)), float(m.min_near)
-        self.loss.zero_()          # (the jitter of THIS step was drawn during the previous step's backward, off the critical path)
+        self._clear_loss()         # (the jitter of THIS step was drawn during the previous step's backward, off the critical path)
         o, d = self.rays_o.data_ptr(), self.rays_d.data_ptr()
 
         # ---------------- forward: proposal levels
@@ -217,7 +227,10 @@ class FusedRGBStep:
             side.wait_stream(main)
         if self.perturb:                                   # next step's jitter ([N, T+1] uniforms per level, reference order)
             with torch.cuda.stream(side if forked else main):
-                self.noise_flat.uniform_()
+                with span("uniform_fill", n=self.noise_flat.numel()):
+                    rc = lib.sanerf_uniform_fill(self.noise_flat.data_ptr(), self.noise_flat.numel(), self.seed,
+                                                 self.rng_state.data_ptr(), None, 0, _lib.current_stream(self.dev))
+                check(rc, "uniform_fill")
         if have_gw2:                                       # distortion loss: concurrent with the view head on the main stream
             with torch.cuda.stream(side):
                 with span("distortion_loss", N=N, T=T):
@@ -493,6 +506,7 @@ class FusedRGBFrame(FusedRGBStep):
         self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)
         self.image = torch.empty(N, 3, **f32)
         self.loss = torch.zeros(1, **f32)
+        self.rng_state = torch.zeros(4, device=dev, dtype=torch.int32)
         self.graph = {}                                    # model.training -> captured forward (aabb_train / aabb_infer)
         self.eager_runs = 0
 

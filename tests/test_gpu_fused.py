@@ -299,3 +299,31 @@ def test_sample_pdf_with_fused_compositing_equals_two_kernels(cuda):
     assert torch.equal(w_out, w0)                          # same arithmetic as the compositing kernel
     for a, b in zip(outs, ref):
         assert torch.equal(a, b)
+
+
+def test_uniform_fill_is_uniform_and_advances(cuda):
+    """sanerf_uniform_fill: [0,1) values, flat histogram, fresh numbers on every launch (also when replayed in a CUDA graph),
+    optional accumulator clear."""
+    from sanerf_b200 import _lib
+    lib = _lib.load()
+    n = 1 << 20
+    out = torch.empty(n + 3, device="cuda")[:n + 1]           # odd length: exercises the tail
+    state = torch.zeros(2, device="cuda", dtype=torch.int32)
+    acc = torch.ones(1, device="cuda")
+    st = _lib.current_stream(out.device)
+    _lib.check(lib.sanerf_uniform_fill(out.data_ptr(), n + 1, 1234, state.data_ptr(), acc.data_ptr(), 1, st), "uniform_fill")
+    a = out.clone()
+    assert float(acc) == 0.0 and float(a.min()) >= 0.0 and float(a.max()) < 1.0
+    hist = torch.histc(a, bins=64, min=0, max=1) / a.numel()
+    assert (hist - 1 / 64).abs().max().item() < 2e-3 and abs(float(a.mean()) - 0.5) < 2e-3
+    assert abs(float((a[:-1] * a[1:]).mean()) - 0.25) < 2e-3                      # no lag-1 correlation
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g):
+            _lib.check(lib.sanerf_uniform_fill(out.data_ptr(), n + 1, 1234, state.data_ptr(), None, 0,
+                                               _lib.current_stream(out.device)), "uniform_fill")
+    g.replay(); b = out.clone(); g.replay(); c = out.clone()
+    torch.cuda.synchronize()
+    assert int(state[0]) == 3 and int(state[1]) == 0
+    assert not torch.equal(a, b) and not torch.equal(b, c)
