@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 23
+#define SANERF_ABI_VERSION 24
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -401,6 +401,27 @@ SANERF_API int sanerf_field_head_backward(const float* enc, const float* h1, con
                                const float* w1, const float* w2, const float* w3, uint32_t B, float* g_enc,
                                const float* x01, const int32_t* offsets, float S, uint32_t H, float* g_table,
                                float* g_w1, float* g_w2, float* g_w3, int precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Early ray termination that skips WORK (inference frames): the final level is evaluated front to back in chunks of
+ * chunk_len = 8 samples, for the rays still alive only.  The reference declares --T_thresh (main.py:71-72) and never reads
+ * it; the rule used is SURVEY 8 c5: sample k of a ray contributes iff T_k = exp(-sum_{j<k} delta_j sigma_j) >= t_thresh.
+ *  sanerf_field_head_forward_chunk: as sanerf_field_head_forward (inference form: nothing saved) for samples
+ *    [chunk*chunk_len, (chunk+1)*chunk_len) of the rays ray_list[0 .. *list_count) (device-side count, <= max_rays);
+ *    x01 [N,T,3] and out [N,T,16] keep their dense layout, rows of other samples are not touched.
+ *  sanerf_head_composite_chunk: trunc_exp + compositing of that chunk (same arithmetic as sanerf_head_composite_forward)
+ *    ACCUMULATED into per-ray state — optical [N] (carried sum of delta*sigma), weights_sum [N], depth [N], out [N,15],
+ *    n_alive [N], all zero-filled by the caller before chunk 0 — and the rays whose transmittance after the chunk is still
+ *    >= t_thresh are appended to next_list (next_count zero-filled by the caller; both NULL for the last chunk).
+ * ---------------------------------------------------------------------------------------- */
+SANERF_API int sanerf_field_head_forward_chunk(const float* x01, const float* table, const int32_t* offsets, float S,
+                              uint32_t H, const float* w1, const float* w2, const float* w3, float* out, int precision,
+                              const uint32_t* ray_list, const uint32_t* list_count, uint32_t max_rays, uint32_t chunk,
+                              uint32_t chunk_len, uint32_t T, void* stream);
+SANERF_API int sanerf_head_composite_chunk(const float* head, const float* deltas, const float* ts, const uint32_t* ray_list,
+                              const uint32_t* list_count, uint32_t max_rays, uint32_t T, uint32_t chunk, uint32_t chunk_len,
+                              int last_sample_opaque, float t_thresh, uint32_t* next_list, uint32_t* next_count,
+                              float* optical, float* weights_sum, float* depth, float* out, int32_t* n_alive, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics (no reference equivalent): one tcgen05 tile product D[M,N] with operands staged the way the fused

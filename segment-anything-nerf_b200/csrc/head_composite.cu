@@ -94,6 +94,105 @@ __device__ __forceinline__ float transpose_sum16(float (&v)[16], uint32_t lane) 
 }
 }  // namespace hc
 
+// ---- chunked front-to-back compositing with early ray termination ---------------------------------------------------
+// The frame renderer evaluates the final level in chunks of CL = 8 samples per ray, front to back (mlp_tc.cu:
+// sanerf_field_head_forward_chunk), for the rays still alive only.  This kernel composites ONE chunk of those rays, carrying
+// the optical depth, weights_sum, depth, the 15 channel sums and the alive-sample count in per-ray state arrays, and
+// appends the rays whose transmittance after the chunk is still >= t_thresh to the work list of the next chunk
+// (warp-aggregated append; the order of the list does not matter).  Eight lanes own a ray, a lane owns a sample.
+// Same per-sample arithmetic and the same termination rule as head_composite_forward_kernel: sample k contributes iff
+// T_k = exp(-sum_{j<k} delta_j sigma_j) >= t_thresh, so the result equals the un-chunked kernel's up to the
+// association order of the prefix sum; what chunking adds is that the FIELD is not evaluated behind the termination point.
+struct ChunkArgs {
+    const float* head;          // [N*T, 16]
+    const float* deltas;        // [N*T]
+    const float* ts;            // [N*T]
+    const uint32_t* ray_list;   // rays of this chunk
+    const uint32_t* list_count;
+    uint32_t* next_list;        // or NULL for the last chunk
+    uint32_t* next_count;
+    float* optical;             // [N] carried sum of delta * sigma
+    float* weights_sum;         // [N]
+    float* depth;               // [N]
+    float* out;                 // [N, 15]
+    int32_t* n_alive;           // [N]
+    uint32_t T, chunk, chunk_len;
+    int last_opaque;
+    float t_thresh;
+};
+
+__global__ void __launch_bounds__(128) head_composite_chunk_kernel(const ChunkArgs a) {
+    pdl_begin();
+    constexpr uint32_t kFull = 0xffffffffu, CL = 8;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane >> 3, j = lane & 7u;
+    const uint32_t count = __ldg(a.list_count);
+    const uint32_t q = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4u + sub;     // index into the work list
+    const bool have = q < count;
+    const uint32_t r = have ? __ldg(a.ray_list + q) : 0u;
+    const uint32_t k = a.chunk * CL + j;                           // sample index within the ray
+    const size_t i = (size_t)r * a.T + k;
+    float f[16];
+    if (have) hc::load_row(a.head, i, f);
+    else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) f[c] = 0.0f;
+    }
+    const float sigma = have ? expf(f[0]) : 0.0f;
+    float x = have ? __ldg(a.deltas + i) * sigma : 0.0f;
+    if (have && a.last_opaque && k == a.T - 1u) x = INFINITY;
+    float incl = x;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const float v = __shfl_up_sync(kFull, incl, o, 8);
+        if (j >= (uint32_t)o) incl += v;
+    }
+    float excl = __shfl_up_sync(kFull, incl, 1, 8);
+    if (j == 0) excl = 0.0f;
+    const float carry = have ? a.optical[r] : 0.0f;
+    const float S = carry + excl;
+    const float total = carry + __shfl_sync(kFull, incl, 7, 8);   // optical depth after this chunk
+    const float Tk = expf(-S);
+    float w = (1.0f - expf(-x)) * Tk;
+    const bool alive = have && !(Tk < a.t_thresh);
+    if (isnan(w)) w = 0.0f;
+    else if (isinf(w)) w = copysignf(FLT_MAX, w);
+    w = alive ? w : 0.0f;
+    float ws = w, dep = have ? w * __ldg(a.ts + i) : 0.0f;
+    float acc[15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) acc[c] = w * f[c + 1];
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+        ws += __shfl_xor_sync(kFull, ws, o, 8);
+        dep += __shfl_xor_sync(kFull, dep, o, 8);
+#pragma unroll
+        for (int c = 0; c < 15; ++c) acc[c] += __shfl_xor_sync(kFull, acc[c], o, 8);
+    }
+    const uint32_t alive_mask = __ballot_sync(kFull, alive);
+    const int n_alive_chunk = __popc((alive_mask >> (sub * 8u)) & 0xffu);
+    // ray survives into the next chunk iff its transmittance there is still above the threshold
+    const bool more = have && (a.next_list != nullptr) && !(expf(-total) < a.t_thresh);
+    if (have) {
+        if (j == 0) {
+            a.optical[r] = total;
+            a.weights_sum[r] += ws;
+            a.depth[r] += dep;
+            a.n_alive[r] += n_alive_chunk;
+        }
+        // 15 channel sums: lanes j = 0..7 write two channels each (all lanes of the segment hold the totals)
+#pragma unroll
+        for (int c = 0; c < 15; ++c)
+            if ((uint32_t)(c >> 1) == j) a.out[(size_t)r * 15 + c] += acc[c];
+    }
+    const uint32_t more_mask = __ballot_sync(kFull, more && j == 0);
+    if (more_mask != 0u) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.next_count, (uint32_t)__popc(more_mask));
+        base = __shfl_sync(kFull, base, 0);
+        if (more && j == 0) a.next_list[base + __popc(more_mask & ((1u << lane) - 1u))] = r;
+    }
+}
+
 __global__ void __launch_bounds__(32 * hc::kRaysPerBlock) head_composite_forward_kernel(
     const hc::Args a, float* __restrict__ sigma, float* __restrict__ weights, float* __restrict__ weights_sum,
     float* __restrict__ depth, float* __restrict__ out, int32_t* __restrict__ n_alive) {
@@ -247,4 +346,22 @@ extern "C" int sanerf_head_composite_backward(const float* head, const float* de
     SANERF_LAUNCH(head_composite_backward_kernel, div_up(N, (uint32_t)hc::kRaysPerBlock), 32 * hc::kRaysPerBlock, 0, static_cast<cudaStream_t>(stream), a, g_weights, g_weights_sum, g_depth, g_out,
                                                                           g_sigma_direct, g_head);
     return check_launch("head_composite_backward_kernel");
+}
+
+extern "C" int sanerf_head_composite_chunk(const float* head, const float* deltas, const float* ts, const uint32_t* ray_list,
+                                           const uint32_t* list_count, uint32_t max_rays, uint32_t T, uint32_t chunk,
+                                           uint32_t chunk_len, int last_sample_opaque, float t_thresh, uint32_t* next_list,
+                                           uint32_t* next_count, float* optical, float* weights_sum, float* depth, float* out,
+                                           int32_t* n_alive, void* stream) {
+    if (max_rays == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(head); SANERF_REQUIRE_PTR(deltas); SANERF_REQUIRE_PTR(ts); SANERF_REQUIRE_PTR(ray_list);
+    SANERF_REQUIRE_PTR(list_count); SANERF_REQUIRE_PTR(optical); SANERF_REQUIRE_PTR(weights_sum); SANERF_REQUIRE_PTR(depth);
+    SANERF_REQUIRE_PTR(out); SANERF_REQUIRE_PTR(n_alive);
+    if (chunk_len != 8 || T % 8 != 0 || (chunk + 1) * chunk_len > T)
+        return fail(SANERF_ERR_INVALID_ARG, "head_composite_chunk: chunk_len must be 8, T a multiple of 8, the chunk inside the ray");
+    if ((next_list == nullptr) != (next_count == nullptr)) return fail(SANERF_ERR_INVALID_ARG, "next_list and next_count go together");
+    ChunkArgs a{head, deltas, ts, ray_list, list_count, next_list, next_count, optical, weights_sum, depth, out, n_alive,
+                T, chunk, chunk_len, last_sample_opaque, t_thresh};
+    SANERF_LAUNCH(head_composite_chunk_kernel, div_up(max_rays, 16u), 128, 0, static_cast<cudaStream_t>(stream), a);
+    return check_launch("head_composite_chunk_kernel");
 }

@@ -59,7 +59,22 @@ struct HeadFwdParams {
     uint32_t B, H;
     float S;
     int precision;           // 0: 3xTF32 (fp32 parity), 1: single tf32 pass
+    // Chunked front-to-back evaluation (early ray termination): when ray_list != NULL the kernel evaluates samples
+    // [chunk * chunk_len, (chunk + 1) * chunk_len) of the rays ray_list[0 .. *list_count) only; compact index b' maps to
+    // sample (ray_list[b' / chunk_len], chunk * chunk_len + b' % chunk_len) of the [N, T] layout of x01 / out.
+    const uint32_t* ray_list;
+    const uint32_t* list_count;
+    uint32_t chunk, chunk_len, T;
 };
+
+// compact index -> row of x01 / out; returns false past the end of the work list
+__device__ __forceinline__ bool head_row(const HeadFwdParams& p, uint32_t work, uint32_t bprime, uint32_t& row) {
+    if (bprime >= work) return false;
+    if (p.ray_list == nullptr) { row = bprime; return true; }
+    const uint32_t q = bprime / p.chunk_len, j = bprime - q * p.chunk_len;
+    row = __ldg(p.ray_list + q) * p.T + p.chunk * p.chunk_len + j;
+    return true;
+}
 
 __device__ __forceinline__ float round_tf32(float x) {
     uint32_t r;
@@ -184,9 +199,12 @@ __device__ __forceinline__ void relu_to_tmem(uint32_t lane_base, uint32_t c_acc,
     }
 }
 
-__global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const HeadFwdParams p, const uint32_t tiles) {
+__global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const HeadFwdParams p, const uint32_t tiles_arg) {
     pdl_begin();
     using namespace head;
+    // number of samples to evaluate: all B, or chunk_len per ray still alive (the count lives on the device: no host sync)
+    const uint32_t work = (p.ray_list != nullptr) ? __ldg(p.list_count) * p.chunk_len : p.B;
+    const uint32_t tiles = (p.ray_list != nullptr) ? (work + kTile - 1) / kTile : tiles_arg;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_mma;
     __shared__ uint32_t s_tmem;
@@ -228,8 +246,8 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
         for (uint32_t it = 0, tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
             const uint32_t slot = it & 1u;
             umma::mbar_wait(umma::smem_u32(&s_empty[slot]), ((it >> 1) & 1u) ^ 1u);
-            const uint32_t b = tile * kTile + r;
-            const bool live = b < p.B;
+            uint32_t b = 0;
+            const bool live = head_row(p, work, tile * kTile + r, b);
             float enc[2 * kLevelsPerThread];
             if (p.x01 != nullptr) {
                 float x[3] = {0.5f, 0.5f, 0.5f};
@@ -316,8 +334,9 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             }
             umma::mbar_wait(umma::smem_u32(&s_mma), mma_phase); mma_phase ^= 1u;
             umma::fence_after_sync();
-            const uint32_t b = tile * kTile + tid;
-            const bool keep = (p.h1_out != nullptr) && b < p.B;
+            uint32_t b = 0;
+            const bool row_live = head_row(p, work, tile * kTile + tid, b);
+            const bool keep = (p.h1_out != nullptr) && row_live;
             relu_to_tmem(lane_base, cD1, split, keep ? p.h1_out : nullptr, b);
             umma::tmem_st_wait();
             umma::fence_before_sync();
@@ -348,7 +367,7 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             umma::fence_after_sync();
             float v[16];
             umma::tmem_ld16(lane_base + cD3, v);
-            if (b < p.B) {
+            if (row_live) {
                 float4* dst = reinterpret_cast<float4*>(p.out + (size_t)b * kOut);
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -816,11 +835,33 @@ extern "C" int sanerf_field_head_forward(const float* x01, const float* table, c
     SANERF_REQUIRE_PTR(w1); SANERF_REQUIRE_PTR(w2); SANERF_REQUIRE_PTR(w3); SANERF_REQUIRE_PTR(out);
     if (precision != 0 && precision != 1) return fail(SANERF_ERR_INVALID_ARG, "field_head: precision 0 (3xTF32) or 1 (TF32)");
     if ((h1_out == nullptr) != (h2_out == nullptr)) return fail(SANERF_ERR_INVALID_ARG, "field_head: h1_out and h2_out go together");
-    HeadFwdParams p{x01, table, offsets, enc_in, w1, w2, w3, enc_out, h1_out, h2_out, out, B, H, S, precision};
+    HeadFwdParams p{x01, table, offsets, enc_in, w1, w2, w3, enc_out, h1_out, h2_out, out, B, H, S, precision,
+                    nullptr, nullptr, 0u, 0u, 0u};
     const uint32_t tiles = div_up(B, head::kTile);
     const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
     cudaError_t e = cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kFwdSmem);
     if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "field_head_forward: %s", cudaGetErrorString(e));
+    SANERF_LAUNCH(head_forward_kernel, blocks, head::kThreads, head::kFwdSmem, static_cast<cudaStream_t>(stream), p, tiles);
+    return check_launch("head_forward_kernel");
+}
+
+extern "C" int sanerf_field_head_forward_chunk(const float* x01, const float* table, const int32_t* offsets, float S, uint32_t H,
+                                               const float* w1, const float* w2, const float* w3, float* out, int precision,
+                                               const uint32_t* ray_list, const uint32_t* list_count, uint32_t max_rays,
+                                               uint32_t chunk, uint32_t chunk_len, uint32_t T, void* stream) {
+    if (max_rays == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(x01); SANERF_REQUIRE_PTR(table); SANERF_REQUIRE_PTR(offsets);
+    SANERF_REQUIRE_PTR(w1); SANERF_REQUIRE_PTR(w2); SANERF_REQUIRE_PTR(w3); SANERF_REQUIRE_PTR(out);
+    SANERF_REQUIRE_PTR(ray_list); SANERF_REQUIRE_PTR(list_count);
+    if (precision != 0 && precision != 1) return fail(SANERF_ERR_INVALID_ARG, "field_head: precision 0 (3xTF32) or 1 (TF32)");
+    if (chunk_len == 0 || T % chunk_len != 0 || (chunk + 1) * chunk_len > T)
+        return fail(SANERF_ERR_INVALID_ARG, "field_head_forward_chunk: chunk_len must divide T and the chunk lie inside the ray");
+    HeadFwdParams p{x01, table, offsets, nullptr, w1, w2, w3, nullptr, nullptr, nullptr, out, max_rays * T, H, S, precision,
+                    ray_list, list_count, chunk, chunk_len, T};
+    const uint32_t tiles = div_up(max_rays * chunk_len, head::kTile);           // upper bound: the kernel reads the live count
+    const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
+    cudaError_t e = cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kFwdSmem);
+    if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "field_head_forward_chunk: %s", cudaGetErrorString(e));
     SANERF_LAUNCH(head_forward_kernel, blocks, head::kThreads, head::kFwdSmem, static_cast<cudaStream_t>(stream), p, tiles);
     return check_launch("head_forward_kernel");
 }

@@ -16,7 +16,7 @@ _HEADER = os.path.join(os.path.dirname(_PKG_DIR), "include", "sanerf_b200.h")
 
 SANERF_F32, SANERF_F16 = 0, 1
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
-ABI_VERSION = 23
+ABI_VERSION = 24
 
 c_void_p, c_int, c_u32, c_u64, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                           ctypes.c_uint64, ctypes.c_float)
@@ -87,6 +87,10 @@ _SIGNATURES = {
     "sanerf_uniform_fill": [c_void_p, c_u64, c_u64, c_void_p, c_void_p, c_u32, c_void_p],
     "sanerf_field_head_forward": [c_void_p, c_void_p, c_void_p, c_float, c_u32, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "sanerf_field_head_forward_chunk": [c_void_p, c_void_p, c_void_p, c_float, c_u32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_void_p],
+    "sanerf_head_composite_chunk": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_int,
+                                    c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sanerf_field_head_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32,
                                    c_void_p, c_void_p, c_void_p, c_float, c_u32, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_void_p],

@@ -470,8 +470,9 @@ class FusedRGBFrame(FusedRGBStep):
     the interactive frame (nerf/utils.py:1647-1712 ``test_gui``, renderer.py:185-219 staged ``render``) reduces to for
     the RGB pass; a SAM model's feature branch is not touched (its outputs are not part of an RGB frame)."""
 
-    def __init__(self, model, n_rays, use_graph=True, bg_color=1.0):
+    def __init__(self, model, n_rays, use_graph=True, bg_color=1.0, chunked=True):
         opt = model.opt
+        self.chunked = bool(chunked)       # with model.t_thresh > 0: evaluate the final level in chunks and skip terminated rays
         if opt.with_mask or opt.sum_after_mlp:
             raise UnsupportedConfig("FusedRGBFrame covers deferred shading without mask heads")
         if not field_head_supported(model.grid, model.grid_mlp):
@@ -502,8 +503,18 @@ class FusedRGBFrame(FusedRGBStep):
                                 sigma=torch.empty(N, t, **f32), weights=torch.empty(N, t, **f32), enc=None,
                                 ws=torch.empty(N, **f32), depth=torch.empty(N, **f32)))
         self.head = torch.empty(N * self.steps[2], 16, **f32)
-        self.geo_sum = torch.empty(N, 15, **f32)
-        self.n_alive = torch.empty(N, device=dev, dtype=torch.int32)
+        # per-ray compositing state in ONE buffer (cleared by one launch before a chunked frame):
+        # {optical depth, weights_sum, depth, 15 channel sums, alive count, live-ray counts of chunks 1..}
+        self.chunk_len = 8
+        self.n_chunks = self.steps[2] // self.chunk_len if self.steps[2] % self.chunk_len == 0 else 0
+        self.state = torch.zeros(N * 19 + 16, **f32)
+        self.optical, self.ws_acc, self.depth_acc = self.state[:N], self.state[N:2 * N], self.state[2 * N:3 * N]
+        self.geo_sum = self.state[3 * N:18 * N].view(N, 15)
+        self.n_alive = self.state[18 * N:19 * N].view(torch.int32)
+        self.counts = self.state[19 * N:19 * N + 16].view(torch.int32)          # [0] is unused: chunk 0 covers every ray
+        self.all_rays = torch.arange(N, device=dev, dtype=torch.int32)
+        self.n_rays_dev = torch.tensor([N], device=dev, dtype=torch.int32)
+        self.lists = [torch.empty(N, device=dev, dtype=torch.int32) for _ in range(max(self.n_chunks - 1, 0))]
         self.image = torch.empty(N, 3, **f32)
         self.loss = torch.zeros(1, **f32)
         self.rng_state = torch.zeros(4, device=dev, dtype=torch.int32)
@@ -519,21 +530,50 @@ class FusedRGBFrame(FusedRGBStep):
         T, B = L["T"], N * L["T"]
         g = m.grid
         w1, w2, w3 = (l.weight for l in m.grid_mlp.net)
-        with span("field_head_forward", B=B):
-            rc = lib.sanerf_field_head_forward(L["x01"].data_ptr(), g.embeddings.data_ptr(), g.offsets.data_ptr(),
-                                               float(np.log2(g.per_level_scale)), int(g.base_resolution), None, w1.data_ptr(),
-                                               w2.data_ptr(), w3.data_ptr(), B, None, None, None, self.head.data_ptr(),
-                                               self.precision, st)
-        check(rc, "field_head_forward")
-        with span("head_composite_forward", N=N, T=T):
-            rc = lib.sanerf_head_composite_forward(self.head.data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), N, T,
-                                                   self.opaque, float(m.t_thresh), None, L["weights"].data_ptr(),
-                                                   L["ws"].data_ptr(), L["depth"].data_ptr(), self.geo_sum.data_ptr(),
-                                                   self.n_alive.data_ptr(), st)
-        check(rc, "head_composite_forward")
+        S, H = float(np.log2(g.per_level_scale)), int(g.base_resolution)
+        ws_buf, depth_buf = L["ws"], L["depth"]
+        if float(m.t_thresh) > 0.0 and self.n_chunks > 1 and self.chunked:
+            # early ray termination that skips the field evaluation behind the termination point: chunks of 8 samples,
+            # front to back, for the rays still alive (device-side work lists; no host synchronisation)
+            ws_buf, depth_buf = self.ws_acc, self.depth_acc
+            with span("clear_state", n=self.state.numel()):
+                rc = lib.sanerf_uniform_fill(self.state.data_ptr(), 0, 0, self.rng_state.data_ptr() + 8, self.state.data_ptr(),
+                                             self.state.numel(), st)
+            check(rc, "clear_state")
+            CL = self.chunk_len
+            for c in range(self.n_chunks):
+                rays = self.all_rays if c == 0 else self.lists[c - 1]
+                count = self.n_rays_dev if c == 0 else self.counts[c:c + 1]
+                last = c == self.n_chunks - 1
+                with span("field_head_forward_chunk", N=N, chunk=c):
+                    rc = lib.sanerf_field_head_forward_chunk(L["x01"].data_ptr(), g.embeddings.data_ptr(), g.offsets.data_ptr(), S, H,
+                                                             w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), self.head.data_ptr(),
+                                                             self.precision, rays.data_ptr(), count.data_ptr(), N, c, CL, T, st)
+                check(rc, "field_head_forward_chunk")
+                with span("head_composite_chunk", N=N, chunk=c):
+                    rc = lib.sanerf_head_composite_chunk(self.head.data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(),
+                                                         rays.data_ptr(), count.data_ptr(), N, T, c, CL, self.opaque,
+                                                         float(m.t_thresh), None if last else self.lists[c].data_ptr(),
+                                                         None if last else self.counts[c + 1:c + 2].data_ptr(),
+                                                         self.optical.data_ptr(), ws_buf.data_ptr(), depth_buf.data_ptr(),
+                                                         self.geo_sum.data_ptr(), self.n_alive.data_ptr(), st)
+                check(rc, "head_composite_chunk")
+        else:
+            with span("field_head_forward", B=B):
+                rc = lib.sanerf_field_head_forward(L["x01"].data_ptr(), g.embeddings.data_ptr(), g.offsets.data_ptr(), S, H, None,
+                                                   w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), B, None, None, None,
+                                                   self.head.data_ptr(), self.precision, st)
+            check(rc, "field_head_forward")
+            with span("head_composite_forward", N=N, T=T):
+                rc = lib.sanerf_head_composite_forward(self.head.data_ptr(), L["deltas"].data_ptr(), L["t_mid"].data_ptr(), N, T,
+                                                       self.opaque, float(m.t_thresh), None, L["weights"].data_ptr(),
+                                                       L["ws"].data_ptr(), L["depth"].data_ptr(), self.geo_sum.data_ptr(),
+                                                       self.n_alive.data_ptr(), st)
+            check(rc, "head_composite_forward")
+        self._out_ws, self._out_depth = ws_buf, depth_buf
         v1, v2, v3 = (l.weight for l in m.view_mlp.net)
         with span("view_head", N=N):
-            rc = lib.sanerf_view_head(self.geo_sum.data_ptr(), L["ws"].data_ptr(), self.rays_d.data_ptr(), None, v1.data_ptr(),
+            rc = lib.sanerf_view_head(self.geo_sum.data_ptr(), ws_buf.data_ptr(), self.rays_d.data_ptr(), None, v1.data_ptr(),
                                       v2.data_ptr(), v3.data_ptr(), self.bg, 1.0, N, self.image.data_ptr(), None, None, None,
                                       None, None, None, st)
         check(rc, "view_head")
@@ -554,8 +594,7 @@ class FusedRGBFrame(FusedRGBStep):
             else:
                 self.eager_runs += 1
                 self._launch_render()
-        L = self.lv[2]
-        return {"image": self.image, "depth": L["depth"], "weights_sum": L["ws"], "n_alive": self.n_alive}
+        return {"image": self.image, "depth": self._out_depth, "weights_sum": self._out_ws, "n_alive": self.n_alive}
 
 
 class FusedSAMStep:
@@ -586,7 +625,7 @@ class FusedSAMStep:
         if h * w != n_rays:
             raise UnsupportedConfig("FusedSAMStep renders one h x w feature map per step")
         self.model, self.optimizer, self.world_size = model, optimizer, world_size
-        self.frame = FusedRGBFrame(model, n_rays, use_graph=False, bg_color=1.0)      # launched inside this step's graph
+        self.frame = FusedRGBFrame(model, n_rays, use_graph=False, bg_color=1.0, chunked=False)      # launched inside this step's graph
         self.N, self.h, self.w = int(n_rays), int(h), int(w)
         self.use_graph = bool(use_graph)
         dev = self.dev = self.frame.dev

@@ -225,3 +225,38 @@ def test_fused_sam_step_graph_replay_equals_autograd_steps(cuda):
     assert True in ta._plans[(h * w, h, w, tuple(target.shape))].graphs
     for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
+
+
+def test_chunked_frame_with_termination_matches_unchunked(cuda):
+    """Early ray termination that skips work (front-to-back chunks of 8 samples, device-side live-ray lists) == the
+    un-chunked frame with the same threshold (same rule): image, depth, weights_sum, and the alive counts
+    exactly; with threshold ~0 it reproduces the frame without termination."""
+    from nerf.network import NeRFNetwork
+    from sanerf_b200.step import FusedRGBFrame
+    from sanerf_b200.train import default_opt
+    torch.manual_seed(2)
+    model = NeRFNetwork(default_opt()).cuda().eval()
+    with torch.no_grad():
+        for enc in [model.grid, *model.prop_encoders]:
+            enc.embeddings.uniform_(-0.5, 0.5)
+        model.grid_mlp.net[2].weight[0].mul_(6.0).add_(0.3)          # strong densities: most rays terminate inside the 32 samples
+    g = torch.Generator().manual_seed(9)
+    n = 3000
+    o = (torch.rand(n, 3, generator=g) - 0.5).cuda()
+    d = torch.randn(n, 3, generator=g).cuda()
+    for thresh in (1e-2, 1e-4, 1e-30):
+        model.t_thresh = thresh
+        ref = {k: v.clone() for k, v in FusedRGBFrame(model, n, chunked=False)(o, d).items()}
+        plan = FusedRGBFrame(model, n, chunked=True)
+        for _ in range(3):                                           # eager, capture, replay
+            out = plan(o, d)
+            torch.testing.assert_close(out["image"], ref["image"], rtol=1e-5, atol=2e-6)
+            torch.testing.assert_close(out["depth"], ref["depth"], rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(out["weights_sum"], ref["weights_sum"], rtol=1e-5, atol=2e-6)
+            same = (out["n_alive"] == ref["n_alive"]).float().mean().item()
+            assert same > 0.999, same                                # prefix sums associate differently: ties at the threshold only
+        if thresh == 1e-2:
+            assert float(ref["n_alive"].float().mean()) < 28         # the scene really terminates rays
+        live = plan.counts[1:plan.n_chunks].tolist()
+        assert all(a >= b for a, b in zip([n] + live, live)), live   # live-ray lists shrink front to back
+    model.t_thresh = 0.0
