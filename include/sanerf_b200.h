@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 24
+#define SANERF_ABI_VERSION 25
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -110,11 +110,18 @@ SANERF_API int sanerf_grad_weight_decay(const void* embeddings, void* grad, cons
  */
 SANERF_API int sanerf_ray_features_forward(const float* x01, const float* weights, const float* embeddings,
                                 const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
-                                uint32_t H, float* out, void* stream);
+                                uint32_t H, float* out, uint32_t out_stride, void* stream);
 SANERF_API int sanerf_ray_features_backward(const float* x01, const float* weights, const float* g_out,
                                  const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
                                  uint32_t H, float* grad_embeddings, uint32_t level_begin, uint32_t level_end,
-                                 void* stream);
+                                 uint32_t g_stride, void* stream);
+/* out_stride / g_stride: floats between consecutive rays of out / g_out (0 = L*C; otherwise >= L*C and a multiple of 4), so
+ * that the features can be written straight into - and their gradient read straight from - the wider input row of the
+ * samvit head (renderer.py:380) without a concatenation copy.
+ * sanerf_sam_pack writes the rest of that row: out[r, 0..] = [geo_sum (15), weights_sum * SH4(normalised rays_d) (16, only
+ * when use_view_direction), image (3), depth (1)], rows out_stride floats apart. */
+SANERF_API int sanerf_sam_pack(const float* geo_sum, const float* weights_sum, const float* rays_d, const float* image,
+                    const float* depth, uint32_t N, int use_view_direction, float* out, uint32_t out_stride, void* stream);
 
 /* Debug / parity entry point (no reference equivalent — SURVEY §8 c7): for every sample,
  * level < L and corner < 2^D write the table row (relative to the level's offset) the

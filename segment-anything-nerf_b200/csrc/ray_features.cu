@@ -34,6 +34,7 @@ struct RayFeatParams {
     uint32_t N, T, L, H;
     float S;
     uint32_t level_begin, level_end;   // backward: levels [level_begin, level_end) of this launch (forward: all)
+    uint32_t row_stride;               // floats between consecutive rays of out / g_out (>= L*C, multiple of 4)
 };
 
 constexpr uint32_t kRayWarps = 8;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) ray_features_forward_kernel(co
     }
 #pragma unroll
     for (uint32_t c = 0; c < C; ++c) sum[c] = warp_sum(sum[c]);
-    if (lane == 0) RowIO<float, C>::store(p.out + ((size_t)ray * p.L + level) * C, sum);
+    if (lane == 0) RowIO<float, C>::store(p.out + (size_t)ray * p.row_stride + level * C, sum);
 }
 
 template <uint32_t C>
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) ray_features_backward_kernel(c
     const uint32_t ray = blockIdx.x * kRayWarps + warp, level = p.level_begin + blockIdx.y;
     if (ray >= p.N) return;
     float g[C];
-    RowIO<float, C>::load(p.g_out + ((size_t)ray * p.L + level) * C, g);     // same address in every lane: one broadcast
+    RowIO<float, C>::load(p.g_out + (size_t)ray * p.row_stride + level * C, g);     // same address in every lane: one broadcast
     bool any = false;
 #pragma unroll
     for (uint32_t c = 0; c < C; ++c) any |= (g[c] != 0.0f);
@@ -154,21 +155,23 @@ using namespace sanerf;
 
 extern "C" int sanerf_ray_features_forward(const float* x01, const float* weights, const float* embeddings,
                                            const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
-                                           uint32_t H, float* out, void* stream) {
+                                           uint32_t H, float* out, uint32_t out_stride, void* stream) {
     if (N == 0) return SANERF_OK;
     SANERF_REQUIRE_PTR(x01);
     SANERF_REQUIRE_PTR(weights);
     SANERF_REQUIRE_PTR(embeddings);
     SANERF_REQUIRE_PTR(offsets);
     SANERF_REQUIRE_PTR(out);
-    RayFeatParams p{x01, weights, embeddings, nullptr, offsets, out, nullptr, N, T, L, H, S, 0u, L};
+    if (out_stride == 0) out_stride = L * C;
+    if (out_stride < L * C || (out_stride & 3u)) return fail(SANERF_ERR_INVALID_ARG, "ray_features: row stride must be >= L*C and a multiple of 4");
+    RayFeatParams p{x01, weights, embeddings, nullptr, offsets, out, nullptr, N, T, L, H, S, 0u, L, out_stride};
     return launch_ray_features<false>(p, C, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sanerf_ray_features_backward(const float* x01, const float* weights, const float* g_out,
                                             const int32_t* offsets, uint32_t N, uint32_t T, uint32_t C, uint32_t L, float S,
                                             uint32_t H, float* grad_embeddings, uint32_t level_begin, uint32_t level_end,
-                                            void* stream) {
+                                            uint32_t g_stride, void* stream) {
     if (level_end > L) level_end = L;
     if (N == 0 || level_begin >= level_end) return SANERF_OK;
     SANERF_REQUIRE_PTR(x01);
@@ -176,6 +179,8 @@ extern "C" int sanerf_ray_features_backward(const float* x01, const float* weigh
     SANERF_REQUIRE_PTR(g_out);
     SANERF_REQUIRE_PTR(offsets);
     SANERF_REQUIRE_PTR(grad_embeddings);
-    RayFeatParams p{x01, weights, nullptr, g_out, offsets, nullptr, grad_embeddings, N, T, L, H, S, level_begin, level_end};
+    if (g_stride == 0) g_stride = L * C;
+    if (g_stride < L * C || (g_stride & 3u)) return fail(SANERF_ERR_INVALID_ARG, "ray_features: row stride must be >= L*C and a multiple of 4");
+    RayFeatParams p{x01, weights, nullptr, g_out, offsets, nullptr, grad_embeddings, N, T, L, H, S, level_begin, level_end, g_stride};
     return launch_ray_features<true>(p, C, static_cast<cudaStream_t>(stream));
 }

@@ -349,6 +349,33 @@ __global__ void __launch_bounds__(vt::kThreads) view_head_train_kernel(const Vie
     }
 }
 
+// Tail of the samvit head's input row (renderer.py:380 / :383): f[r] = [f_sam (written by ray_features_forward), f_image or
+// geo_sum, image, depth].  f_image = [geo_sum (15), weights_sum * SH4(d) (16)] with the same normalisation + SH evaluation as
+// view_head_kernel.  One thread per ray; replaces torch.cat + the broadcast multiply + a separate SH launch.
+__global__ void __launch_bounds__(128) sam_pack_kernel(const float* __restrict__ geo_sum, const float* __restrict__ weights_sum,
+                                                       const float* __restrict__ rays_d, const float* __restrict__ image,
+                                                       const float* __restrict__ depth, uint32_t N, int use_view_direction,
+                                                       float* __restrict__ out, uint32_t out_stride) {
+    pdl_begin();
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    float* dst = out + (size_t)r * out_stride;
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < 15; ++i) dst[c++] = __ldg(geo_sum + (size_t)r * 15 + i);
+    if (use_view_direction) {
+        float x = __ldg(rays_d + (size_t)r * 3), y = __ldg(rays_d + (size_t)r * 3 + 1), z = __ldg(rays_d + (size_t)r * 3 + 2);
+        const float n = sqrtf(x * x + y * y + z * z);
+        x /= n; y /= n; z /= n;
+        float sh[16];
+        sh_eval<4, false>(x, y, z, sh, nullptr);
+        const float ws = __ldg(weights_sum + r);
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) dst[c++] = ws * sh[i];
+    }
+    for (uint32_t i = 0; i < 3; ++i) dst[c++] = __ldg(image + (size_t)r * 3 + i);
+    dst[c] = __ldg(depth + r);
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -375,4 +402,15 @@ extern "C" int sanerf_view_head(const float* geo_sum, const float* weights_sum, 
     }
     else SANERF_LAUNCH((view_head_kernel<false>), blocks, vh::kRays, vh::kSmemFwd, st, p);
     return check_launch("view_head_kernel");
+}
+
+extern "C" int sanerf_sam_pack(const float* geo_sum, const float* weights_sum, const float* rays_d, const float* image,
+                               const float* depth, uint32_t N, int use_view_direction, float* out, uint32_t out_stride,
+                               void* stream) {
+    if (N == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(geo_sum); SANERF_REQUIRE_PTR(weights_sum); SANERF_REQUIRE_PTR(rays_d); SANERF_REQUIRE_PTR(image);
+    SANERF_REQUIRE_PTR(depth); SANERF_REQUIRE_PTR(out);
+    SANERF_LAUNCH(sam_pack_kernel, div_up(N, 128u), 128, 0, static_cast<cudaStream_t>(stream), geo_sum, weights_sum, rays_d, image,
+                  depth, N, use_view_direction, out, out_stride);
+    return check_launch("sam_pack_kernel");
 }

@@ -16,7 +16,7 @@ _HEADER = os.path.join(os.path.dirname(_PKG_DIR), "include", "sanerf_b200.h")
 
 SANERF_F32, SANERF_F16 = 0, 1
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
-ABI_VERSION = 24
+ABI_VERSION = 25
 
 c_void_p, c_int, c_u32, c_u64, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                           ctypes.c_uint64, ctypes.c_float)
@@ -38,9 +38,10 @@ _SIGNATURES = {
     "sanerf_grid_dump_indices": [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_float, c_u32,
                                  c_u32, c_int, c_void_p],
     "sanerf_ray_features_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_float, c_u32,
-                                    c_void_p, c_void_p],
+                                    c_void_p, c_u32, c_void_p],
     "sanerf_ray_features_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_float, c_u32,
-                                     c_void_p, c_u32, c_u32, c_void_p],
+                                     c_void_p, c_u32, c_u32, c_u32, c_void_p],
+    "sanerf_sam_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_int, c_void_p, c_u32, c_void_p],
     "sanerf_sh_encode_forward": [c_void_p, c_void_p, c_u32, c_u32, c_u32, c_void_p, c_u32, c_void_p],
     "sanerf_sh_encode_backward": [c_void_p, c_void_p, c_u32, c_u32, c_u32, c_void_p, c_void_p, c_void_p],
     "sanerf_freq_encode_forward": [c_void_p, c_u32, c_u32, c_u32, c_u32, c_void_p, c_void_p],

@@ -317,7 +317,7 @@ class _RayFeatures(Function):
         out = torch.empty(N, L * C, device=table.device, dtype=torch.float32)
         with _lib.stats.span("ray_features_forward", N=N, T=T, C=C):
             rc = _lib.load().sanerf_ray_features_forward(x01.data_ptr(), weights.data_ptr(), table.data_ptr(),
-                                                         offsets.data_ptr(), N, T, C, L, S, H, out.data_ptr(), _stream(table))
+                                                         offsets.data_ptr(), N, T, C, L, S, H, out.data_ptr(), 0, _stream(table))
         _lib.check(rc, "ray_features_forward")
         ctx.save_for_backward(x01, weights, offsets)
         ctx.meta = (N, T, C, L, S, H, tuple(table.shape))
@@ -331,7 +331,7 @@ class _RayFeatures(Function):
         g_out = g_out.contiguous().float()
         with _lib.stats.span("ray_features_backward", N=N, T=T, C=C):
             rc = _lib.load().sanerf_ray_features_backward(x01.data_ptr(), weights.data_ptr(), g_out.data_ptr(),
-                                                          offsets.data_ptr(), N, T, C, L, S, H, g_table.data_ptr(), 0, L,
+                                                          offsets.data_ptr(), N, T, C, L, S, H, g_table.data_ptr(), 0, L, 0,
                                                           _stream(g_out))
         _lib.check(rc, "ray_features_backward")
         return None, None, g_table, None, None, None
@@ -450,6 +450,103 @@ def layernorm_mse(x, ln, target_map, loss, y_out=None):
                                               g_x.data_ptr(), ln.weight.grad.data_ptr(), ln.bias.grad.data_ptr(), _stream(x))
     _lib.check(rc, "layernorm_mse")
     return g_x
+
+
+class SamvitHead:
+    """The samvit head of the stage-2 step (network.py:120-123: SkipConnMLP 163 -> 256 x 4 -> 256 with the input re-joined at
+    layer 2, then LayerNorm) as an autograd-free plan on STATIC buffers: no concatenation, no contiguous() copies, no
+    additions and no allocations inside the captured step.
+
+    Layout trick: one [M, 420] buffer ``skip`` holds layer 1's output in columns 0..255 and the head's INPUT in columns
+    256..418 (column 419 pads the row to a 16-byte multiple), so the skip layer's 419-wide input exists without a copy:
+    ``ray_features_forward`` writes the 128 feature columns and ``sanerf_sam_pack`` the other 35 straight into it.  The
+    backward mirrors it with ``dskip``: the skip layer's data gradient lands there, its first 256 columns feed layer 1's
+    backward as a strided operand, and layer 0's data gradient is ACCUMULATED onto columns 256..383 by the GEMM's reducing
+    epilogue — which leaves d loss / d f_sam exactly where ``ray_features_backward`` reads it (row stride 420)."""
+
+    WIDTH, IN, LD = 256, 163, 420
+
+    def __init__(self, mlp, ln, M, device):
+        net = mlp.net
+        ok = (len(net) == 5 and list(mlp.skip_layers) == [2] and net[0].in_features == self.IN
+              and all(l.out_features == self.WIDTH for l in net) and net[2].in_features == self.WIDTH + self.IN
+              and all(l.bias is not None for l in net) and isinstance(ln, torch.nn.LayerNorm)
+              and tuple(ln.normalized_shape) == (self.WIDTH,) and ln.elementwise_affine)
+        if not ok:
+            raise ValueError("SamvitHead covers the reference's samvit_mlp (163 -> 256 x 5, skip at layer 2, LayerNorm(256))")
+        self.mlp, self.ln, self.M = mlp, ln, int(M)
+        f32 = dict(device=device, dtype=torch.float32)
+        W = self.WIDTH
+        self.skip = torch.zeros(M, self.LD, **f32)
+        self.dskip = torch.zeros(M, self.LD, **f32)
+        self.f = self.skip[:, W:W + self.IN]                        # the head's input row (strided view)
+        self.h0, self.h2, self.h3, self.out, self.samvit = (torch.empty(M, W, **f32) for _ in range(5))
+        self.g_out, self.g3, self.g2, self.g0 = (torch.empty(M, W, **f32) for _ in range(4))
+        self.precision = PRECISION_IDS[mlp.precision]
+
+    def forward(self):
+        """skip[:, 256:419] (filled by the caller) -> out [M, 256] (pre-LayerNorm)."""
+        net, W, M, pr = self.mlp.net, self.WIDTH, self.M, self.precision
+        w = [l.weight.detach() for l in net]
+        b = [l.bias.detach() for l in net]
+        gemm_tc(self.f, w[0], self.h0, M, W, self.IN, bias=b[0], act=True, precision=pr)
+        gemm_tc(self.h0, w[1], self.skip, M, W, W, bias=b[1], act=True, precision=pr)             # -> skip[:, :256]
+        gemm_tc(self.skip, w[2], self.h2, M, W, W + self.IN, bias=b[2], act=True, precision=pr)   # 419-wide input, no concat
+        gemm_tc(self.h2, w[3], self.h3, M, W, W, bias=b[3], act=True, precision=pr)
+        gemm_tc(self.h3, w[4], self.out, M, W, W, bias=b[4], act=False, precision=pr)
+        return self.out
+
+    def loss_backward(self, target_map, loss):
+        """LayerNorm + MSE forward / backward (one kernel): loss accumulated, ln gradients accumulated, g_out filled."""
+        M, N = self.out.shape
+        hw = target_map.shape[-2] * target_map.shape[-1]
+        if hw != M or target_map.shape[1] != N or not target_map.is_contiguous():
+            raise RuntimeError("SamvitHead needs a contiguous [1, 256, h, w] target with h*w rows")
+        ln = self.ln
+        with _lib.stats.span("layernorm_mse", M=M):
+            rc = _lib.load().sanerf_layernorm_mse(self.out.data_ptr(), ln.weight.data_ptr(), ln.bias.data_ptr(), float(ln.eps),
+                                                  target_map.data_ptr(), 1, hw, M, N, self.samvit.data_ptr(), loss.data_ptr(),
+                                                  self.g_out.data_ptr(), ln.weight.grad.data_ptr(), ln.bias.grad.data_ptr(),
+                                                  _stream(self.out))
+        _lib.check(rc, "layernorm_mse")
+
+    def backward(self, side_stream, n_feat, slope=0.01, k_splits=16):
+        """g_out -> weight / bias gradients ACCUMULATED into the parameters' .grad (flat views), and d loss / d f[:, :n_feat]
+        returned as a view of ``dskip`` (row stride 420).  The weight-gradient GEMMs and bias column sums run on
+        ``side_stream`` beside the dependent chain of data-gradient GEMMs; the CALLER joins the side stream."""
+        net, W, M, pr = self.mlp.net, self.WIDTH, self.M, self.precision
+        w = [l.weight.detach() for l in net]
+        gw = [l.weight.grad for l in net]
+        gb = [l.bias.grad for l in net]
+        lib = _lib.load()
+        main = torch.cuda.current_stream(self.out.device)
+        inputs = [self.f, self.h0, self.skip, self.h2, self.h3]
+        in_cols = [self.IN, W, W + self.IN, W, W]
+        g1 = self.dskip[:, :W]                                      # gradient w.r.t. layer 1's output (strided)
+
+        def weight_grad(i, g):
+            side_stream.wait_stream(main)                           # g is complete
+            with torch.cuda.stream(side_stream):
+                gemm_tc(g, inputs[i], gw[i], W, in_cols[i], M, a_trans=True, b_trans=True, k_splits=k_splits, epilogue=2,
+                        precision=pr)
+                with _lib.stats.span("colsum_add", M=M, N=W):
+                    rc = lib.sanerf_colsum_add(g.data_ptr(), g.stride(0), M, W, gb[i].data_ptr(), _stream(g))
+                _lib.check(rc, "colsum_add")
+
+        weight_grad(4, self.g_out)
+        gemm_tc(self.g_out, w[4], self.g3, M, W, W, b_trans=True, epilogue=1, mask=self.h3, mask_cols=W, slope=slope, precision=pr)
+        weight_grad(3, self.g3)
+        gemm_tc(self.g3, w[3], self.g2, M, W, W, b_trans=True, epilogue=1, mask=self.h2, mask_cols=W, slope=slope, precision=pr)
+        weight_grad(2, self.g2)
+        # skip layer: [M, 419] data gradient; the first 256 columns pass through layer 1's leaky-ReLU derivative
+        gemm_tc(self.g2, w[2], self.dskip, M, W + self.IN, W, b_trans=True, epilogue=1, mask=self.skip, mask_cols=W, slope=slope,
+                precision=pr)
+        weight_grad(1, g1)
+        gemm_tc(g1, w[1], self.g0, M, W, W, b_trans=True, epilogue=1, mask=self.h0, mask_cols=W, slope=slope, precision=pr)
+        weight_grad(0, self.g0)
+        g_feat = self.dskip[:, W:W + n_feat]                        # holds the skip path's share already
+        gemm_tc(self.g0, w[0], g_feat, M, n_feat, W, b_trans=True, epilogue=2, precision=pr)      # += layer 0's share
+        return g_feat
 
 
 class _SkipMLP(Function):

@@ -646,6 +646,16 @@ class FusedSAMStep:
         if a != 0 or g.embeddings.grad is None or not g.embeddings.grad.is_contiguous():
             raise RuntimeError("FusedSAMStep needs s_grid.embeddings to lead a FusedAdam flat buffer")
         self._head_params = [p for p in model.samvit_mlp.parameters()]
+        # the autograd-free samvit head (static buffers), when the model is the reference's configuration on the tensor cores
+        mlp, ln = model.samvit_mlp[0], model.samvit_mlp[1]
+        self.head = None
+        feat_ok = g.num_levels * g.level_dim == 128 and (opt.sam_use_view_direction or False)
+        if (getattr(mlp, "tc", False) and feat_ok and tuple(target_shape[-2:]) == (self.h, self.w)
+                and all(p.grad is not None for p in self._head_params) and not torch.is_autocast_enabled()):
+            try:
+                self.head = fused.SamvitHead(mlp, ln, self.N, dev)
+            except ValueError:
+                self.head = None
 
     def _main_range(self):
         return self.optimizer.ranges[id(self.model.s_grid.embeddings)]
@@ -655,7 +665,8 @@ class FusedSAMStep:
         """Frozen stage-1 forward: nothing here reads s_grid."""
         with torch.no_grad():
             self.frame._launch_render()
-            self.sh = self.model.view_encoder(self.frame.rays_d)                      # [N,16], once per ray
+            if self.head is None:
+                self.sh = self.model.view_encoder(self.frame.rays_d)                  # [N,16], once per ray
 
     def _launch_back(self):
         m, lib, N, fr = self.model, _lib.load(), self.N, self.frame
@@ -665,35 +676,38 @@ class FusedSAMStep:
         g = m.s_grid
         S, H, C, nl = float(np.log2(g.per_level_scale)), int(g.base_resolution), int(g.level_dim), int(g.num_levels)
         st = _lib.current_stream(self.dev)
-        with span("ray_features_forward", N=N, T=T, C=C):
-            rc = lib.sanerf_ray_features_forward(L["x01"].data_ptr(), L["weights"].data_ptr(), g.embeddings.data_ptr(),
-                                                 g.offsets.data_ptr(), N, T, C, nl, S, H, self.f_sam.data_ptr(), st)
-        check(rc, "ray_features_forward")
         ws, depth = L["ws"], L["depth"]
-        if m.opt.sam_use_view_direction:                                             # renderer.py:380 / :383
-            parts = [self.f_sam, fr.geo_sum, ws.unsqueeze(-1) * self.sh, fr.image, depth.unsqueeze(-1)]
+        head = self.head
+        if head is not None:
+            # samvit head without autograd and without torch glue kernels: the features and the rest of the input row are
+            # written straight into the head's skip buffer (fused.SamvitHead), five tensor-core GEMMs forward, LayerNorm +
+            # MSE forward/backward in one kernel, per layer a weight-gradient GEMM reducing into the flat gradient views + a
+            # column sum (bias) on the side stream and a data-gradient GEMM with the activation derivative in its epilogue
+            with span("ray_features_forward", N=N, T=T, C=C):
+                rc = lib.sanerf_ray_features_forward(L["x01"].data_ptr(), L["weights"].data_ptr(), g.embeddings.data_ptr(),
+                                                     g.offsets.data_ptr(), N, T, C, nl, S, H, head.f.data_ptr(), head.LD, st)
+            check(rc, "ray_features_forward")
+            with span("sam_pack", N=N):
+                rc = lib.sanerf_sam_pack(fr.geo_sum.data_ptr(), ws.data_ptr(), fr.rays_d.data_ptr(), fr.image.data_ptr(),
+                                         depth.data_ptr(), N, int(bool(m.opt.sam_use_view_direction)),
+                                         head.f.data_ptr() + 4 * nl * C, head.LD, st)
+            check(rc, "sam_pack")
+            head.forward()
+            self._clear_loss()
+            head.loss_backward(self.target, self.loss)
+            g_sam = head.backward(self.side_stream, nl * C)
+            g_stride = head.LD
+            self.samvit, self.last_f = head.samvit, head.f
         else:
-            parts = [self.f_sam, fr.geo_sum, fr.image, depth.unsqueeze(-1)]
-        mlp, ln = m.samvit_mlp[0], m.samvit_mlp[1]
-        f = torch.cat(parts, dim=-1)
-        direct = (getattr(mlp, "tc", False) and fused.skip_mlp_supported(mlp, f) and mlp.net[0].bias is not None
-                  and tuple(self.target.shape[-2:]) == (self.h, self.w) and isinstance(ln, torch.nn.LayerNorm)
-                  and tuple(ln.normalized_shape) == (256,) and ln.elementwise_affine and ln.weight.grad is not None)
-        if direct:
-            # samvit head without autograd: five tensor-core GEMMs forward (bias + leaky ReLU in the epilogue), LayerNorm +
-            # MSE forward/backward in one kernel, then per layer a weight-gradient GEMM reducing straight into the flat
-            # gradient views, a column sum (bias) and a data-gradient GEMM with the activation derivative in its epilogue
-            prec = PRECISION_IDS[mlp.precision]
-            weights = [l.weight.detach() for l in mlp.net]
-            out, inputs = fused.skip_mlp_forward(f, weights, [l.bias.detach() for l in mlp.net], mlp.skip_layers, prec)
-            self.samvit = torch.empty_like(out)
-            self.loss.zero_()
-            g_out = fused.layernorm_mse(out, ln, self.target, self.loss, self.samvit)
-            g_sam, keep = fused.skip_mlp_backward(g_out, inputs, weights, mlp.skip_layers,
-                                                  [l.weight.grad for l in mlp.net], [l.bias.grad for l in mlp.net], prec,
-                                                  input_cols=nl * C, side_stream=self.side_stream, join=False)
-            self.last_f = f
-        else:
+            with span("ray_features_forward", N=N, T=T, C=C):
+                rc = lib.sanerf_ray_features_forward(L["x01"].data_ptr(), L["weights"].data_ptr(), g.embeddings.data_ptr(),
+                                                     g.offsets.data_ptr(), N, T, C, nl, S, H, self.f_sam.data_ptr(), 0, st)
+            check(rc, "ray_features_forward")
+            if m.opt.sam_use_view_direction:                                         # renderer.py:380 / :383
+                parts = [self.f_sam, fr.geo_sum, ws.unsqueeze(-1) * self.sh, fr.image, depth.unsqueeze(-1)]
+            else:
+                parts = [self.f_sam, fr.geo_sum, fr.image, depth.unsqueeze(-1)]
+            f = torch.cat(parts, dim=-1)
             f.requires_grad_(True)
             with torch.enable_grad():
                 samvit = m.samvit_mlp(f)
@@ -705,14 +719,21 @@ class FusedSAMStep:
             self.loss.copy_(loss.detach().reshape(1))
             self.last_f, self.samvit = f.detach(), samvit.detach()
             g_sam = f.grad[:, :nl * C].contiguous()
+            g_stride = 0
         st = _lib.current_stream(self.dev)
         with span("ray_features_backward", N=N, T=T, C=C):
             rc = lib.sanerf_ray_features_backward(L["x01"].data_ptr(), L["weights"].data_ptr(), g_sam.data_ptr(),
-                                                  g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), 0, nl, st)
+                                                  g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), 0, nl,
+                                                  g_stride, st)
         check(rc, "ray_features_backward")
-        if direct:                                         # weight-gradient GEMMs ran beside the data-gradient chain + scatter
+        if head is not None:                               # weight-gradient GEMMs ran beside the data-gradient chain + scatter
             torch.cuda.current_stream(self.dev).wait_stream(self.side_stream)
-            del keep
+
+    def _clear_loss(self):
+        with _lib.stats.span("clear_loss"):
+            rc = _lib.load().sanerf_uniform_fill(self.loss.data_ptr(), 0, 0, self.frame.rng_state.data_ptr(), self.loss.data_ptr(), 1,
+                                                 _lib.current_stream(self.dev))
+        _lib.check(rc, "clear_loss")
 
     # ---- optimizer ----------------------------------------------------------------------------------------
     def _update_main(self):

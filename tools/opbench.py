@@ -133,10 +133,10 @@ st = _lib.current_stream(dev)
 rf_bytes = Nr * Tr * (16 + 16 * 8 * 8 * 4) + Nr * 128 * 4
 report("ray features forward (encode + weighted ray sum)", "SAM grid L16 F8 T2^19, 4096 rays x 32, ray-ordered",
        timeit(lambda: _lib.check(lib.sanerf_ray_features_forward(xr.data_ptr(), wr.data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
-                                                                 Nr, Tr, 8, 16, S, H, f_out.data_ptr(), st), "rf")), rf_bytes)
+                                                                 Nr, Tr, 8, 16, S, H, f_out.data_ptr(), 0, st), "rf")), rf_bytes)
 report("ray features backward (factorised-gradient scatter)", "SAM grid L16 F8 T2^19, 4096 rays x 32, ray-ordered",
        timeit(lambda: _lib.check(lib.sanerf_ray_features_backward(xr.data_ptr(), wr.data_ptr(), g_ray.data_ptr(), enc.offsets.data_ptr(),
-                                                                  Nr, Tr, 8, 16, S, H, g_tab.data_ptr(), 0, 16, st), "rb")), rf_bytes)
+                                                                  Nr, Tr, 8, 16, S, H, g_tab.data_ptr(), 0, 16, 0, st), "rb")), rf_bytes)
 del enc, g_tab
 Mg = 4096
 for name, (N_, K_, kw) in {"forward layer 4096x256x256 (bias + leaky ReLU)": (256, 256, dict(act=True)),
