@@ -636,6 +636,8 @@ class FusedSAMStep:
         self.loss = torch.zeros(1, **f32)
         self.update_stream = torch.cuda.Stream(dev, priority=_update_priority(world_size))
         self.side_stream = torch.cuda.Stream(dev)          # weight-gradient GEMMs of the samvit head
+        self.copy_stream = torch.cuda.Stream(dev)          # upload of a host target beside the frozen front
+        self.copy_done = torch.cuda.Event()
         self.critical_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("SANERF_CRIT_PRIO", -1)))
         self.pending_main = False
         self.sharded_update = True
@@ -801,24 +803,64 @@ class FusedSAMStep:
             self._launch_back()
         return self.loss[0]
 
+    def _front_half(self):
+        """deferred s_grid update || frozen stage-1 forward (nothing here reads the target feature map)."""
+        def body():
+            main, upd = self._deferred_update()
+            self._launch_front()
+            main.wait_stream(upd)
+        _critical(self, body)
+
+    def _back_half(self):
+        def body():
+            self._launch_back()
+            self._update_rest()
+        _critical(self, body)
+
     def __call__(self, rays_o, rays_d, target):
-        """One training step; inputs may live on the host (pinned) or the device.  Returns the loss (static buffer)."""
+        """One training step; inputs may live on the host (pinned) or the device.  Returns the loss (static buffer).
+        A HOST target ([1,256,h,w]: 4 MB at 64 x 64) is uploaded on a copy stream while the frozen front runs — the step is
+        then replayed as two graphs around the wait for that copy; a device target is copied in stream order and the step
+        is one graph."""
         fr = self.frame
         fr.rays_o.copy_(rays_o, non_blocking=True)
         fr.rays_d.copy_(rays_d, non_blocking=True)
-        self.target.copy_(target, non_blocking=True)
+        cur = torch.cuda.current_stream(self.dev)
+        split = (not target.is_cuda) and self.use_graph and self.eager_runs >= 1 and \
+            (self.world_size == 1 or self.optimizer.symm is not None)
+        if split:
+            cs = self.copy_stream
+            cs.wait_stream(cur)                            # the previous step has finished reading self.target
+            with torch.cuda.stream(cs):
+                self.target.copy_(target, non_blocking=True)
+                self.copy_done.record(cs)
+        else:
+            self.target.copy_(target, non_blocking=True)
         with torch.cuda.device(self.dev):
             if not self.use_graph or self.eager_runs < 1:
                 self.eager_runs += 1
                 self._whole_step()
             elif self.world_size == 1 or self.optimizer.symm is not None:
-                mode = bool(self.model.training)
-                if mode not in self.graphs:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._whole_step()
-                    self.graphs[mode] = (g,)
-                self.graphs[mode][0].replay()
+                key = (bool(self.model.training), split)
+                if key not in self.graphs:
+                    if split:
+                        gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gf):
+                            self._front_half()
+                        with torch.cuda.graph(gb):
+                            self._back_half()
+                        self.graphs[key] = (gf, gb)
+                    else:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._whole_step()
+                        self.graphs[key] = (g,)
+                if split:
+                    self.graphs[key][0].replay()
+                    cur.wait_event(self.copy_done)
+                    self.graphs[key][1].replay()
+                else:
+                    self.graphs[key][0].replay()
             else:
                 mode = bool(self.model.training)
                 if mode not in self.graphs:

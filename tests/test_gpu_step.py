@@ -221,8 +221,13 @@ def test_fused_sam_step_graph_replay_equals_autograd_steps(cuda):
     for _ in range(4):
         la, lb = ta.step(o, d, target, h, w).clone(), tb.step(o, d, target, h, w).clone()
         torch.testing.assert_close(la, lb, rtol=2e-4, atol=1e-6)
+    host_target = target.cpu().pin_memory()                 # a host target: uploaded beside the frozen front, two graphs
+    for _ in range(2):
+        la, lb = ta.step(o, d, host_target, h, w).clone(), tb.step(o, d, target, h, w).clone()
+        torch.testing.assert_close(la, lb, rtol=2e-4, atol=1e-6)
+    assert (True, True) in ta._plans[(h * w, h, w, tuple(target.shape))].graphs
     ta.flush()
-    assert True in ta._plans[(h * w, h, w, tuple(target.shape))].graphs
+    assert (True, False) in ta._plans[(h * w, h, w, tuple(target.shape))].graphs
     for (n, p), (_, q) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert ((p - q).norm() / q.norm().clamp_min(1e-12)).item() < 1e-3, n
 
