@@ -261,6 +261,19 @@ def _span_table(spans):
     return [(name, dict(kv), c, s / c) for (name, kv), (c, s) in acc.items()]
 
 
+L2_PEAK_GBS = 6300 * 1.965          # LTS throughput cap ~6300 B/clk full chip (B300_MICROARCH.md) at 1965 MHz = 12.4 TB/s
+
+
+def _l2_roofline(lts_bytes, avg_ms):
+    """Second roofline of the gather: bytes the kernel moves through the L2 (ncu lts__t_sectors x 32, one capture per round,
+    profiles/) over the live launch time, against the LTS throughput cap."""
+    if not lts_bytes or not avg_ms:
+        return None
+    achieved = lts_bytes / (avg_ms * 1e-3) / 1e9
+    return {"lts_bytes_per_launch": lts_bytes, "achieved_gbs": achieved, "peak_gbs": L2_PEAK_GBS,
+            "peak_source": "B300_MICROARCH.md: LTS throughput cap ~6300 B/clk x 1965 MHz", "frac": achieved / L2_PEAK_GBS}
+
+
 def _span_ms(table, name, **match):
     for nm, info, _, ms in table:
         if nm == name and all(info.get(k) == v for k, v in match.items()):
@@ -353,6 +366,15 @@ def bench_rgb(ctx):
         if ms:
             kernels[name] = {"avg_ms": ms, "frac_strict": strict / (ms * 1e-3) / 1e9 / ctx.peak,
                              "frac_with_saved": (strict + extra) / (ms * 1e-3) / 1e9 / ctx.peak}
+    if "main_scatter" in kernels:
+        # second roofline of the scatter: red.global.add requests at ~1.29 clk per lane-request and SM (B300_MICROARCH.md,
+        # REDG spread) = 225 G/s on 148 SMs; ~25 M requests per launch (33.5 M corner updates, half of the x-pairs merged)
+        req = B_FINAL * 16 * 8 * 0.75
+        rate = 148 * 1.965e9 / 1.29
+        kernels["main_scatter"]["red_request_bound"] = {
+            "requests_per_launch": req, "peak_requests_per_s": rate, "bound_ms": req / rate * 1e3,
+            "frac": (req / rate * 1e3) / kernels["main_scatter"]["avg_ms"],
+            "note": "ncu: lts throughput 70.6 % of peak (profiles/r2_ncu_kernels.md); the L2 reduction rate, not HBM, binds"}
 
     line = {
         "metric": METRIC, "value": world * N_RAYS * args.steps / (total_ms / 1e3), "unit": "rays/s", "n_gpus": world,
@@ -374,7 +396,9 @@ def bench_rgb(ctx):
             "per sample", traffic=HEAD_FWD_NCU.get("dram_bytes"),
             frac_strict=hf["frac_strict"], frac_with_saved_activations=hf["frac_with_saved"],
             saved_bytes_per_sample=saved, lts_bytes=HEAD_FWD_NCU.get("lts_bytes"), ncu_source=HEAD_FWD_NCU.get("source"),
-            launches_timed=n_eager,
+            launches_timed=n_eager, l2=_l2_roofline(HEAD_FWD_NCU.get("lts_bytes"), hf["avg_ms"]),
+            binding="L2 -> L1 sector traffic: every 8-byte table row costs a 32-byte sector (ncu lts__t_sectors: 3.6x the "
+                    "algorithmic bytes), profiles/r2_ncu_kernels.md",
             timing="CUDA events around the kernel's launches in an eager replay of the same step after the timed region "
                    "(the timed region itself replays a CUDA graph)")
     line["kernels"] = kernels
