@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 25
+#define SANERF_ABI_VERSION 26
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -328,18 +328,23 @@ SANERF_API int sanerf_layernorm_mse(const float* x, const float* gamma, const fl
 /* ------------------------------------------------------------------------------------------
  * Fused Adam over one flat fp32 buffer (main.py:296 Adam(eps=1e-15), :312-313 LambdaLR 0.1^min(it/iters,1)).
  * sanerf_adam_schedule advances the device-side step counter and writes dyn[4] = {lr_t, 1-b1^t, 1-b2^t, 1-ema_t}
- * with ema_t = min(ema_decay, (1+t)/(10+t)) (torch_ema's warm-up, nerf/utils.py:616 with main.py:316 ema_decay=0.95);
+ * with ema_t = min(ema_decay, (1+t)/(10+t)) (torch_ema's warm-up, nerf/utils.py:616 with main.py:316 ema_decay=0.95; only
+ * used by the optional per-step EMA - the reference updates its EMA per epoch, see sanerf_ema_update);
  * when `gate` is given it is set to 1 ("the step starting now leaves a gradient for the deferred ranges").
  * sanerf_adam_step applies the update (gradient pre-multiplied by grad_scale, e.g. 1/world_size) and can zero
  * the gradient in the same pass; with `gate` != NULL it returns without touching anything when *gate == 0 (a deferred
  * range whose update was already applied by a flush); with `ema` != NULL (same length as params) it also performs
- * shadow -= (1-ema_t)*(shadow - param_new) in the same pass (nerf/utils.py:1862).  Both are CUDA-graph replayable.
+ * shadow -= (1-ema_t)*(shadow - param_new) in the same pass (per-step EMA; optional).  Both are CUDA-graph replayable.
  * ---------------------------------------------------------------------------------------- */
 SANERF_API int sanerf_adam_schedule(int32_t* step, float* dyn, float lr0, float beta1, float beta2,
                          float decay_iters, int32_t* gate, float ema_decay, void* stream);
 SANERF_API int sanerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint64_t n,
                      const float* dyn, float beta1, float beta2, float eps, float grad_scale,
                      int zero_grad, const int32_t* gate, float* ema, void* stream);
+/* torch_ema.ExponentialMovingAverage.update() over a flat buffer: shadow -= one_minus_decay * (shadow - params), with
+ * one_minus_decay = 1 - min(decay, (1 + k) / (10 + k)) for the k-th update.  The reference updates once per EPOCH
+ * (nerf/utils.py:1862) or per 16 GUI steps (:1627); passing `ema` to sanerf_adam_step instead updates per optimizer step. */
+SANERF_API int sanerf_ema_update(float* shadow, const float* params, uint64_t n, float one_minus_decay, void* stream);
 /* Half-precision table with an fp32 master copy (BASELINE configs[4], T = 2^22 fp16 parameters; the reference reaches
  * half tables through grid.py:43-46): grads16 [n] half (the scatter target / its reduce-scattered sum), master /
  * exp_avg / exp_avg_sq [n] fp32; the updated parameters are written to master AND, rounded, to params16 in one pass.

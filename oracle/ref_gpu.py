@@ -62,8 +62,9 @@ def ref_grid_cls(ext):
     return RefExtGridEncoder
 
 
-def reference_rgb_step(device, lr=1e-2, ema_decay=0.95):
-    """The stage-1 training step the reference runs on a GPU (nerf/utils.py:897-930, 1811-1836, 1862; main.py:296,316):
+def reference_rgb_step(device, lr=1e-2, ema_decay=None):
+    """The stage-1 training step the reference runs on a GPU (nerf/utils.py:897-930, 1811-1836; main.py:296; the EMA of
+    main.py:316 is updated once per epoch, nerf/utils.py:1862, so ``ema_decay`` is None unless a per-step variant is wanted):
     returns ``step(rays_o, rays_d, gt) -> None`` on a fresh random-init model, or raises FileNotFoundError when
     ``oracle/_ref`` is not built."""
     ext = build_ref.load("gridencoder")

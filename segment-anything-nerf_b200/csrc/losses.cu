@@ -325,6 +325,23 @@ __global__ void __launch_bounds__(256) uniform_fill_kernel(float* __restrict__ o
     }
 }
 
+// torch_ema.ExponentialMovingAverage.update(): shadow -= (1 - decay_t) * (shadow - param).  The reference calls it once per
+// EPOCH (nerf/utils.py:1862, after the loop of train_one_epoch) / once per 16 GUI steps (:1627), not per optimizer step.
+__global__ void __launch_bounds__(256) ema_update_kernel(float* __restrict__ shadow, const float* __restrict__ param, size_t n4,
+                                                         size_t n, float one_minus_decay) {
+    pdl_begin();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 e = __ldcs(reinterpret_cast<const float4*>(shadow) + i);
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(param) + i);
+        e.x -= one_minus_decay * (e.x - q.x); e.y -= one_minus_decay * (e.y - q.y);
+        e.z -= one_minus_decay * (e.z - q.z); e.w -= one_minus_decay * (e.w - q.w);
+        __stcs(reinterpret_cast<float4*>(shadow) + i, e);
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        shadow[i] -= one_minus_decay * (shadow[i] - param[i]);
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -407,4 +424,15 @@ extern "C" int sanerf_uniform_fill(float* out, uint64_t n, uint64_t seed, uint32
     SANERF_LAUNCH(uniform_fill_kernel, (uint32_t)div_up(work, (size_t)256), 256, 0, static_cast<cudaStream_t>(stream), out,
                   (size_t)n, seed, state, zero, zero_n);
     return check_launch("uniform_fill_kernel");
+}
+
+extern "C" int sanerf_ema_update(float* shadow, const float* params, uint64_t n, float one_minus_decay, void* stream) {
+    if (n == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(shadow); SANERF_REQUIRE_PTR(params);
+    if (((uintptr_t)shadow | (uintptr_t)params) & 15u) return fail(SANERF_ERR_MISALIGNED, "ema_update: buffers must be 16-byte aligned");
+    const size_t n4 = (size_t)n / 4;
+    const size_t blocks = div_up(div_up(n4 > 0 ? n4 : (size_t)1, (size_t)256), (size_t)4);
+    SANERF_LAUNCH(ema_update_kernel, (uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream), shadow, params, n4, (size_t)n,
+                  one_minus_decay);
+    return check_launch("ema_update_kernel");
 }

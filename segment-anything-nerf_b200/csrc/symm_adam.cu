@@ -2,7 +2,7 @@
 //
 //   all ranks:  barrier  ->  this rank's 1/world slice:  g = sum over ranks of grad      (multimem.ld_reduce through the
 //                                                         switch, or peer loads)
-//                                                        Adam (+ EMA) on the slice with the summed gradient
+//                                                        Adam (+ optional per-step EMA) on the slice
 //                                                        broadcast the new parameters     (multimem.st, or peer stores)
 //               barrier  ->  clear the local gradient range
 //

@@ -16,7 +16,7 @@ _HEADER = os.path.join(os.path.dirname(_PKG_DIR), "include", "sanerf_b200.h")
 
 SANERF_F32, SANERF_F16 = 0, 1
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
-ABI_VERSION = 25
+ABI_VERSION = 26
 
 c_void_p, c_int, c_u32, c_u64, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                           ctypes.c_uint64, ctypes.c_float)
@@ -80,6 +80,7 @@ _SIGNATURES = {
     "sanerf_adam_schedule": [c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_float, c_void_p],
     "sanerf_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_u64, c_void_p, c_float, c_float, c_float,
                          c_float, c_int, c_void_p, c_void_p, c_void_p],
+    "sanerf_ema_update": [c_void_p, c_void_p, c_u64, c_float, c_void_p],
     "sanerf_adam_step_half": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u64, c_void_p, c_float, c_float, c_float,
                               c_float, c_int, c_void_p],
     "sanerf_symm_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -28,6 +28,8 @@ def checkpoint_state(model, trainer=None, epoch=0, stats=None, full=False):
              "model": {k: v.detach().clone() for k, v in model.state_dict().items()}}
     if full and trainer is not None:
         opt = trainer.optimizer
+        if opt.sharded:
+            opt.gather_sharded_state()                    # multi-GPU: Adam moments are rank-sharded (collective)
         params = list(opt.params)
         step = float(opt.step_count.item())
         per_param = {}

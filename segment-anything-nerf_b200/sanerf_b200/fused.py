@@ -658,9 +658,11 @@ class FusedAdam:
     NCCL all-reduce buffer); one kernel updates everything and clears the gradient in the same pass.  The step
     counter and the schedule live on the device, so a captured CUDA graph replays with a moving learning rate.
 
-    ``ema_decay`` (the reference trains with 0.95: main.py:316, nerf/utils.py:616 ``torch_ema.ExponentialMovingAverage``
-    updated after every optimizer step, :1862): a shadow copy of the flat parameters follows them inside the same
-    kernel pass, with torch_ema's warm-up ``min(decay, (1 + t) / (10 + t))``.
+    ``ema_decay`` (the reference trains with 0.95: main.py:316, nerf/utils.py:616 ``torch_ema.ExponentialMovingAverage``):
+    a shadow copy of the flat parameters, updated by ``ema_update()`` — which the reference calls once per EPOCH
+    (nerf/utils.py:1862, after the loop of ``train_one_epoch``; :1627 once per 16 GUI steps), with torch_ema's warm-up
+    ``min(decay, (1 + k) / (10 + k))`` over the number of updates.  ``ema_every_step=True`` instead folds the update into
+    every Adam pass (same formula over the step count; one extra read + write of the shadow in the same kernel).
 
     ``gate`` (1 int32 on the device) makes a DEFERRED range update idempotent: ``schedule()`` sets it at the start of
     a step, ``apply(..., gated=True)`` does nothing while it is 0, and ``clear_gate()`` (called by a trainer's
@@ -668,7 +670,8 @@ class FusedAdam:
     step's CUDA graph finds nothing to do instead of moving the parameters by momentum on a zero gradient.
     """
 
-    def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000, ema_decay=None, world_size=1):
+    def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, decay_iters=20000, ema_decay=None, world_size=1,
+                 ema_every_step=False):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
         # every slot is a multiple of 32 elements: views stay 16-byte aligned and any range of whole slots splits into
@@ -702,6 +705,8 @@ class FusedAdam:
         self.gate = torch.zeros(1, device=dev, dtype=torch.int32)
         self.ema_decay = None if ema_decay is None else float(ema_decay)
         self.ema = self.flat_param.clone() if ema_decay is not None else None
+        self.ema_every_step = bool(ema_every_step) and self.ema is not None
+        self.ema_updates = 0
         self._ema_backup = None
 
     def zero_grad(self):
@@ -725,7 +730,7 @@ class FusedAdam:
         with torch.cuda.device(dev), _lib.stats.span("adam_schedule"):
             rc = lib.sanerf_adam_schedule(self.step_count.data_ptr(), self.dyn.data_ptr(), self.lr, self.betas[0],
                                           self.betas[1], self.decay_iters, self.gate.data_ptr(),
-                                          0.0 if self.ema_decay is None else self.ema_decay, _lib.current_stream(dev))
+                                          self.ema_decay if self.ema_every_step else 0.0, _lib.current_stream(dev))
         _lib.check(rc, "adam_schedule")
 
     def apply(self, start=0, stop=None, grad_scale=1.0, zero_grad=True, gated=False):
@@ -743,7 +748,7 @@ class FusedAdam:
                                       self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off, n, self.dyn.data_ptr(),
                                       self.betas[0], self.betas[1], self.eps, float(grad_scale), int(zero_grad),
                                       self.gate.data_ptr() if gated else None,
-                                      None if self.ema is None else self.ema.data_ptr() + off, _lib.current_stream(dev))
+                                      self.ema.data_ptr() + off if self.ema_every_step else None, _lib.current_stream(dev))
         _lib.check(rc, "adam_step")
 
     def apply_symm(self, start, stop, gated=False, blocks=None, channel=0):
@@ -765,7 +770,7 @@ class FusedAdam:
         """Ranges updated rank-sharded (``apply_symm`` / the NCCL reduce-scatter form) keep exp_avg / exp_avg_sq / EMA
         only for the rank's own slice: make them whole on every rank (checkpoints, EMA evaluation).  Collective."""
         import torch.distributed as dist
-        bufs = [self.exp_avg, self.exp_avg_sq] + ([self.ema] if self.ema is not None else [])
+        bufs = [self.exp_avg, self.exp_avg_sq] + ([self.ema] if self.ema_every_step else [])
         for (a, b), (lo, hi) in self.sharded.items():
             for buf in bufs:
                 tmp = torch.zeros(b - a, device=buf.device)
@@ -780,15 +785,30 @@ class FusedAdam:
         self.schedule()
         self.apply(0, None, grad_scale, zero_grad)
 
-    # ---- EMA (torch_ema surface the reference's Trainer uses: update is inside ``apply``; store / copy_to / restore
-    # bracket evaluation and best-checkpoint saving, nerf/utils.py:1684-1695, 1900-1902, 2035-2036, 2083-2095)
+    # ---- EMA (torch_ema surface the reference's Trainer uses: update once per epoch, nerf/utils.py:1862; store / copy_to /
+    # restore bracket evaluation and best-checkpoint saving, :1684-1695, 1900-1902, 2035-2036, 2083-2095)
+    def ema_update(self):
+        """``ExponentialMovingAverage.update()``: call after the epoch's last step (and after the trainer's ``flush()``, so
+        that a deferred table update has landed).  A no-op in ``ema_every_step`` mode."""
+        if self.ema is None:
+            raise RuntimeError("FusedAdam was built without ema_decay")
+        if self.ema_every_step:
+            return
+        self.ema_updates += 1
+        decay = min(self.ema_decay, (1 + self.ema_updates) / (10 + self.ema_updates))
+        dev = self.flat_param.device
+        with torch.cuda.device(dev), _lib.stats.span("ema_update", n=self.flat_param.numel()):
+            rc = _lib.load().sanerf_ema_update(self.ema.data_ptr(), self.flat_param.data_ptr(), self.flat_param.numel(),
+                                               1.0 - decay, _lib.current_stream(dev))
+        _lib.check(rc, "ema_update")
+
     def ema_store(self):
         self._ema_backup = self.flat_param.clone()
 
     def ema_copy_to(self):
         if self.ema is None:
             raise RuntimeError("FusedAdam was built without ema_decay")
-        if self.sharded:
+        if self.sharded and self.ema_every_step:
             self.gather_sharded_state()
         self.flat_param.copy_(self.ema)
 
@@ -802,10 +822,11 @@ class FusedAdam:
         """Same layout as ``torch_ema.ExponentialMovingAverage.state_dict()`` over the trainable parameters."""
         if self.ema is None:
             raise RuntimeError("FusedAdam was built without ema_decay")
-        if self.sharded:
+        if self.sharded and self.ema_every_step:
             self.gather_sharded_state()
         shadow = [self.ema[a:a + p.numel()].view_as(p).clone() for p, (a, _) in ((p, self.ranges[id(p)]) for p in self.params)]
-        return {"decay": self.ema_decay, "num_updates": int(self.step_count.item()), "shadow_params": shadow,
+        n_upd = int(self.step_count.item()) if self.ema_every_step else self.ema_updates
+        return {"decay": self.ema_decay, "num_updates": n_upd, "shadow_params": shadow,
                 "collected_params": None}
 
     def load_ema_state_dict(self, state):
@@ -817,3 +838,4 @@ class FusedAdam:
         for p, s in zip(self.params, shadow):
             a, _ = self.ranges[id(p)]
             self.ema[a:a + p.numel()].copy_(s.reshape(-1))
+        self.ema_updates = int(state.get("num_updates") or 0)

@@ -81,7 +81,7 @@ class SymmetricState:
         with torch.cuda.device(dev), _lib.stats.span("symm_adam_step", n=stop - start):
             rc = lib.sanerf_symm_adam_step(
                 opt.flat_param.data_ptr(), opt.flat_grad.data_ptr(), opt.exp_avg.data_ptr(), opt.exp_avg_sq.data_ptr(),
-                None if opt.ema is None else opt.ema.data_ptr(), self.param_mc or None, self.grad_mc or None,
+                opt.ema.data_ptr() if opt.ema_every_step else None, self.param_mc or None, self.grad_mc or None,
                 self.param_peers, self.grad_peers, self.flag_peers, self.epoch.data_ptr(), self.error.data_ptr(),
                 int(start), int(stop), self.world, self.rank, opt.dyn.data_ptr(), opt.betas[0], opt.betas[1], opt.eps,
                 float(grad_scale), opt.gate.data_ptr() if gated else None, int(blocks), int(threads), int(channel), _lib.current_stream(dev))

@@ -78,6 +78,12 @@ class RGBTrainer:
             if plan is not None:
                 plan.flush()
 
+    def end_epoch(self):
+        """What ``train_one_epoch`` does after its loop (nerf/utils.py:1862): one EMA update (when built with ``ema_decay``)."""
+        self.flush()
+        if self.optimizer.ema is not None:
+            self.optimizer.ema_update()
+
     def step(self, rays_o, rays_d, gt_rgb):
         _check_equal_shards(self, rays_o.shape[0])
         plan = self.plan(rays_o.shape[0])
@@ -210,6 +216,12 @@ class SAMTrainer:
             except UnsupportedConfig:
                 self._plans[key] = None
         return self._plans[key]
+
+    def end_epoch(self):
+        """What ``train_one_epoch`` does after its loop (nerf/utils.py:1862): one EMA update (when built with ``ema_decay``)."""
+        self.flush()
+        if self.optimizer.ema is not None:
+            self.optimizer.ema_update()
 
     def flush(self):
         """Apply the s_grid update the hand-scheduled step defers to the start of the next step (call before reading

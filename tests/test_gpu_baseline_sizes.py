@@ -200,25 +200,41 @@ def test_proposal_networks_do_not_move_without_gradient(cuda):
 
 
 def test_ema_follows_torch_ema_semantics(cuda):
-    """FusedAdam(ema_decay=0.95): shadow -= (1 - min(decay, (1+t)/(10+t))) * (shadow - param) after every update
-    (torch_ema.ExponentialMovingAverage.update, nerf/utils.py:616, 1862), including the deferred main table."""
+    """EMA(0.95) as torch_ema.ExponentialMovingAverage keeps it (nerf/utils.py:616): shadow -= (1 - min(decay, (1+k)/(10+k))) *
+    (shadow - param) at every ``update()`` — which the reference calls once per EPOCH (nerf/utils.py:1862) = ``end_epoch()``
+    here; ``ema_every_step`` folds the same update into every Adam pass, including the deferred main table's."""
+    from sanerf_b200.fused import FusedAdam
     from sanerf_b200.train import RGBTrainer
     from tests.test_gpu_step import _setup
     model, _, o, d, gt = _setup(128, seed=13)
     tr = RGBTrainer(model, ema_decay=0.95)
     opt = tr.optimizer
     shadow = opt.flat_param.clone()
-    for t in range(1, 5):
-        tr.step(o, d, gt)
-        tr.flush()
-        decay = min(0.95, (1 + t) / (10 + t))
+    for k in range(1, 4):                                  # three "epochs" of two steps
+        tr.step(o, d, gt); tr.step(o, d, gt)
+        assert torch.equal(opt.ema, shadow)                # steps alone do not touch the shadow
+        tr.end_epoch()
+        decay = min(0.95, (1 + k) / (10 + k))
         shadow -= (1 - decay) * (shadow - opt.flat_param)
         torch.testing.assert_close(opt.ema, shadow, rtol=1e-5, atol=1e-7)
     state = opt.ema_state_dict()
-    assert state["num_updates"] == 4 and len(state["shadow_params"]) == len(opt.params)
+    assert state["num_updates"] == 3 and len(state["shadow_params"]) == len(opt.params)
     live = opt.flat_param.clone()
     opt.ema_store(); opt.ema_copy_to()
-    torch.testing.assert_close(model.grid.embeddings.reshape(-1),
-                               shadow[:model.grid.embeddings.numel()], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(model.grid.embeddings.reshape(-1), shadow[:model.grid.embeddings.numel()], rtol=1e-5, atol=1e-7)
     opt.ema_restore()
     assert torch.equal(opt.flat_param, live)
+    # per-step variant: the update rides in the Adam kernels
+    model2, _, o, d, gt = _setup(128, seed=14)
+    tr2 = RGBTrainer(model2)
+    tr2.optimizer = FusedAdam([p for p in model2.parameters()], lr=1e-2, eps=1e-15, decay_iters=20000, ema_decay=0.95,
+                              ema_every_step=True)
+    tr2._prop_range = tr2.optimizer.range_of([*model2.prop_encoders.parameters(), *model2.prop_mlp.parameters()])
+    tr2._plans.clear()
+    opt2 = tr2.optimizer
+    shadow = opt2.flat_param.clone()
+    for t in range(1, 4):
+        tr2.step(o, d, gt); tr2.flush()
+        decay = min(0.95, (1 + t) / (10 + t))
+        shadow -= (1 - decay) * (shadow - opt2.flat_param)
+        torch.testing.assert_close(opt2.ema, shadow, rtol=1e-5, atol=1e-7)

@@ -173,6 +173,7 @@ def test_reference_format_checkpoint_round_trip(cuda, tmp_path):
     a.plan(256).perturb = False
     for _ in range(3):
         a.step(o, dr, gt)
+    a.end_epoch()                                           # the per-epoch EMA update (nerf/utils.py:1862)
     path = str(tmp_path / "ngp_ep0003.pth")
     save_checkpoint(path, model, a, epoch=3, full=True)
     ck = torch.load(path)
@@ -187,7 +188,8 @@ def test_reference_format_checkpoint_round_trip(cuda, tmp_path):
     for (k, p), (_, q) in zip(model.named_parameters(), twin.named_parameters()):
         assert torch.equal(p, q), k
     assert torch.equal(a.optimizer.exp_avg, b.optimizer.exp_avg) and torch.equal(a.optimizer.ema, b.optimizer.ema)
-    assert int(b.optimizer.step_count) == 3 and b.global_step == 3
+    assert int(b.optimizer.step_count) == 3 and b.global_step == 3 and b.optimizer.ema_updates == 1
+    assert not torch.equal(a.optimizer.ema, a.optimizer.flat_param)
     for _ in range(2):
         la, lb = a.step(o, dr, gt).clone(), b.step(o, dr, gt).clone()
         torch.testing.assert_close(la, lb, rtol=2e-4, atol=1e-6)
