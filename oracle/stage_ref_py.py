@@ -33,6 +33,7 @@ FILES = [
     "freqencoder/freq.py",
     "nerf/network.py",
     "nerf/renderer.py",
+    "nerf/utils.py",          # the Trainer (train_step / train_one_epoch / save_checkpoint / load_checkpoint): tests/test_gpu_dropin.py
 ]
 
 

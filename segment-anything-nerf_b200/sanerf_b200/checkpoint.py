@@ -7,6 +7,12 @@ the reference's sub-module names, so the ``'model'`` entry is interchangeable in
 written in ``torch.optim.Adam.state_dict()`` layout (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``) from the flat
 buffers of ``FusedAdam`` and read back into them; ``'ema'`` follows ``torch_ema.ExponentialMovingAverage.state_dict()``.
 
+The optimizer entry mirrors what ``torch.optim.Adam(model.get_params(lr), eps=1e-15).state_dict()`` holds in the reference
+(main.py:296 with network.py:278-308): one param group per sub-module in ``get_params`` order, parameter indices running
+through the groups, state only for parameters that were updated — so the reference's own ``Trainer.load_checkpoint`` restores
+it into its torch optimizer, and a file written by the reference's ``save_checkpoint(full=True)`` restores ``FusedAdam``
+(``tests/test_gpu_dropin.py`` does both with the reference's unmodified Trainer).
+
 ``warm_start`` is main.py:255-262: load a stage-1 checkpoint non-strictly and freeze every parameter it provided.
 """
 from __future__ import annotations
@@ -17,6 +23,17 @@ import torch
 def _flush(trainer):
     if trainer is not None and hasattr(trainer, "flush"):
         trainer.flush()                       # a deferred table update must land before parameters are read or replaced
+
+
+def _param_groups(model, opt):
+    """([indices per group], [parameters in index order]) as ``torch.optim.Adam(model.get_params(lr))`` numbers them
+    (network.py:278-308: grid, grid_mlp, view_mlp, prop_encoders, prop_mlp[, s_grid, samvit_mlp])."""
+    groups, order = [], []
+    for g in model.get_params(opt.lr):
+        ps = list(g["params"])
+        groups.append(list(range(len(order), len(order) + len(ps))))
+        order += ps
+    return groups, order
 
 
 def checkpoint_state(model, trainer=None, epoch=0, stats=None, full=False):
@@ -30,19 +47,26 @@ def checkpoint_state(model, trainer=None, epoch=0, stats=None, full=False):
         opt = trainer.optimizer
         if opt.sharded:
             opt.gather_sharded_state()                    # multi-GPU: Adam moments are rank-sharded (collective)
-        params = list(opt.params)
         step = float(opt.step_count.item())
+        lr_now = float(opt.dyn[0].item())
+        groups, order = _param_groups(model, opt)
         per_param = {}
-        for i, p in enumerate(params):
+        for i, p in enumerate(order):
+            if id(p) not in opt.ranges or step == 0:
+                continue                                  # frozen / never updated: torch's Adam holds no state for it
             a, _ = opt.ranges[id(p)]
             n = p.numel()
             per_param[i] = {"step": torch.tensor(step), "exp_avg": opt.exp_avg[a:a + n].view_as(p).clone(),
                             "exp_avg_sq": opt.exp_avg_sq[a:a + n].view_as(p).clone()}
         state["optimizer"] = {"state": per_param,
-                              "param_groups": [{"lr": float(opt.dyn[0].item()), "betas": tuple(opt.betas), "eps": opt.eps,
-                                                "weight_decay": 0, "amsgrad": False, "initial_lr": opt.lr,
-                                                "params": list(range(len(params)))}]}
-        state["lr_scheduler"] = {"last_epoch": int(step), "base_lrs": [opt.lr], "_step_count": int(step) + 1}
+                              "param_groups": [{"lr": lr_now, "betas": tuple(opt.betas), "eps": opt.eps, "weight_decay": 0,
+                                                "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                                                "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                                                "initial_lr": opt.lr, "params": idx} for idx in groups]}
+        state["lr_scheduler"] = {"base_lrs": [opt.lr] * len(groups), "last_epoch": int(step), "verbose": False,
+                                 "_step_count": int(step) + 1, "_get_lr_called_within_step": False,
+                                 "_last_lr": [lr_now] * len(groups), "lr_lambdas": [None] * len(groups)}
+        state["scaler"] = {}                              # torch.cuda.amp.GradScaler(enabled=False).state_dict() (main.py:222: fp16 off)
         if opt.ema is not None:
             state["ema"] = opt.ema_state_dict()
     return state
@@ -70,15 +94,17 @@ def load_checkpoint(checkpoint, model, trainer=None, model_only=False, map_locat
     opt = trainer.optimizer
     if "optimizer" in ckpt:
         st = ckpt["optimizer"]["state"]
-        if len(st) == len(opt.params):
-            step = 0
-            for i, p in enumerate(opt.params):
-                a, _ = opt.ranges[id(p)]
-                n = p.numel()
-                opt.exp_avg[a:a + n].copy_(st[i]["exp_avg"].reshape(-1))
-                opt.exp_avg_sq[a:a + n].copy_(st[i]["exp_avg_sq"].reshape(-1))
-                step = max(step, int(float(st[i]["step"])))
-            opt.step_count.fill_(step)
+        _, order = _param_groups(model, opt)
+        step = 0
+        for i, p in enumerate(order):
+            if i not in st or id(p) not in opt.ranges:
+                continue
+            a, _ = opt.ranges[id(p)]
+            n = p.numel()
+            opt.exp_avg[a:a + n].copy_(st[i]["exp_avg"].reshape(-1))
+            opt.exp_avg_sq[a:a + n].copy_(st[i]["exp_avg_sq"].reshape(-1))
+            step = max(step, int(float(st[i]["step"])))
+        opt.step_count.fill_(step)
     return list(res.missing_keys), list(res.unexpected_keys)
 
 

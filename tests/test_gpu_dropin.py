@@ -196,3 +196,89 @@ def test_reference_format_checkpoint_round_trip(cuda, tmp_path):
     a.flush(); b.flush()
     for (k, p), (_, q) in zip(model.named_parameters(), twin.named_parameters()):
         assert _rel(p, q) < 1e-4, k
+
+
+TRAINER_CHILD = os.path.join(ROOT, "tests", "dropin_trainer_child.py")
+
+
+def _run_trainer_child(mode, state_path, out_path, workspace, steps=3, rays=512):
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref_py", "nerf", "utils.py")):
+        pytest.skip("oracle/_ref_py/nerf/utils.py not staged (python -m oracle.stage_ref_py where /root/reference exists)")
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    env["WANDB_MODE"] = "disabled"
+    r = subprocess.run([sys.executable, TRAINER_CHILD, "--mode", mode, "--state", state_path, "--out", out_path,
+                        "--workspace", workspace, "--steps", str(steps), "--rays", str(rays)],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-5000:]
+    return torch.load(out_path, map_location="cpu", weights_only=False)
+
+
+def test_reference_trainer_runs_on_our_operators_and_checkpoints_interoperate(cuda, stage1, tmp_path):
+    """the reference's own ``Trainer`` (nerf/utils.py, unmodified) — ``train_one_epoch`` with ``train_step``,
+    backward, ``torch.optim.Adam(model.get_params(lr), eps=1e-15)``, LambdaLR per step, EMA(0.95) per epoch — on THIS
+    repository's NeRFNetwork / operators, against this repository's own trainer from the same checkpoint, rays and jitter
+    stream; then checkpoints in both directions: the reference's ``save_checkpoint(full=True)`` file restores FusedAdam, and
+    a file written here is restored by the reference's ``load_checkpoint`` into its torch optimizer / scheduler / EMA."""
+    from nerf.network import NeRFNetwork
+    from sanerf_b200.checkpoint import load_checkpoint, save_checkpoint
+    from sanerf_b200.train import RGBTrainer, default_opt
+    _, path, _ = stage1
+    steps, n = 3, 512
+    ref = _run_trainer_child("train", path, str(tmp_path / "trainer_ref.pt"), str(tmp_path / "ws"), steps, n)
+    assert ref["global_step"] == steps
+
+    # (1) this repository's trainer (autograd path: same torch.rand draws in the reference's order), same everything
+    twin = NeRFNetwork(default_opt(lambda_distort=0.02))
+    load_checkpoint(path, twin)
+    twin = twin.cuda()
+    tr = RGBTrainer(twin, fused_step=False, ema_decay=0.95)
+    g = torch.Generator().manual_seed(77)
+    batches = []
+    for _ in range(steps):
+        o = (torch.rand(n, 3, generator=g) - 0.5).cuda()
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+        rgb = torch.rand(n, 3, generator=g).cuda()
+        batches.append((o, d, rgb))
+    torch.manual_seed(1234)
+    losses = [float(tr.step(*b)) for b in batches]
+    tr.end_epoch()
+    assert abs(sum(losses) / steps - ref["avg_loss"]) < 1e-4 * abs(ref["avg_loss"])
+    for k, v in twin.state_dict().items():
+        if v.dtype.is_floating_point and "aabb" not in k:
+            assert _rel(v.cpu(), ref["params"][k]) < 1e-3, k
+    for p, s in zip(tr.optimizer.params, ref["ema"]):
+        a, _ = tr.optimizer.ranges[id(p)]
+        assert _rel(tr.optimizer.ema[a:a + p.numel()].cpu(), s.reshape(-1)) < 1e-3
+    assert abs(float(tr.optimizer.dyn[0]) * 0.1 ** (1 / 20000) - ref["lr"]) < 1e-7 * ref["lr"] + 1e-9    # LambdaLR after 3 steps
+
+    # (2) the file the reference's Trainer wrote -> this repository's loader
+    fresh = NeRFNetwork(default_opt()).cuda()
+    tf = RGBTrainer(fresh, fused_step=False, ema_decay=0.95)
+    missing, unexpected = load_checkpoint(ref["ckpt"], fresh, tf)
+    assert not missing and not unexpected
+    for k, v in fresh.state_dict().items():
+        assert torch.equal(v.cpu(), ref["params"][k]), k
+    assert int(tf.optimizer.step_count) == steps and tf.global_step == steps and tf.optimizer.ema_updates == 1
+    ck = torch.load(ref["ckpt"], map_location="cpu", weights_only=False)
+    a, _ = tf.optimizer.ranges[id(fresh.grid.embeddings)]
+    assert torch.equal(tf.optimizer.exp_avg[a:a + fresh.grid.embeddings.numel()].cpu(),
+                       ck["optimizer"]["state"][0]["exp_avg"].reshape(-1))
+    for p, s in zip(tf.optimizer.params, ref["ema"]):
+        a, _ = tf.optimizer.ranges[id(p)]
+        assert torch.equal(tf.optimizer.ema[a:a + p.numel()].cpu(), s.reshape(-1))
+
+    # (3) a file written here -> the reference's own Trainer.load_checkpoint
+    ours = str(tmp_path / "ours_ep0001.pth")
+    save_checkpoint(ours, twin, tr, epoch=1, full=True)
+    back = _run_trainer_child("load", ours, str(tmp_path / "trainer_back.pt"), str(tmp_path / "ws2"))
+    text = "\n".join(back["logs"])
+    for needle in ("loaded model", "loaded EMA", "loaded optimizer", "loaded scheduler"):
+        assert needle in text and "Failed" not in text and "failed" not in text, text
+    assert back["global_step"] == steps and back["epoch"] == 1 and back["ema_updates"] == 1
+    for k, v in twin.state_dict().items():
+        assert torch.equal(v.cpu(), back["params"][k]), k
+    assert back["opt_state_keys"] == list(range(13))                  # 13 trained tensors, numbered through the 5 groups
+    a, _ = tr.optimizer.ranges[id(twin.grid.embeddings)]
+    assert torch.equal(back["opt_state"][0]["exp_avg"].reshape(-1), tr.optimizer.exp_avg[a:a + twin.grid.embeddings.numel()].cpu())
+    assert abs(back["lr"] - float(tr.optimizer.dyn[0])) < 1e-9
