@@ -3,8 +3,9 @@
 
   --mode train : ``Trainer(..., model=NeRFNetwork(opt), optimizer=torch.optim.Adam(model.get_params(lr), eps=1e-15),
                  ema_decay=0.95, lr_scheduler=LambdaLR, scheduler_update_every_step=True)`` exactly as main.py:296-319 builds it,
-                 ``trainer.train_one_epoch(loader)`` over K synthetic ray batches (train_step, backward, post_train_step with
-                 the in-place TV gradient, optimizer / scheduler step, the per-epoch EMA update), then the reference's own
+                 ``trainer.train_one_epoch(loader)`` over K synthetic ray batches (train_step, backward, post_train_step,
+                 optimizer / scheduler step, the per-epoch EMA update; lambda_tv = 0: with eps = 1e-15 any TV gradient moves
+                 every sampled row by a full step, which the comparison trainer does not apply), then the reference's own
                  ``trainer.save_checkpoint(full=True)``
   --mode load  : the reference's own ``trainer.load_checkpoint(path)`` of a file written by sanerf_b200.checkpoint
 
@@ -69,7 +70,7 @@ def main():
     opt = types.SimpleNamespace(
         bound=128, contract=True, min_near=0.2, density_thresh=10, num_steps=[128, 64, 32], background="last_sample",
         with_sam=False, with_mask=False, sum_after_mlp=False, sam_use_view_direction=True, mask_mlp_type="default",
-        lambda_proposal=1.0, lambda_distort=0.02, lambda_entropy=0.0, lambda_tv=1e-8, lambda_wd=0.0, max_ray_batch=16384,
+        lambda_proposal=1.0, lambda_distort=0.02, lambda_entropy=0.0, lambda_tv=0.0, lambda_wd=0.0, max_ray_batch=16384,
         num_rays=args.rays, num_points=2 ** 18, adaptive_num_rays=False, lr=1e-2, iters=20000, fp16=False, use_wandb=False,
         cache_size=0, cache_interval=4, error_map=False, fused=True)
     dev = torch.device("cuda", 0)
