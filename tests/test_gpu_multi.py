@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_update_and_gradient_equivalence(cuda, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, the box has {torch.cuda.device_count()}")
