@@ -648,6 +648,16 @@ class FusedSAMStep:
         if a != 0 or g.embeddings.grad is None or not g.embeddings.grad.is_contiguous():
             raise RuntimeError("FusedSAMStep needs s_grid.embeddings to lead a FusedAdam flat buffer")
         self._head_params = [p for p in model.samvit_mlp.parameters()]
+        # The s_grid update is too long to hide behind the frozen front (42 M parameters: ~225 us of HBM traffic against a
+        # ~210 us front that owns the register files): the table is split at a level boundary.  The scatter runs as two
+        # launches (levels complete in order); the Adam pass of the FIRST part starts as soon as its gradient is complete,
+        # beside the scatter of the remaining levels (an L2-reduction-bound kernel that leaves the HBM bandwidth free), and
+        # only the second part is deferred to the start of the next step.
+        split_level = int(os.environ.get("SANERF_SAM_SPLIT", 8))
+        nccl_path = world_size > 1 and optimizer.symm is None
+        self.split_level = split_level if (0 < split_level < g.num_levels and not nccl_path) else 0
+        self.split_at = a + int(g.offsets[self.split_level].item()) * g.level_dim if self.split_level else a
+        self.scatter_done = torch.cuda.Event()
         # the autograd-free samvit head (static buffers), when the model is the reference's configuration on the tensor cores
         mlp, ln = model.samvit_mlp[0], model.samvit_mlp[1]
         self.head = None
@@ -670,7 +680,7 @@ class FusedSAMStep:
             if self.head is None:
                 self.sh = self.model.view_encoder(self.frame.rays_d)                  # [N,16], once per ray
 
-    def _launch_back(self):
+    def _launch_back(self, fuse_updates=False):
         m, lib, N, fr = self.model, _lib.load(), self.N, self.frame
         span, check = _lib.stats.span, _lib.check
         L = fr.lv[2]
@@ -723,13 +733,23 @@ class FusedSAMStep:
             g_sam = f.grad[:, :nl * C].contiguous()
             g_stride = 0
         st = _lib.current_stream(self.dev)
-        with span("ray_features_backward", N=N, T=T, C=C):
-            rc = lib.sanerf_ray_features_backward(L["x01"].data_ptr(), L["weights"].data_ptr(), g_sam.data_ptr(),
-                                                  g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), 0, nl,
-                                                  g_stride, st)
-        check(rc, "ray_features_backward")
+        main = torch.cuda.current_stream(self.dev)
+        cut = self.split_level if fuse_updates else 0
+        for lo, hi in (((0, cut), (cut, nl)) if cut else ((0, nl),)):
+            with span("ray_features_backward", N=N, T=T, C=C, levels=hi - lo):
+                rc = lib.sanerf_ray_features_backward(L["x01"].data_ptr(), L["weights"].data_ptr(), g_sam.data_ptr(),
+                                                      g.offsets.data_ptr(), N, T, C, nl, S, H, g.embeddings.grad.data_ptr(), lo, hi,
+                                                      g_stride, st)
+            check(rc, "ray_features_backward")
+            if cut and hi == cut:                          # levels [0, cut) are complete: their Adam pass starts now
+                self.scatter_done.record(main)
+                with torch.cuda.stream(self.update_stream):
+                    self.update_stream.wait_event(self.scatter_done)
+                    self._update_early()
+        if cut:
+            main.wait_stream(self.update_stream)
         if head is not None:                               # weight-gradient GEMMs ran beside the data-gradient chain + scatter
-            torch.cuda.current_stream(self.dev).wait_stream(self.side_stream)
+            main.wait_stream(self.side_stream)
 
     def _clear_loss(self):
         with _lib.stats.span("clear_loss"):
@@ -738,8 +758,20 @@ class FusedSAMStep:
         _lib.check(rc, "clear_loss")
 
     # ---- optimizer ----------------------------------------------------------------------------------------
+    def _update_early(self):
+        """Adam of the table's first part [a, split_at) — issued on the update stream beside the scatter of the later levels."""
+        a, _ = self._main_range()
+        opt = self.optimizer
+        if self.split_at <= a:
+            return
+        if opt.symm is not None:
+            opt.apply_symm(a, self.split_at, channel=1)
+        else:
+            opt.apply(a, self.split_at, grad_scale=1.0, zero_grad=True)
+
     def _update_main(self):
         a, b = self._main_range()
+        a = self.split_at                                  # the deferred part (everything when the split is off)
         opt = self.optimizer
         if self.world_size == 1:
             opt.apply(a, b, grad_scale=1.0, zero_grad=True, gated=True)
@@ -760,7 +792,7 @@ class FusedSAMStep:
     def _update_rest(self):
         b, n = self._main_range()[1], self.optimizer.flat_param.numel()
         if self.optimizer.symm is not None:
-            self.optimizer.apply_symm(b, n)
+            self.optimizer.apply_symm(b, n, channel=2)
             return
         if self.world_size > 1:
             dist.all_reduce(self.optimizer.flat_grad[b:n], op=dist.ReduceOp.SUM)
@@ -791,7 +823,7 @@ class FusedSAMStep:
         main, upd = self._deferred_update()
         self._launch_front()
         main.wait_stream(upd)
-        self._launch_back()
+        self._launch_back(fuse_updates=True)
         self._update_rest()
 
     def gradients_only(self, rays_o, rays_d, target):
@@ -813,7 +845,7 @@ class FusedSAMStep:
 
     def _back_half(self):
         def body():
-            self._launch_back()
+            self._launch_back(fuse_updates=True)
             self._update_rest()
         _critical(self, body)
 
