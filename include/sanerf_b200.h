@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SANERF_ABI_VERSION 26
+#define SANERF_ABI_VERSION 27
 
 #if defined(__GNUC__)
 #define SANERF_API __attribute__((visibility("default")))
@@ -311,6 +311,11 @@ SANERF_API int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const f
                    uint32_t ldc, uint32_t M, uint32_t N, uint32_t K, uint32_t k_splits, int epilogue,
                    const float* bias, int act, float slope, const float* mask, uint32_t ldm, uint32_t mask_cols,
                    float* colsum, int precision, void* stream);
+/* Strided device-to-device copy of a [rows, cols] fp32 matrix (a copy node, no kernel): used to keep copies of the two samvit
+ * weights whose rows are not 16-byte multiples (163 and 419 columns) with a padded leading dimension, which makes them
+ * addressable by the TMA (csrc/gemm_tma.cu). */
+SANERF_API int sanerf_copy_rows(float* dst, uint32_t ld_dst, const float* src, uint32_t ld_src, uint32_t rows, uint32_t cols,
+                     void* stream);
 SANERF_API int sanerf_colsum_add(const float* X, uint32_t ld, uint32_t M, uint32_t N, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------

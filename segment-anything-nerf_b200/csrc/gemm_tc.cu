@@ -350,6 +350,20 @@ __global__ void __launch_bounds__(256) colsum_add_kernel(const float* __restrict
     }
 }
 
+// csrc/gemm_tma.cu: the TMA-fed variant for plain forward products (both operands row-major, 16-byte aligned rows);
+// returns -1 when the call is not eligible
+int launch_gemm_tma(const float* A, uint32_t lda, const float* B, uint32_t ldb, int b_trans, float* C, uint32_t ldc, uint32_t M,
+                    uint32_t N, uint32_t K, int epilogue, const float* bias, int act, float slope, const float* mask, uint32_t ldm,
+                    uint32_t mask_cols, int precision, cudaStream_t stream);
+
+static bool gemm_tma_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("SANERF_GEMM_TMA");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on;
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -369,6 +383,11 @@ extern "C" int sanerf_gemm_tc(const float* A, uint32_t lda, int a_trans, const f
     if (k_splits == 0) k_splits = 1;
     if (k_splits > 1 && epilogue != 2)
         return fail(SANERF_ERR_INVALID_ARG, "gemm_tc: K can only be split with the accumulating epilogue");
+    if (!a_trans && epilogue != 2 && k_splits == 1 && colsum == nullptr && (precision >> 4) == 0 && gemm_tma_enabled()) {
+        const int rc = launch_gemm_tma(A, lda, B, ldb, b_trans, C, ldc, M, N, K, epilogue, bias, act, slope, mask, ldm, mask_cols,
+                                       precision, static_cast<cudaStream_t>(stream));
+        if (rc != -1) return rc;                      // -1: operands not TMA-addressable (row stride not a multiple of 16 bytes)
+    }
     const uint32_t chunks = (K + gemm::kKC - 1u) / gemm::kKC;
     GemmParams p;
     p.A = A; p.B = B; p.C = C; p.bias = bias; p.mask = mask; p.colsum = colsum;

@@ -436,3 +436,14 @@ extern "C" int sanerf_ema_update(float* shadow, const float* params, uint64_t n,
                   one_minus_decay);
     return check_launch("ema_update_kernel");
 }
+
+extern "C" int sanerf_copy_rows(float* dst, uint32_t ld_dst, const float* src, uint32_t ld_src, uint32_t rows, uint32_t cols,
+                                void* stream) {
+    if (rows == 0 || cols == 0) return SANERF_OK;
+    SANERF_REQUIRE_PTR(dst); SANERF_REQUIRE_PTR(src);
+    if (ld_dst < cols || ld_src < cols) return fail(SANERF_ERR_INVALID_ARG, "copy_rows: leading dimensions must cover the columns");
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)ld_dst * 4u, src, (size_t)ld_src * 4u, (size_t)cols * 4u, rows,
+                                      cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "copy_rows: %s", cudaGetErrorString(e));
+    return SANERF_OK;
+}

@@ -16,7 +16,7 @@ _HEADER = os.path.join(os.path.dirname(_PKG_DIR), "include", "sanerf_b200.h")
 
 SANERF_F32, SANERF_F16 = 0, 1
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
-ABI_VERSION = 26
+ABI_VERSION = 27
 
 c_void_p, c_int, c_u32, c_u64, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                           ctypes.c_uint64, ctypes.c_float)
@@ -74,6 +74,7 @@ _SIGNATURES = {
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sanerf_gemm_tc": [c_void_p, c_u32, c_int, c_void_p, c_u32, c_int, c_void_p, c_u32, c_u32, c_u32, c_u32, c_u32, c_int,
                        c_void_p, c_int, c_float, c_void_p, c_u32, c_u32, c_void_p, c_int, c_void_p],
+    "sanerf_copy_rows": [c_void_p, c_u32, c_void_p, c_u32, c_u32, c_u32, c_void_p],
     "sanerf_colsum_add": [c_void_p, c_u32, c_u32, c_u32, c_void_p, c_void_p],
     "sanerf_layernorm_mse": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_u64, c_u64, c_u32, c_u32, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p],

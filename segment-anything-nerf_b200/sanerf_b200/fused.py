@@ -483,11 +483,30 @@ class SamvitHead:
         self.h0, self.h2, self.h3, self.out, self.samvit = (torch.empty(M, W, **f32) for _ in range(5))
         self.g_out, self.g3, self.g2, self.g0 = (torch.empty(M, W, **f32) for _ in range(4))
         self.precision = PRECISION_IDS[mlp.precision]
+        # copies of the two weights whose rows are not 16-byte multiples ([256,163], [256,419]) with padded leading
+        # dimensions: TMA-addressable, so that every GEMM of the dependent chain takes the TMA-fed kernel (gemm_tma.cu)
+        self.w0p = torch.zeros(W, self.IN + 1, **f32)
+        self.w2p = torch.zeros(W, self.LD, **f32)
+
+    def refresh_weights(self):
+        """Re-copy the padded weight copies from the parameters (two copy nodes; call once per step before ``forward``)."""
+        lib, net = _lib.load(), self.mlp.net
+        st = _stream(self.w0p)
+        for dst, lin in ((self.w0p, net[0]), (self.w2p, net[2])):
+            rc = lib.sanerf_copy_rows(dst.data_ptr(), dst.stride(0), lin.weight.data_ptr(), lin.weight.stride(0), lin.out_features,
+                                      lin.in_features, st)
+            _lib.check(rc, "copy_rows")
+
+    def _weights(self):
+        net = self.mlp.net
+        w = [l.weight.detach() for l in net]
+        w[0], w[2] = self.w0p[:, :self.IN], self.w2p[:, :self.WIDTH + self.IN]
+        return w
 
     def forward(self):
         """skip[:, 256:419] (filled by the caller) -> out [M, 256] (pre-LayerNorm)."""
         net, W, M, pr = self.mlp.net, self.WIDTH, self.M, self.precision
-        w = [l.weight.detach() for l in net]
+        w = self._weights()
         b = [l.bias.detach() for l in net]
         gemm_tc(self.f, w[0], self.h0, M, W, self.IN, bias=b[0], act=True, precision=pr)
         gemm_tc(self.h0, w[1], self.skip, M, W, W, bias=b[1], act=True, precision=pr)             # -> skip[:, :256]
@@ -515,7 +534,7 @@ class SamvitHead:
         returned as a view of ``dskip`` (row stride 420).  The weight-gradient GEMMs and bias column sums run on
         ``side_stream`` beside the dependent chain of data-gradient GEMMs; the CALLER joins the side stream."""
         net, W, M, pr = self.mlp.net, self.WIDTH, self.M, self.precision
-        w = [l.weight.detach() for l in net]
+        w = self._weights()
         gw = [l.weight.grad for l in net]
         gb = [l.bias.grad for l in net]
         lib = _lib.load()

@@ -676,6 +676,11 @@ class FusedSAMStep:
     def _launch_front(self):
         """Frozen stage-1 forward: nothing here reads s_grid."""
         with torch.no_grad():
+            if self.head is not None:                      # padded copies of two samvit weights, beside the front
+                cur = torch.cuda.current_stream(self.dev)
+                self.side_stream.wait_stream(cur)
+                with torch.cuda.stream(self.side_stream):
+                    self.head.refresh_weights()
             self.frame._launch_render()
             if self.head is None:
                 self.sh = self.model.view_encoder(self.frame.rays_d)                  # [N,16], once per ray
@@ -704,6 +709,7 @@ class FusedSAMStep:
                                          depth.data_ptr(), N, int(bool(m.opt.sam_use_view_direction)),
                                          head.f.data_ptr() + 4 * nl * C, head.LD, st)
             check(rc, "sam_pack")
+            torch.cuda.current_stream(self.dev).wait_stream(self.side_stream)       # the refreshed weight copies
             head.forward()
             self._clear_loss()
             head.loss_backward(self.target, self.loss)

@@ -296,3 +296,51 @@ def test_layernorm_mse_fused_equals_torch(cuda):
     torch.testing.assert_close(g_x, xr.grad, rtol=1e-4, atol=1e-9)
     torch.testing.assert_close(ln.weight.grad, gw_ref, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(ln.bias.grad, gb_ref, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("M,N,K,lda,ldb", [(4096, 256, 256, 256, 256), (300, 256, 256, 256, 256), (4096, 256, 419, 420, 420),
+                                           (128, 64, 40, 40, 40), (1000, 200, 163, 420, 164)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_gemm_tma_path_equals_register_path(cuda, M, N, K, lda, ldb, precision):
+    """The TMA-fed forward GEMM (csrc/gemm_tma.cu: cp.async.bulk.tensor boxes into 128-byte-swizzled stages, hi / lo planes
+    derived in shared memory) against the register-staged kernel (csrc/gemm_tc.cu; precision bit 7 forces it) and fp64:
+    row / column / K tails are zero-filled by the TMA, strided operands (lda, ldb > K) are addressed through the tensor map."""
+    from sanerf_b200 import fused
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, lda, generator=g).cuda()[:, :K]
+    B = (torch.randn(N, ldb, generator=g) / K ** 0.5).cuda()[:, :K]
+    bias = torch.randn(N, generator=g).cuda()
+    prec = fused.PRECISION_IDS[precision]
+    out_tma, out_reg = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    fused.gemm_tc(A, B, out_tma, M, N, K, bias=bias, act=True, precision=prec)
+    fused.gemm_tc(A, B, out_reg, M, N, K, bias=bias, act=True, precision=prec | 128)
+    ref = torch.nn.functional.leaky_relu(A.double() @ B.double().t() + bias.double(), 0.01)
+    tol = 1e-5 if precision == "fp32" else 3e-3
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(out_tma.double(), ref, rtol=tol, atol=tol * scale)
+    torch.testing.assert_close(out_tma, out_reg, rtol=1e-6 if precision == "fp32" else 1e-5, atol=1e-6 * scale)
+
+
+@pytest.mark.parametrize("M,N,K,ldb", [(4096, 256, 256, 256), (4096, 419, 256, 420), (300, 128, 256, 164), (200, 64, 40, 64)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_gemm_tma_data_gradient_equals_register_path(cuda, M, N, K, ldb, masked):
+    """Data-gradient products C = (A . Bt) * act'(mask) with Bt = an nn.Linear weight as stored ([K, N] row-major): the TMA
+    path loads it as an MN-major operand (32 x 32 boxes, 128-byte swizzle with 32-byte atoms) — against the register-staged
+    kernel and fp64; N / K / M tails and a padded leading dimension included."""
+    from sanerf_b200 import fused
+    g = torch.Generator().manual_seed(M + N + K + ldb)
+    A = torch.randn(M, K, generator=g).cuda()
+    Bt = (torch.randn(K, ldb, generator=g) / K ** 0.5).cuda()[:, :N]
+    mask = torch.randn(M, N, generator=g).cuda()
+    kw = dict(b_trans=True, epilogue=1, mask=mask, mask_cols=N - 3) if masked else dict(b_trans=True)
+    out_tma, out_reg = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    fused.gemm_tc(A, Bt, out_tma, M, N, K, precision=0, **kw)
+    fused.gemm_tc(A, Bt, out_reg, M, N, K, precision=128, **kw)
+    ref = A.double() @ Bt.double()
+    if masked:
+        d = torch.where(mask.double() > 0, 1.0, 0.01)
+        d[:, N - 3:] = 1.0
+        ref = ref * d
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(out_tma.double(), ref, rtol=1e-5, atol=1e-5 * scale)
+    torch.testing.assert_close(out_tma, out_reg, rtol=1e-6, atol=1e-6 * scale)
