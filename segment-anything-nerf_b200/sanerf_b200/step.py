@@ -682,6 +682,8 @@ class FusedSAMStep:
                 with torch.cuda.stream(self.side_stream):
                     self.head.refresh_weights()
             self.frame._launch_render()
+            if self.head is not None:
+                cur.wait_stream(self.side_stream)          # joined here: the front may be captured as a graph of its own
             if self.head is None:
                 self.sh = self.model.view_encoder(self.frame.rays_d)                  # [N,16], once per ray
 
@@ -709,7 +711,6 @@ class FusedSAMStep:
                                          depth.data_ptr(), N, int(bool(m.opt.sam_use_view_direction)),
                                          head.f.data_ptr() + 4 * nl * C, head.LD, st)
             check(rc, "sam_pack")
-            torch.cuda.current_stream(self.dev).wait_stream(self.side_stream)       # the refreshed weight copies
             head.forward()
             self._clear_loss()
             head.loss_backward(self.target, self.loss)
