@@ -97,6 +97,7 @@ def slice_bounds(start, stop, world, rank):
     """The slice of [start, stop) rank ``rank`` reduces, updates and broadcasts (same arithmetic as symm_adam_kernel)."""
     n4 = (stop - start) // 4
     per = (n4 + world - 1) // world
-    lo = start // 4 + rank * per
-    hi = min(lo + per, start // 4 + n4)
-    return 4 * lo, 4 * max(hi, lo)
+    end = start // 4 + n4
+    lo = min(start // 4 + rank * per, end)              # ranks past the end of a short range own an empty slice
+    hi = min(lo + per, end)
+    return 4 * lo, 4 * hi
