@@ -648,12 +648,12 @@ class FusedSAMStep:
         if a != 0 or g.embeddings.grad is None or not g.embeddings.grad.is_contiguous():
             raise RuntimeError("FusedSAMStep needs s_grid.embeddings to lead a FusedAdam flat buffer")
         self._head_params = [p for p in model.samvit_mlp.parameters()]
-        # The s_grid update is too long to hide behind the frozen front (42 M parameters: ~225 us of HBM traffic against a
-        # ~210 us front that owns the register files): the table is split at a level boundary.  The scatter runs as two
-        # launches (levels complete in order); the Adam pass of the FIRST part starts as soon as its gradient is complete,
-        # beside the scatter of the remaining levels (an L2-reduction-bound kernel that leaves the HBM bandwidth free), and
-        # only the second part is deferred to the start of the next step.
-        split_level = int(os.environ.get("SANERF_SAM_SPLIT", 8))
+        # Optional (SANERF_SAM_SPLIT=<level>, default off): split the s_grid update at a level boundary - the scatter runs as
+        # two launches (levels complete in order), the Adam pass / exchange of the FIRST part starts as soon as its gradient
+        # is complete, beside the scatter of the remaining levels, and only the second part is deferred to the next step's
+        # front.  Measured: no gain on one GPU (0.9085 vs 0.9069 ms at level 8) and slower at two (1.097 / 1.164 ms at
+        # levels 8 / 10 vs 1.060): the update's CTAs take register-file slots from the scatter as they do from the front.
+        split_level = int(os.environ.get("SANERF_SAM_SPLIT", 0))
         nccl_path = world_size > 1 and optimizer.symm is None
         self.split_level = split_level if (0 < split_level < g.num_levels and not nccl_path) else 0
         self.split_at = a + int(g.offsets[self.split_level].item()) * g.level_dim if self.split_level else a
