@@ -163,7 +163,8 @@ __global__ void adam_schedule_kernel(int32_t* step, float* dyn, float lr0, float
     dyn[2] = 1.0f - powf(beta2, (float)t);
 }
 
-__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+template <int kThreadsMax>
+__global__ void __launch_bounds__(kThreadsMax) adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, size_t n4, size_t n,
                                                         const float* __restrict__ dyn, float beta1, float beta2,
                                                         float eps, float grad_scale, int zero_grad,
@@ -393,7 +394,17 @@ extern "C" int sanerf_adam_step(float* params, float* grads, float* exp_avg, flo
     // critical chain, whose CTAs can only be placed when CTAs of this kernel retire.  (Measured alternative: two
     // persistent CTAs per SM - no better; the interference is in the memory system, see the streaming accesses above.)
     blocks = div_up(blocks, (size_t)4);
-    SANERF_LAUNCH(adam_step_kernel, (uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream), 
+    // Large passes that run BESIDE other kernels (the deferred table update beside the next step's front) can instead be
+    // launched as a small persistent grid of 1024-thread CTAs (SANERF_ADAM_PERSISTENT=<CTAs>): each owns one SM's register
+    // file for the whole pass, so the pass keeps a fixed slice of the machine instead of waiting for slots the front's
+    // register-hungry CTAs leave free ("register-file exclusivity").
+    static const int persistent = [] { const char* e = getenv("SANERF_ADAM_PERSISTENT"); return e ? atoi(e) : 0; }();
+    if (persistent > 0 && n >= (1u << 22)) {
+        SANERF_LAUNCH(adam_step_kernel<1024>, (uint32_t)persistent, 1024, 0, static_cast<cudaStream_t>(stream),
+            params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad, gate, ema);
+        return check_launch("adam_step_kernel");
+    }
+    SANERF_LAUNCH(adam_step_kernel<256>, (uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream), 
         params, grads, exp_avg, exp_avg_sq, n4, (size_t)n, dyn, beta1, beta2, eps, grad_scale, zero_grad, gate, ema);
     return check_launch("adam_step_kernel");
 }
