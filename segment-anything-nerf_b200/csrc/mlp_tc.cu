@@ -414,7 +414,8 @@ static_assert(kBwdSmem <= 227 * 1024, "backward tiles exceed shared memory");
 // TMEM columns: A-operand staging (hi, lo), data-gradient accumulator, weight-gradient accumulators (M = 64)
 constexpr uint32_t cAhi = 0, cAlo = 64, cDG = 128, cW2 = 192, cW1 = 256, cW3 = 288, cDGE = 304 /* two 32-column buffers */,
                    kBwdTmemCols = 512;
-constexpr uint32_t kBwdThreads = 512;
+constexpr uint32_t kBwdThreads = 512;                   // worker threads (and the whole lock-step kernel)
+constexpr uint32_t kBwdThreads2 = kBwdThreads + 32;      // + one issuing warp
 }  // namespace head
 
 struct HeadBwdParams {
@@ -437,6 +438,7 @@ struct HeadBwdParams {
     float* g_w3;          // [16,64]
     uint32_t B;
     int precision;
+    int dbg;              // diagnostics (SANERF_HEAD_TRACE builds): phases to leave out when timing
 };
 
 // stage the TRANSPOSE of an nn.Linear weight [rows=out, cols=in] as a K-major B operand with `cols` rows
@@ -474,14 +476,15 @@ __device__ __forceinline__ void put_mn(uint8_t* hi_plane, uint8_t* lo_plane, uin
 
 // 16 consecutive features of this thread's sample -> TMEM A-operand planes (hi at col, lo at col + 64)
 __device__ __forceinline__ void put_tmem16(uint32_t lane_base, uint32_t col, const float (&v)[16], bool split) {
-    float hi[16], lo[16];
+    float t[16];
 #pragma unroll
-    for (uint32_t j = 0; j < 16; ++j) {
-        if (split) umma::split_tf32(v[j], hi[j], lo[j]);
-        else hi[j] = round_tf32(v[j]);
+    for (uint32_t j = 0; j < 16; ++j) t[j] = split ? __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u) : round_tf32(v[j]);
+    umma::tmem_st16(lane_base + head::cAhi + col, t);
+    if (split) {
+#pragma unroll
+        for (uint32_t j = 0; j < 16; ++j) t[j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
+        umma::tmem_st16(lane_base + head::cAlo + col, t);
     }
-    umma::tmem_st16(lane_base + head::cAhi + col, hi);
-    if (split) umma::tmem_st16(lane_base + head::cAlo + col, lo);
 }
 
 // D[64, N] (+)= At^T . Bt : MN-major swizzled tiles whose 128 rows are the contraction index (low descriptor halves)
@@ -505,6 +508,24 @@ __device__ __forceinline__ void issue_gemm_mn(uint32_t tmem_d, uint32_t a_hi, ui
     }
 }
 
+__device__ __forceinline__ float4 ldg_nc_alloc_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_plain_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_ef_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -513,14 +534,20 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
 
 // Phase timestamps of CTA 0 (diagnostics; compiled in only with -DSANERF_HEAD_TRACE): [thread 0][tile 0..3][11]
 #ifdef SANERF_HEAD_TRACE
-__device__ long long g_head_trace[2 * 4 * 11];
+static int g_head_dbg_host = 0;
+#define HEAD_DBG(bit) ((p.dbg & (bit)) != 0)
+__device__ long long g_head_trace[2 * 4 * 16];
+__device__ long long g_head_marks[8];          // CTA 0, thread 0: entry, prologue done, loop done, exit
+#define HEAD_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_marks[i] = clock64(); } while (0)
 #define HEAD_TRACE(slot)                                                                                   \
     do {                                                                                                   \
         if (blockIdx.x == 0 && it < 4 && (tid == 0 || tid == 128))                                         \
-            g_head_trace[((tid == 0 ? 0 : 1) * 4 + it) * 11 + (slot)] = clock64();                          \
+            g_head_trace[((tid == 0 ? 0 : 1) * 4 + it) * 16 + (slot)] = clock64();                          \
     } while (0)
 #else
 #define HEAD_TRACE(slot) do {} while (0)
+#define HEAD_MARK(i) do {} while (0)
+#define HEAD_DBG(bit) false
 #endif
 
 // Hash-grid scatter of ONE level for this thread's sample, fused into the backward (replaces the matching slice of
@@ -557,7 +584,7 @@ __device__ __noinline__ void scatter_level(const float* __restrict__ x01, float*
 // 16 symmetric worker warps.  Warp w serves TMEM lane quadrant q = w & 3 (tile rows 32 q .. 32 q + 31) and, in the
 // epilogues, the 16 accumulator columns 16 (w >> 2) ..; in the staging phases it moves the 8 tile rows 8 w .. 8 w + 7.
 // Every phase therefore runs with four warps per scheduler instead of one.
-__global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(const HeadBwdParams p, const uint32_t tiles) {
+__global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_lockstep_kernel(const HeadBwdParams p, const uint32_t tiles) {
     pdl_begin();
     using namespace head;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -662,6 +689,8 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         for (uint32_t j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.0f;
         put_tmem16(lane_base, c0, v, split);
 #pragma unroll
+        if (!HEAD_DBG(4))
+#pragma unroll
         for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
     };
 
@@ -704,20 +733,21 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         if (issuer) {
             if (umma::elect_one()) {
                 umma::fence_after_sync();
-                issue_gemm_ts<kHid, kOut>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT3h, dT3l, split);
-                issue_gemm_mn<kOut>(tmem + cW3, dB, dB + (kMn64 >> 4), dG, dG + (kMn32 >> 4), split, first);
+                if (!HEAD_DBG(16)) issue_gemm_ts<kHid, kOut>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT3h, dT3l, split);
+                if (!HEAD_DBG(8)) issue_gemm_mn<kOut>(tmem + cW3, dB, dB + (kMn64 >> 4), dG, dG + (kMn32 >> 4), split, first);
                 umma::commit(umma::smem_u32(&s_mma));
             }
             __syncwarp();
         }
         // H1 -> bufA is needed by step 4 only: written while step 3 runs on the tensor core; the freed registers are
         // refilled with the next tile's rows
+        if (!HEAD_DBG(2))
 #pragma unroll
         for (uint32_t i = 0; i < 4; ++i) {
             put_mask(0, 32 * i + lane, h_c, rh1[i]);
             put_mn(bufA, bufA + kMn64, 32 * i + lane, h_c * 4u, rh1[i].x, rh1[i].y, rh1[i].z, rh1[i].w, split);
         }
-        load_h2_g(next);
+        if (!HEAD_DBG(1)) load_h2_g(next);
         if (scatter && it > 0) scatter_slot(it - 1, tile - gridDim.x, 0);
         mma_done();
         HEAD_TRACE(3);
@@ -729,13 +759,13 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         if (issuer) {
             if (umma::elect_one()) {
                 umma::fence_after_sync();
-                issue_gemm_ts<kHid, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT2h, dT2l, split);
-                issue_gemm_mn<kHid>(tmem + cW2, dB, dB + (kMn64 >> 4), dA, dA + (kMn64 >> 4), split, first);
+                if (!HEAD_DBG(16)) issue_gemm_ts<kHid, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT2h, dT2l, split);
+                if (!HEAD_DBG(8)) issue_gemm_mn<kHid>(tmem + cW2, dB, dB + (kMn64 >> 4), dA, dA + (kMn64 >> 4), split, first);
                 umma::commit(umma::smem_u32(&s_mma));
             }
             __syncwarp();
         }
-        load_h1(next);
+        if (!HEAD_DBG(1)) load_h1(next);
         if (scatter && it > 0) { scatter_slot(it - 1, tile - gridDim.x, 1); scatter_slot(it - 1, tile - gridDim.x, 2); }
         mma_done();
         HEAD_TRACE(6);
@@ -750,13 +780,13 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
         if (issuer) {
             if (umma::elect_one()) {
                 umma::fence_after_sync();
-                issue_gemm_ts<kIn, kHid>(tmem + (scatter ? cDGE + (it & 1u) * 32u : cDG), tmem + cAhi, tmem + cAlo, dT1h, dT1l, split);
-                issue_gemm_mn<kIn>(tmem + cW1, dB, dB + (kMn64 >> 4), dA, dA + (kMn32 >> 4), split, first);
+                if (!HEAD_DBG(16)) issue_gemm_ts<kIn, kHid>(tmem + (scatter ? cDGE + (it & 1u) * 32u : cDG), tmem + cAhi, tmem + cAlo, dT1h, dT1l, split);
+                if (!HEAD_DBG(8)) issue_gemm_mn<kIn>(tmem + cW1, dB, dB + (kMn64 >> 4), dA, dA + (kMn32 >> 4), split, first);
                 umma::commit(umma::smem_u32(&s_mma));
             }
             __syncwarp();
         }
-        load_enc(next);
+        if (!HEAD_DBG(1)) load_enc(next);
         if (scatter && it > 0) scatter_slot(it - 1, tile - gridDim.x, 3);
         mma_done();
         HEAD_TRACE(9);
@@ -818,6 +848,333 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_kernel(con
     if (warp == 0) umma::tmem_dealloc<head::kBwdTmemCols>(tmem);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The backward without the fused scatter (the form the training steps use).  Same operand placement as above, but
+//  * the data-gradient chain (DG2 -> G2 -> DG1 -> G1 -> DGE) and the weight-gradient products complete on SEPARATE
+//    mbarriers: an epilogue reads its accumulator as soon as the chain product is done and writes the next A operand
+//    into tensor memory while the weight-gradient product of the previous stage still runs; the shared-memory copy of
+//    the same gradient tile (the MN-major operand of the NEXT weight-gradient product) is written afterwards, beside
+//    the next chain product.  Per 128-sample tile the tensor pipe sees DG2 | dW3 | DG1 | dW2 | DGE | dW1 back to back
+//    instead of three issue -> drain -> epilogue rounds (measured phase times: profiles/r2_head_backward.md);
+//  * DG2 of a tile only needs G3 in tensor memory, so it is issued before the tile's activations are staged;
+//  * every 16-byte store into an MN-major tile is bank-conflict-free: in the 128-byte-swizzle / 32-byte-atom layout the
+//    32 rows a warp writes land in only four 32-byte slots of a 128-byte line, so lanes alternate (by bit 2 of the lane)
+//    between the two 4-feature chunks that share such a slot - half of the lanes write the lower 16 bytes, half the upper.
+__global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(const HeadBwdParams p, const uint32_t tiles) {
+    HEAD_MARK(0);
+    pdl_begin();
+    HEAD_MARK(1);
+    using namespace head;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_chain, s_wgrad, s_tmem_ready, s_smem_ready;
+    __shared__ __align__(16) uint8_t s_mask[2][kTile][16];     // ReLU sign patterns of H1 / H2: one nibble per 4-feature chunk
+    __shared__ uint32_t s_tmem;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool split = (p.precision == 0);
+    const uint32_t q = warp & 3u, cg = warp >> 2;           // TMEM lane quadrant, 16-column group
+    const uint32_t row = q * 32u + lane;                    // tile row of this thread's TMEM lane
+    const uint32_t sw = (lane >> 2) & 1u;                   // which chunk of a pair this lane takes first (conflict-free stores)
+    uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    if (warp == 0) umma::tmem_alloc<kBwdTmemCols>(umma::smem_u32(&s_tmem));
+    if (tid == 32) {
+        umma::mbar_init(umma::smem_u32(&s_chain), 1);
+        umma::mbar_init(umma::smem_u32(&s_wgrad), 1);
+        umma::mbar_init(umma::smem_u32(&s_tmem_ready), 1);
+        umma::mbar_init(umma::smem_u32(&s_smem_ready), 1);
+        umma::fence_mbar_init();
+    }
+    stage_weight_t(p.w3, smem + oT3, kOut, kHid, split, tid, kBwdThreads2);
+    stage_weight_t(p.w2, smem + oT2, kHid, kHid, split, tid, kBwdThreads2);
+    stage_weight_t(p.w1, smem + oT1, kHid, kIn, split, tid, kBwdThreads2);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    HEAD_MARK(2);
+    const uint32_t tmem = s_tmem;
+    const uint32_t lane_base = umma::tmem_addr(tmem, q * 32u, 0);
+    const uint32_t dT3h = umma::desc_lo(umma::smem_u32(smem + oT3), kHid * 16u), dT3l = dT3h + (kW3 >> 4);
+    const uint32_t dT2h = umma::desc_lo(umma::smem_u32(smem + oT2), kHid * 16u), dT2l = dT2h + (kW2 >> 4);
+    const uint32_t dT1h = umma::desc_lo(umma::smem_u32(smem + oT1), kIn * 16u), dT1l = dT1h + (kW1 >> 4);
+    const uint32_t dA = umma::desc_lo(umma::smem_u32(smem + oBufA), kMnLbo), dB = umma::desc_lo(umma::smem_u32(smem + oBufB), kMnLbo);
+    const uint32_t dG = umma::desc_lo(umma::smem_u32(smem + oBufG), kMnLbo);
+    uint8_t* bufA = smem + oBufA;
+    uint8_t* bufB = smem + oBufB;
+    uint8_t* bufG = smem + oBufG;
+    const uint32_t bar_chain = umma::smem_u32(&s_chain), bar_wgrad = umma::smem_u32(&s_wgrad);
+    const uint32_t bar_tmem_ready = umma::smem_u32(&s_tmem_ready), bar_smem_ready = umma::smem_u32(&s_smem_ready);
+    uint32_t ph_chain = 0, ph_wgrad = 0;
+
+    if (warp == kBwdThreads / 32) {
+        // ===================== issuing warp: six products per tile, each as soon as its operands are published ==========
+        // (the ~200 tcgen05.mma of a tile take 3-4 thousand clocks to ISSUE; on a worker warp that time sat on every
+        // worker's critical path through the next barrier)
+        uint32_t ph_t = 0, ph_s = 0;
+        auto ready = [&](uint32_t bar, uint32_t& ph) { umma::mbar_wait(bar, ph); ph ^= 1u; };
+        // The workers' staging loads go through an L1 that the 222 KB of tiles leave ~30 KB of: the lines it can keep in
+        // flight times the HBM latency bound the loads (measured: 14 k -> 9 k clocks per tile without them).  This warp
+        // therefore pulls the tile after next into L2 with bulk prefetches (no registers, no shared memory), so the
+        // loads meet the L2 latency instead.
+        auto prefetch_tile = [&](uint32_t t) {
+            if (t >= tiles || HEAD_DBG(2)) return;
+            const uint32_t rows = (p.B - t * kTile) < kTile ? (p.B - t * kTile) : kTile;
+            bulk_prefetch_l2(p.h2 + (size_t)t * kTile * kHid, kTile * kHid * 4u);
+            bulk_prefetch_l2(p.h1 + (size_t)t * kTile * kHid, kTile * kHid * 4u);
+            bulk_prefetch_l2(p.enc + (size_t)t * kTile * kIn, kTile * kIn * 4u);
+            bulk_prefetch_l2(p.g_out + (size_t)t * kTile * kOut, rows * kOut * 4u);
+        };
+        if (umma::elect_one()) { prefetch_tile(blockIdx.x); prefetch_tile(blockIdx.x + gridDim.x); }
+        __syncwarp();
+        for (uint32_t it = 0, tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
+            const uint32_t first = (it == 0) ? 0u : 1u;
+            if (umma::elect_one()) prefetch_tile(tile + 2u * gridDim.x);
+            __syncwarp();
+            ready(bar_tmem_ready, ph_t);
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                issue_gemm_ts<kHid, kOut>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT3h, dT3l, split);              // DG2 = G3 W3
+                umma::commit(bar_chain);
+            }
+            __syncwarp();
+            ready(bar_smem_ready, ph_s);
+            if (umma::elect_one()) {
+                umma::fence_proxy_async();
+                umma::fence_after_sync();
+                issue_gemm_mn<kOut>(tmem + cW3, dB, dB + (kMn64 >> 4), dG, dG + (kMn32 >> 4), split, first);     // dW3^T += H2^T G3
+                umma::commit(bar_wgrad);
+            }
+            __syncwarp();
+            ready(bar_tmem_ready, ph_t);
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                issue_gemm_ts<kHid, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT2h, dT2l, split);              // DG1 = G2 W2
+                umma::commit(bar_chain);
+            }
+            __syncwarp();
+            ready(bar_smem_ready, ph_s);
+            if (umma::elect_one()) {
+                umma::fence_proxy_async();
+                umma::fence_after_sync();
+                issue_gemm_mn<kHid>(tmem + cW2, dB, dB + (kMn64 >> 4), dA, dA + (kMn64 >> 4), split, first);     // dW2 += G2^T H1
+                umma::commit(bar_wgrad);
+            }
+            __syncwarp();
+            ready(bar_tmem_ready, ph_t);
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                issue_gemm_ts<kIn, kHid>(tmem + cDG, tmem + cAhi, tmem + cAlo, dT1h, dT1l, split);               // DGE = G1 W1
+                umma::commit(bar_chain);
+            }
+            __syncwarp();
+            ready(bar_smem_ready, ph_s);
+            if (umma::elect_one()) {
+                umma::fence_proxy_async();
+                umma::fence_after_sync();
+                issue_gemm_mn<kIn>(tmem + cW1, dB, dB + (kMn64 >> 4), dA, dA + (kMn32 >> 4), split, first);      // dW1 += G1^T enc
+                umma::commit(bar_wgrad);
+            }
+            __syncwarp();
+        }
+    } else {
+    // ===================== 16 worker warps =====================
+
+    auto wait_chain = [&]() { umma::mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u; umma::fence_after_sync(); };
+    auto wait_wgrad = [&]() { umma::mbar_wait(bar_wgrad, ph_wgrad); ph_wgrad ^= 1u; umma::fence_after_sync(); };
+    // A planes written (tcgen05.st complete) and this thread's reads of the accumulator done
+    auto publish_tmem = [&]() {
+        umma::tmem_st_wait(); umma::fence_before_sync(); named_bar_sync(1, kBwdThreads);
+        if (tid == 0) mbar_arrive(bar_tmem_ready);
+    };
+    // MN-major tiles written: generic-proxy stores -> visible to the tensor core
+    // The generic-proxy -> async-proxy fence for the tiles is executed by the ISSUING thread, after it has observed the
+    // workers' barrier (a proxy fence anywhere on the causality path from the stores to the tensor-core reads orders them).
+    // On the writers' side fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for every global
+    // load the thread has in flight: with the staging registers loaded one phase ahead that exposed the whole HBM latency
+    // three times per tile (measured: 14.1 k -> 10.0 k clocks per tile without the loads, profiles/r2_head_backward.md).
+    auto publish_smem = [&]() {
+        umma::fence_before_sync(); named_bar_sync(1, kBwdThreads);
+        if (tid == 0) mbar_arrive(bar_smem_ready);
+    };
+
+    // ---- staging registers, loaded two phases before they are staged (tile-chunk-major pieces; one instruction = two runs of 16 rows x 16 B
+    // of the two chunks of a pair: lanes alternate between the chunks in groups of four)
+    float4 rh[4], re[2], rg, rgq;     // rh: H2 of the next tile, then H1 of the current one
+    const uint32_t h_cp = warp >> 1, h_r0 = (warp & 1u) * 64u + lane;      // H1 / H2: chunk pair, rows h_r0 + 32 i
+    const uint32_t e_cp = warp >> 2, e_row = (warp & 3u) * 32u + lane;     // enc: chunk pair, one row per lane
+    const uint32_t g_row = warp * 8u + (lane >> 2), g_c = lane & 3u;       // g_out (row-major): 8 rows per instruction
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld_tcm = [&](const float* base, uint32_t chunks, uint32_t tile, uint32_t r, uint32_t c) -> float4 {
+        const uint32_t bb = tile * kTile + r;
+#ifdef SANERF_HEAD_TRACE
+        if (!(tile < tiles && bb < p.B)) return zero4;
+        const float* src = base + tcm_off(bb, c, chunks);
+        return HEAD_DBG(4) ? ldg_nc_alloc_f4(src) : HEAD_DBG(8) ? ldg_plain_f4(src) : HEAD_DBG(16) ? ldg_ef_f4(src) : ldg_nc_f4(src);
+#else
+        return (tile < tiles && bb < p.B) ? ldg_nc_alloc_f4(base + tcm_off(bb, c, chunks)) : zero4;
+#endif
+    };
+    auto ld_row = [&](const float* base, uint32_t width, uint32_t tile, uint32_t r, uint32_t c) -> float4 {
+        const uint32_t bb = tile * kTile + r;
+        return (tile < tiles && bb < p.B) ? ldg_nc_f4(base + (size_t)bb * width + 4u * c) : zero4;
+    };
+    auto put_mask = [&](uint32_t layer, uint32_t r, uint32_t c, const float4& v) {
+        s_mask[layer][r][c] = (uint8_t)((v.x > 0.f) | ((v.y > 0.f) << 1) | ((v.z > 0.f) << 2) | ((v.w > 0.f) << 3));
+    };
+    auto load_h = [&](const float* base, uint32_t tile) {
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) rh[i] = ld_tcm(base, 16, tile, h_r0 + 32u * (i >> 1), 2u * h_cp + ((i & 1u) ^ sw));
+    };
+    auto load_g = [&](uint32_t tile) {
+        rg = ld_row(p.g_out, kOut, tile, g_row, g_c);        // for the MN-major tile: 8 rows per instruction
+        rgq = ld_row(p.g_out, kOut, tile, row, cg);          // for the A planes: this lane's row, columns 4 cg ..
+    };
+    auto load_enc = [&](uint32_t tile) {
+#pragma unroll
+        for (uint32_t i = 0; i < 2; ++i) re[i] = ld_tcm(p.enc, 8, tile, e_row, 2u * e_cp + (i ^ sw));
+    };
+    // a staged 64-wide activation tile -> MN-major hi / lo planes + ReLU sign nibbles
+    auto stage_h = [&](uint8_t* buf, uint32_t layer) {
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            const uint32_t rr = h_r0 + 32u * (i >> 1), c = 2u * h_cp + ((i & 1u) ^ sw);
+            put_mask(layer, rr, c, rh[i]);
+            put_mn(buf, buf + kMn64, rr, c * 4u, rh[i].x, rh[i].y, rh[i].z, rh[i].w, split);
+        }
+    };
+    // masked data gradient, part a: accumulator columns 16 cg .. of this thread's row -> registers -> TMEM A planes
+    float v[16];
+    auto epilogue_tmem = [&](uint32_t layer) {
+        const uint32_t c0 = cg * 16u;
+        const uint32_t nib = *reinterpret_cast<const uint32_t*>(&s_mask[layer][row][cg * 4u]);      // 4 chunks = 16 columns
+        const uint32_t bits = (nib & 0xfu) | ((nib >> 4) & 0xf0u) | ((nib >> 8) & 0xf00u) | ((nib >> 12) & 0xf000u);
+        umma::tmem_ld16(lane_base + cDG + c0, v);
+#pragma unroll
+        for (uint32_t j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.0f;
+        put_tmem16(lane_base, c0, v, split);
+    };
+    // part b: the same 16 values -> MN-major tile bufB; instruction j of a lane carries chunk j ^ sw
+    auto epilogue_smem = [&]() {
+        const uint32_t c0 = cg * 16u;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t o = j ^ 1u;       // the other chunk of the pair
+            const float a = sw ? v[4 * o] : v[4 * j], b = sw ? v[4 * o + 1] : v[4 * j + 1];
+            const float c = sw ? v[4 * o + 2] : v[4 * j + 2], d = sw ? v[4 * o + 3] : v[4 * j + 3];
+            put_mn(bufB, bufB + kMn64, row, c0 + 4u * (j ^ sw), a, b, c, d, split);
+        }
+    };
+
+    load_h(p.h2, blockIdx.x);
+    load_g(blockIdx.x);
+
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
+        const uint32_t first = (it == 0) ? 0u : 1u;
+        const uint32_t next = tile + gridDim.x;
+        HEAD_TRACE(0);
+        // ---- G3 -> TMEM A planes; DG2 = G3 W3 starts before anything else of the tile is staged
+        {
+            float h0, h1, h2, h3, l0, l1, l2, l3;
+            if (split) {
+                umma::split_tf32(rgq.x, h0, l0); umma::split_tf32(rgq.y, h1, l1);
+                umma::split_tf32(rgq.z, h2, l2); umma::split_tf32(rgq.w, h3, l3);
+                umma::tmem_st4(lane_base + cAlo + cg * 4u, l0, l1, l2, l3);
+            } else {
+                h0 = round_tf32(rgq.x); h1 = round_tf32(rgq.y); h2 = round_tf32(rgq.z); h3 = round_tf32(rgq.w);
+            }
+            umma::tmem_st4(lane_base + cAhi + cg * 4u, h0, h1, h2, h3);
+        }
+        publish_tmem();
+        HEAD_TRACE(1);
+        // ---- H2 -> bufB, G3 -> bufG (the previous tile's dW1 has to be done with bufA / bufB first)
+        if (it > 0) wait_wgrad();
+        HEAD_TRACE(2);
+        stage_h(bufB, 1);
+        put_mn(bufG, bufG + kMn32, g_row, g_c * 4u, rg.x, rg.y, rg.z, rg.w, split);
+        publish_smem();
+        if (!HEAD_DBG(1)) load_h(p.h1, tile);                                  // consumed two phases further down
+        HEAD_TRACE(3);
+        wait_chain();                                        // DG2
+        HEAD_TRACE(4);
+        epilogue_tmem(1);                                    // G2 = DG2 * [H2 > 0]
+        publish_tmem();
+        HEAD_TRACE(5);
+        wait_wgrad();                                        // dW3 has released bufB
+        HEAD_TRACE(6);
+        epilogue_smem();
+        stage_h(bufA, 0);                                    // H1: bufA was released by the previous tile's dW1
+        publish_smem();
+        if (!HEAD_DBG(1)) load_enc(tile);                                      // consumed two phases further down
+        HEAD_TRACE(7);
+        wait_chain();                                        // DG1
+        HEAD_TRACE(8);
+        epilogue_tmem(0);                                    // G1 = DG1 * [H1 > 0]
+        publish_tmem();
+        HEAD_TRACE(9);
+        wait_wgrad();                                        // dW2 has released bufA and bufB
+        HEAD_TRACE(10);
+        epilogue_smem();
+#pragma unroll
+        for (uint32_t i = 0; i < 2; ++i)
+            put_mn(bufA, bufA + kMn32, e_row, (2u * e_cp + (i ^ sw)) * 4u, re[i].x, re[i].y, re[i].z, re[i].w, split);
+        HEAD_TRACE(14);
+        publish_smem();
+        HEAD_TRACE(15);
+        if (!HEAD_DBG(1)) { load_h(p.h2, next); load_g(next); }             // the staging registers are free: next tile's H2, G3
+        HEAD_TRACE(11);
+        wait_chain();                                        // DGE
+        HEAD_TRACE(12);
+        {                                                    // g_enc [B,32] row-major: one full 32-byte sector per thread
+            const uint32_t b = tile * kTile + row;
+            float e8[8];
+            umma::tmem_ld8(lane_base + cDG + cg * 8u, e8);
+            if (b < p.B) {
+                float4* dst = reinterpret_cast<float4*>(p.g_enc + (size_t)b * kIn + cg * 8u);
+                dst[0] = make_float4(e8[0], e8[1], e8[2], e8[3]);
+                dst[1] = make_float4(e8[4], e8[5], e8[6], e8[7]);
+            }
+        }
+        HEAD_TRACE(13);
+        // the next tile's G3 goes into the A planes at once: DGE, the last reader, has completed; this tile's reads of
+        // cDG are ordered before the next DG2 by the fence in publish_tmem()
+    }
+    if (it > 0) wait_wgrad();                              // the last dW1: every product of this CTA has completed
+    HEAD_MARK(3);
+
+    // ---- weight gradients: M = 64 accumulators, row (16 q + l) lives in TMEM lane (32 q + l), l < 16
+    {
+        const uint32_t wrow = q * 16 + lane;
+        const bool owns = lane < 16;
+        float w[16];
+        umma::tmem_ld16(lane_base + cW2 + cg * 16u, w);      // dW2[out=wrow][in = 16 cg ..]
+        if (owns && it > 0) {
+#pragma unroll
+            for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w2 + wrow * kHid + cg * 16u + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+        }
+        if (cg < 2) {                                        // dW1[out=wrow][in = 16 cg ..]
+            umma::tmem_ld16(lane_base + cW1 + cg * 16u, w);
+            if (owns && it > 0) {
+#pragma unroll
+                for (uint32_t j = 0; j < 16; j += 4) red_add_v4_f32(p.g_w1 + wrow * kIn + cg * 16u + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+            }
+        }
+        if (cg == 2) {                                       // dW3^T[in=wrow][out=c] -> g_w3[out][in]
+            umma::tmem_ld16(lane_base + cW3, w);
+            if (owns && it > 0) {
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) red_add_f32(p.g_w3 + j * kHid + wrow, w[j]);
+            }
+        }
+    }
+    HEAD_MARK(4);
+    }   // worker warps
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<head::kBwdTmemCols>(tmem);
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -867,8 +1224,12 @@ extern "C" int sanerf_field_head_forward_chunk(const float* x01, const float* ta
 }
 
 #ifdef SANERF_HEAD_TRACE
+extern "C" __attribute__((visibility("default"))) void sanerf_debug_head_flags(int flags) { g_head_dbg_host = flags; }
+extern "C" __attribute__((visibility("default"))) int sanerf_debug_head_marks(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_head_marks, sizeof(long long) * 8) == cudaSuccess ? 0 : 1;
+}
 extern "C" __attribute__((visibility("default"))) int sanerf_debug_head_trace(long long* out) {
-    return cudaMemcpyFromSymbol(out, g_head_trace, sizeof(long long) * 2 * 4 * 11) == cudaSuccess ? 0 : 1;
+    return cudaMemcpyFromSymbol(out, g_head_trace, sizeof(long long) * 2 * 4 * 16) == cudaSuccess ? 0 : 1;
 }
 #endif
 
@@ -886,11 +1247,20 @@ extern "C" int sanerf_field_head_backward(const float* enc, const float* h1, con
     SANERF_REQUIRE_PTR(w1); SANERF_REQUIRE_PTR(w2); SANERF_REQUIRE_PTR(w3);
     SANERF_REQUIRE_PTR(g_w1); SANERF_REQUIRE_PTR(g_w2); SANERF_REQUIRE_PTR(g_w3);
     if (precision != 0 && precision != 1) return fail(SANERF_ERR_INVALID_ARG, "field_head: precision 0 (3xTF32) or 1 (TF32)");
-    HeadBwdParams p{enc, h1, h2, g_out, w1, w2, w3, g_enc, x01, offsets, g_table, S, H, g_w1, g_w2, g_w3, B, precision};
+#ifdef SANERF_HEAD_TRACE
+    const int dbg = g_head_dbg_host;
+#else
+    const int dbg = 0;
+#endif
+    HeadBwdParams p{enc, h1, h2, g_out, w1, w2, w3, g_enc, x01, offsets, g_table, S, H, g_w1, g_w2, g_w3, B, precision, dbg};
     const uint32_t tiles = div_up(B, head::kTile);
     const uint32_t blocks = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
-    cudaError_t e = cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kBwdSmem);
+    // the fused-scatter form keeps the lock-step kernel (SANERF_HEAD_BWD_LOCKSTEP=1 selects it everywhere: A/B timing)
+    static const bool lockstep = [] { const char* s = getenv("SANERF_HEAD_BWD_LOCKSTEP"); return s != nullptr && atoi(s) != 0; }();
+    auto kernel = (x01 != nullptr || lockstep) ? head_backward_lockstep_kernel : head_backward_kernel;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head::kBwdSmem);
     if (e != cudaSuccess) return fail(SANERF_ERR_CUDA, "field_head_backward: %s", cudaGetErrorString(e));
-    SANERF_LAUNCH(head_backward_kernel, blocks, head::kBwdThreads, head::kBwdSmem, static_cast<cudaStream_t>(stream), p, tiles);
+    const uint32_t threads = (x01 != nullptr || lockstep) ? head::kBwdThreads : head::kBwdThreads2;
+    SANERF_LAUNCH(kernel, blocks, threads, head::kBwdSmem, static_cast<cudaStream_t>(stream), p, tiles);
     return check_launch("head_backward_kernel");
 }

@@ -194,6 +194,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
            "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
            "r"(__float_as_uint(v[7])) : "memory");
 }
+// registers -> TMEM: 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 :: "r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // TMEM address of (lane, column) relative to an allocation base: lane in bits 31..16, column in bits 15..0

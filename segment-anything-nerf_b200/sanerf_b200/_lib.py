@@ -11,7 +11,8 @@ import os
 import re
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_LIB_PATH = os.path.join(_PKG_DIR, "lib", "libsanerf_b200.so")
+# SANERF_LIB_PATH: diagnostic builds of the same library (e.g. -DSANERF_HEAD_TRACE); never a different implementation
+_LIB_PATH = os.environ.get("SANERF_LIB_PATH") or os.path.join(_PKG_DIR, "lib", "libsanerf_b200.so")
 _HEADER = os.path.join(os.path.dirname(_PKG_DIR), "include", "sanerf_b200.h")
 
 SANERF_F32, SANERF_F16 = 0, 1

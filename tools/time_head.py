@@ -40,3 +40,13 @@ def timeit(fn, n=10):
 for prec in (0, 1):
     print(f"B={B} precision={prec}: fwd(train) us {timeit(lambda: fwd(prec, True))}  fwd(infer) us {timeit(lambda: fwd(prec, False))}  "
           f"bwd us {timeit(lambda: bwd(prec))}", flush=True)
+
+# warm (no flush between launches): what the cold caches (instructions, weights, first tile) cost
+def warm(fn, n=10):
+    ts = []
+    for i in range(n + 3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        if i >= 3: ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ts)), float(min(ts))
+print(f"B={B} warm: fwd(train) us {warm(lambda: fwd(0, True))}  bwd us {warm(lambda: bwd(0))}", flush=True)
