@@ -82,6 +82,11 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// 256-bit store of eight consecutive floats (one full 32-byte sector)
+__device__ __forceinline__ void stg_f8(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 // write 4 consecutive K elements (one 16-byte chunk) of row r into the hi / lo planes of a chunk-major tile
 __device__ __forceinline__ void put_chunk(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t rows, uint32_t r, uint32_t chunk,
                                           float a, float b, float c, float d, bool split) {
@@ -367,10 +372,11 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             umma::fence_after_sync();
             float v[16];
             umma::tmem_ld16(lane_base + cD3, v);
-            if (row_live) {
-                float4* dst = reinterpret_cast<float4*>(p.out + (size_t)b * kOut);
-#pragma unroll
-                for (uint32_t j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (row_live) {                 // two 256-bit stores: every lane fills whole 32-byte sectors
+                const float lo8[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+                const float hi8[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+                stg_f8(p.out + (size_t)b * kOut, lo8);
+                stg_f8(p.out + (size_t)b * kOut + 8, hi8);
             }
             umma::fence_before_sync();   // orders this tile's TMEM reads before the next tile's MMAs (issued after bar 1)
         }
@@ -522,6 +528,39 @@ __device__ __forceinline__ float4 ldg_ef_f4(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+}
+// stage the TRANSPOSE of an nn.Linear weight (as stage_weight_t) with all of a thread's loads in flight before its first store
+template <uint32_t ROWS, uint32_t COLS, uint32_t NTHREADS>
+__device__ __forceinline__ void stage_weight_t_batched(const float* __restrict__ w, uint8_t* plane_hi, bool split, uint32_t tid) {
+    constexpr uint32_t kPer = (ROWS * COLS + NTHREADS - 1) / NTHREADS;
+    uint8_t* plane_lo = plane_hi + ROWS * COLS * 4;
+    float v[kPer];
+#pragma unroll
+    for (uint32_t j = 0; j < kPer; ++j) {
+        const uint32_t i = tid + j * NTHREADS;
+        v[j] = (i < ROWS * COLS) ? __ldg(w + i) : 0.0f;
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < kPer; ++j) {
+        const uint32_t i = tid + j * NTHREADS;
+        if (i < ROWS * COLS) {
+            const uint32_t r = i / COLS, c = i - r * COLS;          // W[r][c] -> tile row c, contraction index r
+            const uint32_t off = umma::tile_off(COLS, c, r);
+            if (split) {
+                float hi, lo;
+                umma::split_tf32(v[j], hi, lo);
+                *reinterpret_cast<float*>(plane_hi + off) = hi;
+                *reinterpret_cast<float*>(plane_lo + off) = lo;
+            } else {
+                *reinterpret_cast<float*>(plane_hi + off) = round_tf32(v[j]);
+            }
+        }
+    }
+}
+// 256-bit read-only load (two consecutive float4)
+__device__ __forceinline__ void ldg_nc_f8(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gptr), "r"(bytes) : "memory");
@@ -885,9 +924,9 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         umma::mbar_init(umma::smem_u32(&s_smem_ready), 1);
         umma::fence_mbar_init();
     }
-    stage_weight_t(p.w3, smem + oT3, kOut, kHid, split, tid, kBwdThreads2);
-    stage_weight_t(p.w2, smem + oT2, kHid, kHid, split, tid, kBwdThreads2);
-    stage_weight_t(p.w1, smem + oT1, kHid, kIn, split, tid, kBwdThreads2);
+    stage_weight_t_batched<kOut, kHid, kBwdThreads2>(p.w3, smem + oT3, split, tid);
+    stage_weight_t_batched<kHid, kHid, kBwdThreads2>(p.w2, smem + oT2, split, tid);
+    stage_weight_t_batched<kHid, kIn, kBwdThreads2>(p.w1, smem + oT1, split, tid);
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -1001,7 +1040,8 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     // ---- staging registers, loaded two phases before they are staged (tile-chunk-major pieces; one instruction = two runs of 16 rows x 16 B
     // of the two chunks of a pair: lanes alternate between the chunks in groups of four)
     float4 rh[4], re[2], rg, rgq;     // rh: H2 of the next tile, then H1 of the current one
-    const uint32_t h_cp = warp >> 1, h_r0 = (warp & 1u) * 64u + lane;      // H1 / H2: chunk pair, rows h_r0 + 32 i
+    const uint32_t h_cp = warp >> 1, h_r0 = (warp & 1u) * 64u + 2u * lane; // H1 / H2: chunk pair, rows h_r0, h_r0 + 1 (32 B per lane and chunk)
+    const uint32_t b1 = (lane >> 1) & 1u, b2 = sw;                         // lane bits that permute a thread's four pieces over its four stores
     const uint32_t e_cp = warp >> 2, e_row = (warp & 3u) * 32u + lane;     // enc: chunk pair, one row per lane
     const uint32_t g_row = warp * 8u + (lane >> 2), g_c = lane & 3u;       // g_out (row-major): 8 rows per instruction
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1022,9 +1062,18 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     auto put_mask = [&](uint32_t layer, uint32_t r, uint32_t c, const float4& v) {
         s_mask[layer][r][c] = (uint8_t)((v.x > 0.f) | ((v.y > 0.f) << 1) | ((v.z > 0.f) << 2) | ((v.w > 0.f) << 3));
     };
+    // rh[2 t + u] = chunk 2 h_cp + t, row h_r0 + u: one 256-bit load per chunk = 64 rows x 16 B = 1 KB contiguous per warp
     auto load_h = [&](const float* base, uint32_t tile) {
+        const uint32_t bb = tile * kTile + h_r0;
 #pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) rh[i] = ld_tcm(base, 16, tile, h_r0 + 32u * (i >> 1), 2u * h_cp + ((i & 1u) ^ sw));
+        for (uint32_t t = 0; t < 2; ++t) {
+            if (tile < tiles && bb < p.B) {
+                ldg_nc_f8(base + tcm_off(bb, 2u * h_cp + t, 16), rh[2 * t], rh[2 * t + 1]);
+                if (bb + 1u >= p.B) rh[2 * t + 1] = zero4;
+            } else {
+                rh[2 * t] = rh[2 * t + 1] = zero4;
+            }
+        }
     };
     auto load_g = [&](uint32_t tile) {
         rg = ld_row(p.g_out, kOut, tile, g_row, g_c);        // for the MN-major tile: 8 rows per instruction
@@ -1035,12 +1084,22 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         for (uint32_t i = 0; i < 2; ++i) re[i] = ld_tcm(p.enc, 8, tile, e_row, 2u * e_cp + (i ^ sw));
     };
     // a staged 64-wide activation tile -> MN-major hi / lo planes + ReLU sign nibbles
+    // store (j1, j0) of a lane carries piece (t, u) = (j1 ^ b2, j0 ^ b1): over the 32 lanes of one store instruction the rows
+    // take all four values of k & 3 and the chunks both halves of a 32-byte slot - eight 16-byte bank groups, four lanes each
     auto stage_h = [&](uint8_t* buf, uint32_t layer) {
+        float4 pc[4] = {rh[0], rh[1], rh[2], rh[3]};
+        auto cswap = [](bool c, float4& a, float4& b) {
+            const float4 ta = a, tb = b;
+            a = c ? tb : ta; b = c ? ta : tb;
+        };
+        cswap(b1 != 0u, pc[0], pc[1]); cswap(b1 != 0u, pc[2], pc[3]);
+        cswap(b2 != 0u, pc[0], pc[2]); cswap(b2 != 0u, pc[1], pc[3]);
 #pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) {
-            const uint32_t rr = h_r0 + 32u * (i >> 1), c = 2u * h_cp + ((i & 1u) ^ sw);
-            put_mask(layer, rr, c, rh[i]);
-            put_mn(buf, buf + kMn64, rr, c * 4u, rh[i].x, rh[i].y, rh[i].z, rh[i].w, split);
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t t = (j >> 1) ^ b2, u = (j & 1u) ^ b1;
+            const uint32_t rr = h_r0 + u, c = 2u * h_cp + t;
+            put_mask(layer, rr, c, pc[j]);
+            put_mn(buf, buf + kMn64, rr, c * 4u, pc[j].x, pc[j].y, pc[j].z, pc[j].w, split);
         }
     };
     // masked data gradient, part a: accumulator columns 16 cg .. of this thread's row -> registers -> TMEM A planes
@@ -1130,11 +1189,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
             const uint32_t b = tile * kTile + row;
             float e8[8];
             umma::tmem_ld8(lane_base + cDG + cg * 8u, e8);
-            if (b < p.B) {
-                float4* dst = reinterpret_cast<float4*>(p.g_enc + (size_t)b * kIn + cg * 8u);
-                dst[0] = make_float4(e8[0], e8[1], e8[2], e8[3]);
-                dst[1] = make_float4(e8[4], e8[5], e8[6], e8[7]);
-            }
+            if (b < p.B) stg_f8(p.g_enc + (size_t)b * kIn + cg * 8u, e8);
         }
         HEAD_TRACE(13);
         // the next tile's G3 goes into the A planes at once: DGE, the last reader, has completed; this tile's reads of
