@@ -907,7 +907,6 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     using namespace head;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_chain, s_wgrad, s_tmem_ready, s_smem_ready;
-    __shared__ __align__(16) uint8_t s_mask[2][kTile][16];     // ReLU sign patterns of H1 / H2: one nibble per 4-feature chunk
     __shared__ uint32_t s_tmem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool split = (p.precision == 0);
@@ -1043,7 +1042,9 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     const uint32_t h_cp = warp >> 1, h_r0 = (warp & 1u) * 64u + 2u * lane; // H1 / H2: chunk pair, rows h_r0, h_r0 + 1 (32 B per lane and chunk)
     const uint32_t b1 = (lane >> 1) & 1u, b2 = sw;                         // lane bits that permute a thread's four pieces over its four stores
     const uint32_t e_cp = warp >> 2, e_row = (warp & 3u) * 32u + lane;     // enc: chunk pair, one row per lane
-    const uint32_t g_row = warp * 8u + (lane >> 2), g_c = lane & 3u;       // g_out (row-major): 8 rows per instruction
+    // g_out (row-major): 8 rows per instruction; rows 1 <-> 2 and 5 <-> 6 trade places so that the two rows a quarter-warp
+    // stores differ by 2 mod 4 (conflict-free in the swizzled tile)
+    const uint32_t g_i = lane >> 2, g_row = warp * 8u + ((g_i & 4u) | ((g_i & 1u) << 1) | ((g_i >> 1) & 1u)), g_c = lane & 3u;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto ld_tcm = [&](const float* base, uint32_t chunks, uint32_t tile, uint32_t r, uint32_t c) -> float4 {
         const uint32_t bb = tile * kTile + r;
@@ -1059,8 +1060,20 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         const uint32_t bb = tile * kTile + r;
         return (tile < tiles && bb < p.B) ? ldg_nc_f4(base + (size_t)bb * width + 4u * c) : zero4;
     };
-    auto put_mask = [&](uint32_t layer, uint32_t r, uint32_t c, const float4& v) {
-        s_mask[layer][r][c] = (uint8_t)((v.x > 0.f) | ((v.y > 0.f) << 1) | ((v.z > 0.f) << 2) | ((v.w > 0.f) << 3));
+    // an activation chunk as saved by the forward -> MN-major planes.  The hi plane takes the RAW values (the tensor core
+    // ignores the 13 low mantissa bits of a tf32 operand itself: bit-identical products, see gemm_tma.cu), so the epilogue
+    // reads the ReLU signs of its 16 columns straight from that plane - no separate sign table (whose byte stores were
+    // 8-way bank-conflicted: 1.8 M excessive wavefronts per launch, profiles/r2_head_backward.md)
+    auto put_act = [&](uint8_t* hi_plane, uint8_t* lo_plane, uint32_t kk, uint32_t f, const float4& x) {
+        const uint32_t off = umma::mn32_off(kTile, kk, f);
+        if (split) {
+            float h0, h1, h2, h3, l0, l1, l2, l3;
+            umma::split_tf32(x.x, h0, l0); umma::split_tf32(x.y, h1, l1); umma::split_tf32(x.z, h2, l2); umma::split_tf32(x.w, h3, l3);
+            *reinterpret_cast<float4*>(hi_plane + off) = x;
+            *reinterpret_cast<float4*>(lo_plane + off) = make_float4(l0, l1, l2, l3);
+        } else {
+            *reinterpret_cast<float4*>(hi_plane + off) = make_float4(round_tf32(x.x), round_tf32(x.y), round_tf32(x.z), round_tf32(x.w));
+        }
     };
     // rh[2 t + u] = chunk 2 h_cp + t, row h_r0 + u: one 256-bit load per chunk = 64 rows x 16 B = 1 KB contiguous per warp
     auto load_h = [&](const float* base, uint32_t tile) {
@@ -1086,7 +1099,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     // a staged 64-wide activation tile -> MN-major hi / lo planes + ReLU sign nibbles
     // store (j1, j0) of a lane carries piece (t, u) = (j1 ^ b2, j0 ^ b1): over the 32 lanes of one store instruction the rows
     // take all four values of k & 3 and the chunks both halves of a 32-byte slot - eight 16-byte bank groups, four lanes each
-    auto stage_h = [&](uint8_t* buf, uint32_t layer) {
+    auto stage_h = [&](uint8_t* buf) {
         float4 pc[4] = {rh[0], rh[1], rh[2], rh[3]};
         auto cswap = [](bool c, float4& a, float4& b) {
             const float4 ta = a, tb = b;
@@ -1098,16 +1111,22 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         for (uint32_t j = 0; j < 4; ++j) {
             const uint32_t t = (j >> 1) ^ b2, u = (j & 1u) ^ b1;
             const uint32_t rr = h_r0 + u, c = 2u * h_cp + t;
-            put_mask(layer, rr, c, pc[j]);
-            put_mn(buf, buf + kMn64, rr, c * 4u, pc[j].x, pc[j].y, pc[j].z, pc[j].w, split);
+            put_act(buf, buf + kMn64, rr, c * 4u, pc[j]);
         }
     };
     // masked data gradient, part a: accumulator columns 16 cg .. of this thread's row -> registers -> TMEM A planes
     float v[16];
-    auto epilogue_tmem = [&](uint32_t layer) {
+    // `act` = hi plane of the layer's own activation tile (this row, these 16 columns: the ReLU derivative); the four
+    // 16-byte reads of a lane go in the order j ^ sw, like its stores: bank-conflict-free
+    auto epilogue_tmem = [&](const uint8_t* act) {
         const uint32_t c0 = cg * 16u;
-        const uint32_t nib = *reinterpret_cast<const uint32_t*>(&s_mask[layer][row][cg * 4u]);      // 4 chunks = 16 columns
-        const uint32_t bits = (nib & 0xfu) | ((nib >> 4) & 0xf0u) | ((nib >> 8) & 0xf00u) | ((nib >> 12) & 0xf000u);
+        uint32_t bits = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t ch = j ^ sw;
+            const float4 a = *reinterpret_cast<const float4*>(act + umma::mn32_off(kTile, row, c0 + 4u * ch));
+            bits |= (uint32_t)((a.x > 0.f) | ((a.y > 0.f) << 1) | ((a.z > 0.f) << 2) | ((a.w > 0.f) << 3)) << (4u * ch);
+        }
         umma::tmem_ld16(lane_base + cDG + c0, v);
 #pragma unroll
         for (uint32_t j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.0f;
@@ -1150,26 +1169,26 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         // ---- H2 -> bufB, G3 -> bufG (the previous tile's dW1 has to be done with bufA / bufB first)
         if (it > 0) wait_wgrad();
         HEAD_TRACE(2);
-        stage_h(bufB, 1);
+        stage_h(bufB);
         put_mn(bufG, bufG + kMn32, g_row, g_c * 4u, rg.x, rg.y, rg.z, rg.w, split);
         publish_smem();
         if (!HEAD_DBG(1)) load_h(p.h1, tile);                                  // consumed two phases further down
         HEAD_TRACE(3);
         wait_chain();                                        // DG2
         HEAD_TRACE(4);
-        epilogue_tmem(1);                                    // G2 = DG2 * [H2 > 0]
+        epilogue_tmem(bufB);                                    // G2 = DG2 * [H2 > 0]
         publish_tmem();
         HEAD_TRACE(5);
         wait_wgrad();                                        // dW3 has released bufB
         HEAD_TRACE(6);
         epilogue_smem();
-        stage_h(bufA, 0);                                    // H1: bufA was released by the previous tile's dW1
+        stage_h(bufA);                                    // H1: bufA was released by the previous tile's dW1
         publish_smem();
         if (!HEAD_DBG(1)) load_enc(tile);                                      // consumed two phases further down
         HEAD_TRACE(7);
         wait_chain();                                        // DG1
         HEAD_TRACE(8);
-        epilogue_tmem(0);                                    // G1 = DG1 * [H1 > 0]
+        epilogue_tmem(bufA);                                    // G1 = DG1 * [H1 > 0]
         publish_tmem();
         HEAD_TRACE(9);
         wait_wgrad();                                        // dW2 has released bufA and bufB
