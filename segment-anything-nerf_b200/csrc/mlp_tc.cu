@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_lockstep_k
 //    into tensor memory while the weight-gradient product of the previous stage still runs; the shared-memory copy of
 //    the same gradient tile (the MN-major operand of the NEXT weight-gradient product) is written afterwards, beside
 //    the next chain product.  Per 128-sample tile the tensor pipe sees DG2 | dW3 | DG1 | dW2 | DGE | dW1 back to back
-//    instead of three issue -> drain -> epilogue rounds (measured phase times: profiles/r2_head_backward.md);
+//    instead of three issue -> drain -> epilogue rounds (measured phase times: profiles/r2b_head_backward.md);
 //  * DG2 of a tile only needs G3 in tensor memory, so it is issued before the tile's activations are staged;
 //  * every 16-byte store into an MN-major tile is bank-conflict-free: in the 128-byte-swizzle / 32-byte-atom layout the
 //    32 rows a warp writes land in only four 32-byte slots of a 128-byte line, so lanes alternate (by bit 2 of the lane)
@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     // workers' barrier (a proxy fence anywhere on the causality path from the stores to the tensor-core reads orders them).
     // On the writers' side fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for every global
     // load the thread has in flight: with the staging registers loaded one phase ahead that exposed the whole HBM latency
-    // three times per tile (measured: 14.1 k -> 10.0 k clocks per tile without the loads, profiles/r2_head_backward.md).
+    // three times per tile (measured: 14.1 k -> 10.0 k clocks per tile without the loads, profiles/r2b_head_backward.md).
     auto publish_smem = [&]() {
         umma::fence_before_sync(); named_bar_sync(1, kBwdThreads);
         if (tid == 0) mbar_arrive(bar_smem_ready);
@@ -1063,7 +1063,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     // an activation chunk as saved by the forward -> MN-major planes.  The hi plane takes the RAW values (the tensor core
     // ignores the 13 low mantissa bits of a tf32 operand itself: bit-identical products, see gemm_tma.cu), so the epilogue
     // reads the ReLU signs of its 16 columns straight from that plane - no separate sign table (whose byte stores were
-    // 8-way bank-conflicted: 1.8 M excessive wavefronts per launch, profiles/r2_head_backward.md)
+    // 8-way bank-conflicted: 1.8 M excessive wavefronts per launch, profiles/r2b_head_backward.md)
     auto put_act = [&](uint8_t* hi_plane, uint8_t* lo_plane, uint32_t kk, uint32_t f, const float4& x) {
         const uint32_t off = umma::mn32_off(kTile, kk, f);
         if (split) {
