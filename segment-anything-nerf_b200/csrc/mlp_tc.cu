@@ -557,6 +557,14 @@ __device__ __forceinline__ void stage_weight_t_batched(const float* __restrict__
         }
     }
 }
+// 1-D bulk copy global -> shared memory (TMA, no tensor map); completion = transaction bytes on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar_saddr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_saddr), "r"(bytes) : "memory");
+}
 // 256-bit read-only load (two consecutive float4)
 __device__ __forceinline__ void ldg_nc_f8(const float* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -906,7 +914,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     HEAD_MARK(1);
     using namespace head;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_chain, s_wgrad, s_tmem_ready, s_smem_ready;
+    __shared__ __align__(8) uint64_t s_chain, s_wgrad, s_tmem_ready, s_smem_ready, s_land;
     __shared__ uint32_t s_tmem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool split = (p.precision == 0);
@@ -921,6 +929,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         umma::mbar_init(umma::smem_u32(&s_wgrad), 1);
         umma::mbar_init(umma::smem_u32(&s_tmem_ready), 1);
         umma::mbar_init(umma::smem_u32(&s_smem_ready), 1);
+        umma::mbar_init(umma::smem_u32(&s_land), 1);
         umma::fence_mbar_init();
     }
     stage_weight_t_batched<kOut, kHid, kBwdThreads2>(p.w3, smem + oT3, split, tid);
@@ -1039,8 +1048,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
     // ---- staging registers, loaded two phases before they are staged (tile-chunk-major pieces; one instruction = two runs of 16 rows x 16 B
     // of the two chunks of a pair: lanes alternate between the chunks in groups of four)
     float4 rh[4], re[2], rg, rgq;     // rh: H2 of the next tile, then H1 of the current one
-    const uint32_t h_cp = warp >> 1, h_r0 = (warp & 1u) * 64u + 2u * lane; // H1 / H2: chunk pair, rows h_r0, h_r0 + 1 (32 B per lane and chunk)
-    const uint32_t b1 = (lane >> 1) & 1u, b2 = sw;                         // lane bits that permute a thread's four pieces over its four stores
+    const uint32_t h_cp = warp >> 1, h_r0 = (warp & 1u) * 64u + lane;      // H1 / H2: chunk pair, rows h_r0 + 32 i
     const uint32_t e_cp = warp >> 2, e_row = (warp & 3u) * 32u + lane;     // enc: chunk pair, one row per lane
     // g_out (row-major): 8 rows per instruction; rows 1 <-> 2 and 5 <-> 6 trade places so that the two rows a quarter-warp
     // stores differ by 2 mod 4 (conflict-free in the swizzled tile)
@@ -1075,17 +1083,25 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
             *reinterpret_cast<float4*>(hi_plane + off) = make_float4(round_tf32(x.x), round_tf32(x.y), round_tf32(x.z), round_tf32(x.w));
         }
     };
-    // rh[2 t + u] = chunk 2 h_cp + t, row h_r0 + u: one 256-bit load per chunk = 64 rows x 16 B = 1 KB contiguous per warp
-    auto load_h = [&](const float* base, uint32_t tile) {
-        const uint32_t bb = tile * kTile + h_r0;
+    // H2 / H1 do not come through the L1 (which 217 KB of tiles leave ~30 KB of): thread 0 has the raw 32 KB tile-chunk-major
+    // tile LANDED by a bulk copy in the one region that is idle at that time - the lo plane of bufA (H1's), free from the end
+    // of dW2 of one tile to the H1 staging of the next - H2 of the next tile during E4b / E5, then H1 of the tile between its
+    // H2 staging and its own staging; the workers read their pieces from there (conflict-free LDS.128).
+    uint8_t* landing = bufA + kMn64;
+    const uint32_t bar_land = umma::smem_u32(&s_land);
+    uint32_t ph_land = 0;
+    auto land = [&](const float* base, uint32_t tile) {          // thread 0, after a barrier behind every reader of the region
+        umma::fence_proxy_async();                               // earlier generic-proxy accesses of the region -> async-proxy write
+        mbar_arrive_expect_tx(bar_land, kTile * kHid * 4u);
+        bulk_copy_g2s(umma::smem_u32(landing), base + (size_t)tile * kTile * kHid, kTile * kHid * 4u, bar_land);
+    };
+    auto load_h = [&](uint32_t tile) {                           // rh[2 i + t] = row h_r0 + 32 i, chunk 2 h_cp + (t ^ sw)
+        umma::mbar_wait(bar_land, ph_land); ph_land ^= 1u;
 #pragma unroll
-        for (uint32_t t = 0; t < 2; ++t) {
-            if (tile < tiles && bb < p.B) {
-                ldg_nc_f8(base + tcm_off(bb, 2u * h_cp + t, 16), rh[2 * t], rh[2 * t + 1]);
-                if (bb + 1u >= p.B) rh[2 * t + 1] = zero4;
-            } else {
-                rh[2 * t] = rh[2 * t + 1] = zero4;
-            }
+        for (uint32_t i = 0; i < 4; ++i) {
+            const uint32_t rr = h_r0 + 32u * (i >> 1), c = 2u * h_cp + ((i & 1u) ^ sw);
+            rh[i] = *reinterpret_cast<const float4*>(landing + (c * kTile + rr) * 16u);
+            if (tile * kTile + rr >= p.B) rh[i] = zero4;         // rows past B of the last tile are not initialised
         }
     };
     auto load_g = [&](uint32_t tile) {
@@ -1096,22 +1112,12 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
 #pragma unroll
         for (uint32_t i = 0; i < 2; ++i) re[i] = ld_tcm(p.enc, 8, tile, e_row, 2u * e_cp + (i ^ sw));
     };
-    // a staged 64-wide activation tile -> MN-major hi / lo planes + ReLU sign nibbles
-    // store (j1, j0) of a lane carries piece (t, u) = (j1 ^ b2, j0 ^ b1): over the 32 lanes of one store instruction the rows
-    // take all four values of k & 3 and the chunks both halves of a 32-byte slot - eight 16-byte bank groups, four lanes each
+    // a 64-wide activation tile -> MN-major hi (raw) / lo planes; lanes alternate between the two chunks of a pair
     auto stage_h = [&](uint8_t* buf) {
-        float4 pc[4] = {rh[0], rh[1], rh[2], rh[3]};
-        auto cswap = [](bool c, float4& a, float4& b) {
-            const float4 ta = a, tb = b;
-            a = c ? tb : ta; b = c ? ta : tb;
-        };
-        cswap(b1 != 0u, pc[0], pc[1]); cswap(b1 != 0u, pc[2], pc[3]);
-        cswap(b2 != 0u, pc[0], pc[2]); cswap(b2 != 0u, pc[1], pc[3]);
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t t = (j >> 1) ^ b2, u = (j & 1u) ^ b1;
-            const uint32_t rr = h_r0 + u, c = 2u * h_cp + t;
-            put_act(buf, buf + kMn64, rr, c * 4u, pc[j]);
+        for (uint32_t i = 0; i < 4; ++i) {
+            const uint32_t rr = h_r0 + 32u * (i >> 1), c = 2u * h_cp + ((i & 1u) ^ sw);
+            put_act(buf, buf + kMn64, rr, c * 4u, rh[i]);
         }
     };
     // masked data gradient, part a: accumulator columns 16 cg .. of this thread's row -> registers -> TMEM A planes
@@ -1144,8 +1150,9 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         }
     };
 
-    load_h(p.h2, blockIdx.x);
+    if (tid == 0 && blockIdx.x < tiles) land(p.h2, blockIdx.x);
     load_g(blockIdx.x);
+    load_enc(blockIdx.x);
 
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
@@ -1169,10 +1176,11 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         // ---- H2 -> bufB, G3 -> bufG (the previous tile's dW1 has to be done with bufA / bufB first)
         if (it > 0) wait_wgrad();
         HEAD_TRACE(2);
+        load_h(tile);                                        // H2, landed during the previous tile's last phases
         stage_h(bufB);
         put_mn(bufG, bufG + kMn32, g_row, g_c * 4u, rg.x, rg.y, rg.z, rg.w, split);
-        publish_smem();
-        if (!HEAD_DBG(1)) load_h(p.h1, tile);                                  // consumed two phases further down
+        publish_smem();                                      // (also: every worker has read the landing region)
+        if (tid == 0) land(p.h1, tile);                      // consumed two phases further down
         HEAD_TRACE(3);
         wait_chain();                                        // DG2
         HEAD_TRACE(4);
@@ -1182,9 +1190,10 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         wait_wgrad();                                        // dW3 has released bufB
         HEAD_TRACE(6);
         epilogue_smem();
-        stage_h(bufA);                                    // H1: bufA was released by the previous tile's dW1
+        load_h(tile);                                        // H1: raw tile in the landing region = the lo plane it is about to fill
+        named_bar_sync(2, kBwdThreads);                      // every worker holds its pieces before anyone overwrites the region
+        stage_h(bufA);                                       // bufA was released by the previous tile's dW1
         publish_smem();
-        if (!HEAD_DBG(1)) load_enc(tile);                                      // consumed two phases further down
         HEAD_TRACE(7);
         wait_chain();                                        // DG1
         HEAD_TRACE(8);
@@ -1193,6 +1202,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         HEAD_TRACE(9);
         wait_wgrad();                                        // dW2 has released bufA and bufB
         HEAD_TRACE(10);
+        if (tid == 0 && next < tiles) land(p.h2, next);      // dW2 was the last reader of bufA's lo plane
         epilogue_smem();
 #pragma unroll
         for (uint32_t i = 0; i < 2; ++i)
@@ -1200,7 +1210,7 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
         HEAD_TRACE(14);
         publish_smem();
         HEAD_TRACE(15);
-        if (!HEAD_DBG(1)) { load_h(p.h2, next); load_g(next); }             // the staging registers are free: next tile's H2, G3
+        if (!HEAD_DBG(1)) { load_g(next); load_enc(next); }                   // next tile's G3 and encoding: a tile ahead
         HEAD_TRACE(11);
         wait_chain();                                        // DGE
         HEAD_TRACE(12);
