@@ -27,17 +27,21 @@ struct PropParams {
     float S;
 };
 
+// `geo` / `base`: the per-level geometry, computed once per CTA (shared memory; every lane reads the same words: broadcast).
+// Evaluated per thread it was ~50 of the ~280 instructions a sample spends per level (exp2f, the stride loop, two dependent
+// offset loads in front of the gathers) in a kernel that ncu shows issue-bound (issue slots 55 % busy at 4 warps per scheduler).
 template <uint32_t L>
-__device__ __forceinline__ void prop_encode(const PropParams& p, const float (&x)[3], bool oob, float (&enc)[2 * L]) {
+__device__ __forceinline__ void prop_encode(const PropParams& p, const LevelGeom<3>* __restrict__ s_geo, const uint32_t* __restrict__ s_base,
+                                            const float (&x)[3], bool oob, float (&enc)[2 * L]) {
     const float* __restrict__ table = p.table;
     float2 val[L][8];
     float frac[L][3];
 #pragma unroll
     for (uint32_t l = 0; l < L; ++l) {
         if (!oob) {
-            const LevelGeom<3> geo = level_geometry<3>(p.offsets, l, p.S, p.H, 0u);
+            const LevelGeom<3> geo = s_geo[l];
             const Cell<3> cell = locate<3>(geo, x, false, 0u);
-            const size_t base = (size_t)(uint32_t)__ldg(p.offsets + l);
+            const size_t base = (size_t)s_base[l];
 #pragma unroll
             for (uint32_t d = 0; d < 3; ++d) frac[l][d] = cell.f[d];
 #pragma unroll
@@ -71,11 +75,17 @@ template <uint32_t L>
 __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropParams p, float* __restrict__ sigma,
                                                                     float* __restrict__ enc_out) {
     pdl_begin();
-    constexpr uint32_t IN = 2 * L;
-    __shared__ float s_w1[kPropHidden * IN];
+    constexpr uint32_t IN = 2 * L, INP = (IN + 3u) & ~3u;          // weight rows padded to whole float4: 128-bit broadcast reads
+    __shared__ __align__(16) float s_w1[kPropHidden * INP];
     __shared__ float s_w2[kPropHidden];
-    for (uint32_t i = threadIdx.x; i < kPropHidden * IN; i += blockDim.x) s_w1[i] = __ldg(p.w1 + i);
+    __shared__ LevelGeom<3> s_geo[L];
+    __shared__ uint32_t s_base[L];
+    for (uint32_t i = threadIdx.x; i < kPropHidden * IN; i += blockDim.x) s_w1[(i / IN) * INP + (i % IN)] = __ldg(p.w1 + i);
     if (threadIdx.x < kPropHidden) s_w2[threadIdx.x] = __ldg(p.w2 + threadIdx.x);
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + L) {
+        s_geo[threadIdx.x - 32] = level_geometry<3>(p.offsets, threadIdx.x - 32, p.S, p.H, 0u);
+        s_base[threadIdx.x - 32] = (uint32_t)__ldg(p.offsets + (threadIdx.x - 32));
+    }
     __syncthreads();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.B) return;
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropPa
 #pragma unroll
     for (uint32_t d = 0; d < 3; ++d) x[d] = __ldg(p.x01 + (size_t)b * 3 + d);
     float enc[IN];
-    prop_encode<L>(p, x, out_of_range<3>(x), enc);
+    prop_encode<L>(p, s_geo, s_base, x, out_of_range<3>(x), enc);
     if (enc_out != nullptr) {                // kept for the backward: 8 L bytes per sample instead of 8 L gathers
 #pragma unroll
         for (uint32_t l = 0; l < L; ++l)
@@ -92,9 +102,15 @@ __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropPa
     float pre = 0.0f;
 #pragma unroll
     for (uint32_t j = 0; j < kPropHidden; ++j) {
+        float wj[INP];
+#pragma unroll
+        for (uint32_t i = 0; i < INP; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_w1 + j * INP + i);
+            wj[i] = w4.x; wj[i + 1] = w4.y; wj[i + 2] = w4.z; wj[i + 3] = w4.w;
+        }
         float h = 0.0f;
 #pragma unroll
-        for (uint32_t i = 0; i < IN; ++i) h = __fmaf_rn(s_w1[j * IN + i], enc[i], h);
+        for (uint32_t i = 0; i < IN; ++i) h = __fmaf_rn(wj[i], enc[i], h);      // same order as before: bit-identical
         pre = __fmaf_rn(s_w2[j], fmaxf(h, 0.0f), pre);
     }
     sigma[b] = expf(pre);                    // trunc_exp forward (activation.py:10)
