@@ -21,8 +21,11 @@
 
 namespace sanerf {
 
+#ifndef SANERF_GTMA_STAGES
+#define SANERF_GTMA_STAGES 4
+#endif
 namespace gtma {
-constexpr uint32_t kBM = 128, kBN = 64, kKC = 32, kWorkers = 256, kStages = 3;
+constexpr uint32_t kBM = 128, kBN = 64, kKC = 32, kWorkers = 256, kStages = SANERF_GTMA_STAGES;
 constexpr uint32_t kThreads = kWorkers + 64;                        // + MMA-issuing warp + TMA-producer warp
 constexpr uint32_t kATile = kBM * kKC * 4, kBTile = kBN * kKC * 4;  // 16 KB, 8 KB (one plane)
 constexpr uint32_t kStageBytes = 2 * kATile + 2 * kBTile;           // A hi | A lo | B hi | B lo = 48 KB
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(gtma::kThreads) gemm_tma_kernel(const __grid_c
             const uint32_t s = c % kStages;
             umma::mbar_wait(umma::smem_u32(&s_full[s]), (c / kStages) & 1u);
             if (umma::elect_one()) {
+                umma::fence_proxy_async();
                 umma::fence_after_sync();
                 const uint32_t sa = umma::smem_u32(smem + s * kStageBytes);
                 const uint32_t dAh = umma::desc_lo(sa, 16u), dAl = umma::desc_lo(sa + kATile, 16u);
@@ -165,7 +169,8 @@ __global__ void __launch_bounds__(gtma::kThreads) gemm_tma_kernel(const __grid_c
                     *hp = make_float4(rna_tf32(x.x), rna_tf32(x.y), rna_tf32(x.z), rna_tf32(x.w));
                 }
             }
-            umma::fence_proxy_async();                   // generic-proxy stores -> visible to the tensor core
+            // the generic -> async proxy fence for the lo planes is executed by the issuing thread after it has observed this
+            // barrier (one MEMBAR per chunk instead of one per worker warp; profiles/r2b_head_backward.md)
             __syncwarp();
             if (lane == 0) gtma_arrive(umma::smem_u32(&s_full[s]));
         }

@@ -206,6 +206,33 @@ def test_fused_adam_matches_torch_adam(cuda):
     assert int(opt.step_count.item()) == 80
 
 
+def test_fused_adam_large_pass_matches_torch_adam(cuda):
+    """A large pass (whole table sized, with a ragged tail): torch.optim.Adam semantics over several steps of a schedule,
+    gradients cleared; a range whose gate is clear is left untouched."""
+    torch.manual_seed(1)
+    n = (1 << 22) + 768 * 5 + 333                       # whole chunks + a ragged tail
+    p = torch.randn(n, device="cuda").requires_grad_(True)
+    q = p.detach().clone().requires_grad_(True)
+    ref = torch.optim.Adam([q], lr=1e-2, eps=1e-15)
+    sched = torch.optim.lr_scheduler.LambdaLR(ref, lambda it: 0.1 ** min(it / 50, 1))
+    opt = fused.FusedAdam([p], lr=1e-2, eps=1e-15, decay_iters=50)
+    for it in range(6):
+        gr = torch.randn(n, device="cuda") * (0.0 if it == 2 else 1.0)
+        p.grad.copy_(gr)
+        q.grad = gr.clone()
+        opt.step(grad_scale=1.0, zero_grad=True)
+        ref.step(); sched.step()
+        assert float(p.grad.abs().max()) == 0
+    torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-4, atol=1e-5)
+    # a range whose gate is clear is not touched (deferred update after flush())
+    before = p.detach().clone()
+    p.grad.fill_(1.0)
+    opt.clear_gate()
+    opt.apply(0, n, gated=True)
+    torch.cuda.synchronize()
+    assert torch.equal(p.detach(), before) and float(p.grad.min()) == 1.0
+
+
 def test_fused_renderer_equals_generic_renderer(cuda):
     """Same parameters, same random draws: the fused fast path and the op-by-op path agree."""
     from tests.test_gpu_render import build_pair, rays
