@@ -204,8 +204,28 @@ __device__ __forceinline__ void relu_to_tmem(uint32_t lane_base, uint32_t c_acc,
     }
 }
 
+// Phase timestamps of CTA 0 (diagnostics; compiled in only with -DSANERF_HEAD_TRACE): [thread 0][tile 0..3][11]
+#ifdef SANERF_HEAD_TRACE
+static int g_head_dbg_host = 0;
+#define HEAD_DBG(bit) ((p.dbg & (bit)) != 0)
+__device__ long long g_head_trace[2 * 4 * 16];
+__device__ long long g_head_marks[8];          // CTA 0, thread 0: entry, prologue done, loop done, exit
+#define HEAD_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_marks[i] = clock64(); } while (0)
+#define HEAD_TRACE(slot)                                                                                   \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && it < 4 && (tid == 0 || tid == 128))                                         \
+            g_head_trace[((tid == 0 ? 0 : 1) * 4 + it) * 16 + (slot)] = clock64();                          \
+    } while (0)
+#else
+#define HEAD_TRACE(slot) do {} while (0)
+#define HEAD_MARK(i) do {} while (0)
+#define HEAD_DBG(bit) false
+#endif
+
 __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const HeadFwdParams p, const uint32_t tiles_arg) {
+    HEAD_MARK(0);
     pdl_begin();
+    HEAD_MARK(1);
     using namespace head;
     // number of samples to evaluate: all B, or chunk_len per ray still alive (the count lives on the device: no host sync)
     const uint32_t work = (p.ray_list != nullptr) ? __ldg(p.list_count) * p.chunk_len : p.B;
@@ -241,6 +261,7 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
+    HEAD_MARK(2);
 
     if (warp >= kMlpWarps) {
         // ===================== producers: encoding of one sample x 4 levels -> A-operand slot =====================
@@ -329,6 +350,7 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
             const uint32_t slot = it & 1u;
             if (warp == 0) {              // warp-uniform branch + elected lane: the issue loop stays on the uniform datapath
                 umma::mbar_wait(umma::smem_u32(&s_full[slot]), (it >> 1) & 1u);
+                if (it == 0) HEAD_MARK(3);
                 if (umma::elect_one()) {
                     umma::fence_after_sync();
                     issue_gemm_ts<kHid, kIn>(tmem + cD1, tmem + cEnc + slot * 64u, tmem + cEnc + slot * 64u + 32u, dW1h, dW1l, split);
@@ -379,10 +401,13 @@ __global__ void __launch_bounds__(head::kThreads, 1) head_forward_kernel(const H
                 stg_f8(p.out + (size_t)b * kOut + 8, hi8);
             }
             umma::fence_before_sync();   // orders this tile's TMEM reads before the next tile's MMAs (issued after bar 1)
+            if (it == 0) HEAD_MARK(4);
         }
+        HEAD_MARK(5);
     }
     umma::fence_before_sync();
     __syncthreads();
+    HEAD_MARK(6);
     if (warp == 0) umma::tmem_dealloc<head::kTmemCols>(tmem);
 }
 
@@ -578,24 +603,6 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
-
-// Phase timestamps of CTA 0 (diagnostics; compiled in only with -DSANERF_HEAD_TRACE): [thread 0][tile 0..3][11]
-#ifdef SANERF_HEAD_TRACE
-static int g_head_dbg_host = 0;
-#define HEAD_DBG(bit) ((p.dbg & (bit)) != 0)
-__device__ long long g_head_trace[2 * 4 * 16];
-__device__ long long g_head_marks[8];          // CTA 0, thread 0: entry, prologue done, loop done, exit
-#define HEAD_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_marks[i] = clock64(); } while (0)
-#define HEAD_TRACE(slot)                                                                                   \
-    do {                                                                                                   \
-        if (blockIdx.x == 0 && it < 4 && (tid == 0 || tid == 128))                                         \
-            g_head_trace[((tid == 0 ? 0 : 1) * 4 + it) * 16 + (slot)] = clock64();                          \
-    } while (0)
-#else
-#define HEAD_TRACE(slot) do {} while (0)
-#define HEAD_MARK(i) do {} while (0)
-#define HEAD_DBG(bit) false
-#endif
 
 // Hash-grid scatter of ONE level for this thread's sample, fused into the backward (replaces the matching slice of
 // sanerf_grid_encode_backward): the two gradient values come straight from tensor memory, consecutive lanes that share
