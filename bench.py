@@ -382,7 +382,8 @@ def bench_rgb(ctx):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": rgb_config(world),
         "execution": ("hand-scheduled step replayed as one CUDA graph per step" if plan is not None else "autograd"),
-        "ms_per_step_median": statistics.median(per_step), "clocks": clocks,
+        "ms_per_step_median": statistics.median(per_step), "ms_per_step_each": [round(x, 4) for x in per_step],
+        "clocks": clocks,
         "e2e": {"value": world * N_RAYS * args.steps / (e2e_ms / 1e3), "unit": "rays/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": 3 * N_RAYS * 3 * 4, "d2h_bytes_per_step": 4, "last_loss": last_loss[0]},
         "gpu_launches": launches,

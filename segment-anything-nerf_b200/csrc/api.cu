@@ -42,3 +42,24 @@ extern "C" const char* sanerf_status_string(int status) {
         default: return "unknown status";
     }
 }
+
+#ifdef SANERF_HEAD_TRACE
+#include <vector>
+namespace sanerf {
+static std::vector<void (*)(StampBuf*)>& stamp_setters() { static std::vector<void (*)(StampBuf*)> v; return v; }
+void register_stamp_tu(void (*set)(StampBuf*)) { stamp_setters().push_back(set); }
+}  // namespace sanerf
+// op 0: allocate the stamp buffer and hand it to every translation unit; 1: reset; 2: copy {count, stamps} to `out`
+extern "C" __attribute__((visibility("default"))) int sanerf_debug_stamps(int op, void* out) {
+    static sanerf::StampBuf* buf = nullptr;
+    if (op == 0) {
+        if (buf == nullptr && cudaMalloc(&buf, sizeof(sanerf::StampBuf)) != cudaSuccess) return 1;
+        cudaMemset(buf, 0, sizeof(sanerf::StampBuf));
+        for (auto set : sanerf::stamp_setters()) set(buf);
+        return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
+    }
+    if (buf == nullptr) return 1;
+    if (op == 1) return cudaMemset(buf, 0, 8) == cudaSuccess ? 0 : 1;
+    return cudaMemcpy(out, buf, sizeof(sanerf::StampBuf), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
+#endif

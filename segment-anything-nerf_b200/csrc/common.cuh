@@ -46,12 +46,51 @@ inline int check_launch(const char* what) {
 // (griddepcontrol.launch_dependents at kernel entry, -DSANERF_PDL_EARLY_TRIGGER) was measured slower (0.908 ms): parked
 // CTAs take the thread slots the parallel branches of the step need.  A kernel launched through launch_pdl MUST call
 // pdl_begin() before touching memory.  SANERF_PDL=0 in the environment disables the launch attribute.
+#ifdef SANERF_HEAD_TRACE
+// Diagnostic builds only: block 0 of every launch stamps %globaltimer when it passes griddepcontrol.wait, i.e. when the kernel
+// really starts inside a replayed CUDA graph (where events cannot bracket it).  id = source line of the pdl_begin() call * 64 +
+// a 6-bit hash of the file name; tools/graph_timeline.py maps ids back to kernels.  The buffer pointer is a per-translation-unit
+// __device__ variable (no relocatable device code in this build), set through a registry of per-unit setters (api.cu).
+struct KernelStamp { unsigned long long t; unsigned int id, pad; };
+struct StampBuf { unsigned int count, pad; KernelStamp s[4096]; };
+static __device__ StampBuf* tu_stamp_buf = nullptr;
+void register_stamp_tu(void (*set)(StampBuf*));
+namespace {
+inline void set_tu_stamp_buf(StampBuf* b) { cudaMemcpyToSymbol(tu_stamp_buf, &b, sizeof(b)); }
+struct StampReg { StampReg() { register_stamp_tu(&set_tu_stamp_buf); } };
+static StampReg stamp_reg_instance;
+}  // namespace
+__host__ __device__ constexpr unsigned int file_tag(const char* f) {
+    unsigned int h = 0;
+    for (int i = 0; f[i] != 0; ++i) h = (f[i] == '/') ? 0u : h * 31u + (unsigned char)f[i];      // hash of the base name
+    return h & 63u;
+}
+__device__ __forceinline__ void stamp_start(unsigned int id) {
+    StampBuf* b = tu_stamp_buf;
+    if (b != nullptr) {
+        const unsigned int slot = atomicAdd(&b->count, 1u);
+        if (slot < 4096u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            b->s[slot].t = t;
+            b->s[slot].id = id;
+        }
+    }
+}
+#define pdl_begin()                                                                                                      \
+    do {                                                                                                                 \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                                                               \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0)               \
+            ::sanerf::stamp_start((unsigned int)__LINE__ * 64u + ::sanerf::file_tag(__FILE__));                          \
+    } while (0)
+#else
 __device__ __forceinline__ void pdl_begin() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef SANERF_PDL_EARLY_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+#endif
 
 bool pdl_enabled();
 

@@ -14,7 +14,7 @@ model = NeRFNetwork(default_opt()).to(dev)
 trainer = RGBTrainer(model, use_graph=False)
 o, d, rgb = bench.synthetic_rays(bench.N_RAYS, dev, 1234)
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-for i in range(5):
+for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 5):      # warm-up steps (training progress changes the timings)
     trainer.step(o, d, rgb)
 torch.cuda.synchronize()
 flush.fill_(1.0)
