@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(kPropThreads, 2) prop_backward_kernel(const Pr
     __shared__ LevelGeom<3> s_geo[L];
     __shared__ uint32_t s_base[L];
     __shared__ __align__(16) float s_rows[kWarps * 32 * kPropRow];
+    __shared__ uint32_t s_next;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_next = 0u;
     for (uint32_t i = tid; i < kPropHidden * IN; i += blockDim.x) s_w1[i] = __ldg(p.w1 + i);
     if (tid < kPropHidden) s_w2[tid] = __ldg(p.w2 + tid);
     if (tid >= 32 && tid < 32 + L) {
@@ -158,8 +160,20 @@ __global__ void __launch_bounds__(kPropThreads, 2) prop_backward_kernel(const Pr
     for (uint32_t q = 0; q < L; ++q) acc1[q] = 0.0f;
     const float* __restrict__ table = p.table;
 
-    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint32_t b = tile * kPropThreads + tid;
+    // Work distribution inside the CTA is dynamic: its tiles (blockIdx.x, + gridDim.x, ...) are 8 slices of 32 samples each, and
+    // every warp pulls the next slice from a shared counter.  Samples are ray-ordered (a tile = 2-4 whole rays) and the skip below
+    // depends on the position along the ray: with the fixed assignment warp w <-> slice w the same warps of a CTA did all the work
+    // while the others waited at the final barrier (ncu source page: 42-64 % of all warp samples were stall_barrier at the first
+    // instruction behind it).
+    const uint32_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t my_slices = my_tiles * kWarps;
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(&s_next, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= my_slices) break;
+        const uint32_t tile = blockIdx.x + (idx / kWarps) * gridDim.x;
+        const uint32_t b = tile * kPropThreads + (idx % kWarps) * 32u + lane;
         const bool live = b < p.B;
         // Most proposal samples receive no gradient at all (the proposal loss only pushes where the final level's
         // weight exceeds the proposal's bound): a warp whose 32 incoming gradients are all zero contributes nothing to
