@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropPa
         s_base[threadIdx.x - 32] = (uint32_t)__ldg(p.offsets + (threadIdx.x - 32));
     }
     __syncthreads();
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.B) return;
+    // persistent over 256-sample tiles: the weights / geometry prologue (every thread waits for five threads' dependent offset
+    // loads) is paid once per resident CTA instead of once per tile (ncu: 5.5 % of the warp samples sat at that barrier)
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < p.B; b += gridDim.x * blockDim.x) {
     float x[3];
 #pragma unroll
     for (uint32_t d = 0; d < 3; ++d) x[d] = __ldg(p.x01 + (size_t)b * 3 + d);
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(kPropThreads) prop_forward_kernel(const PropPa
         pre = __fmaf_rn(s_w2[j], fmaxf(h, 0.0f), pre);
     }
     sigma[b] = expf(pre);                    // trunc_exp forward (activation.py:10)
+    }
 }
 
 // Backward.  One thread = one sample (persistent grid-stride over 256-sample tiles); everything is warp-synchronous,
@@ -349,7 +351,10 @@ extern "C" int sanerf_prop_density_forward(const float* x01, const float* table,
     if (rc != SANERF_OK) return rc;
     SANERF_REQUIRE_PTR(sigma);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const uint32_t blocks = div_up(B, kPropThreads);
+    const uint32_t tiles = div_up(B, kPropThreads);
+    static const uint32_t per_sm = [] { const char* e = getenv("SANERF_PROP_FWD_CTAS_PER_SM"); return e ? (uint32_t)atoi(e) : 4u; }();
+    const uint32_t cap = (uint32_t)kNumSMs * per_sm;
+    const uint32_t blocks = tiles < cap ? tiles : cap;
     SANERF_PROP_DISPATCH(L, (SANERF_LAUNCH((prop_forward_kernel<LL>), blocks, kPropThreads, 0, st, p, sigma, enc_out)));
     return check_launch("prop_forward_kernel");
 }
