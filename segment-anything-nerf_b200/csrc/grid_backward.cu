@@ -40,6 +40,15 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams 
     // every sample's eight updates one by one: 360 us of the 977 us cfg5 scatter (T = 2^22 fp16, 2^20 samples).
     constexpr bool kAggregate = ((1u << D) * CH <= 16u) && (CH == C);
     const uint32_t lane = threadIdx.x & 31u;
+    // geometry of this CTA's G levels, once per CTA (evaluated per thread it was ~200 of a warp's ~1450 instructions in a kernel
+    // whose warps wait for an issue slot a third of the time, and put two dependent offset loads in front of everything)
+    __shared__ LevelGeom<D> s_geo[G];
+    __shared__ uint32_t s_base[G];
+    if (threadIdx.x < G && level0 + threadIdx.x < p.L) {
+        s_geo[threadIdx.x] = level_geometry<D>(p.offsets, level0 + threadIdx.x, p.S, p.H, p.gridtype);
+        s_base[threadIdx.x] = (uint32_t)__ldg(p.offsets + level0 + threadIdx.x);
+    }
+    __syncthreads();
 
     float x[D];
     bool ok = b < p.B;
@@ -59,9 +68,9 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const GridBwdParams 
         if (level >= p.max_level) break;
         const T* src = p.blc ? grad + ((size_t)b * p.L + level) * C
                              : grad + ((size_t)level * p.B + b) * C;
-        const LevelGeom<D> geo = level_geometry<D>(p.offsets, level, p.S, p.H, p.gridtype);
+        const LevelGeom<D> geo = s_geo[g];
         const Cell<D> cell = locate<D>(geo, x, p.align_corners != 0, p.interp);
-        T* __restrict__ slice = gtab + (size_t)(uint32_t)__ldg(p.offsets + level) * C;
+        T* __restrict__ slice = gtab + (size_t)s_base[g] * C;
         if constexpr (kAggregate) {
             float gv[CH];
 #pragma unroll
