@@ -249,16 +249,20 @@ class FusedRGBStep:
                                                       P["weights"].data_ptr(), P["T"], N, lam_p, self.loss.data_ptr(),
                                                       P["g_weights"].data_ptr(), st2)
                     check(rc, "proposal_loss")
+                # both (short) compositing backwards first: they fit into the window before the field-head backward takes every SM,
+                # so that only the two density backwards are left for the tail behind the hash-grid scatter
+                for li in (1, 0):
+                    P = self.lv[li]
+                    with span("composite_backward", N=N, T=P["T"], C=0):
+                        rc = lib.sanerf_composite_backward(P["sigma"].data_ptr(), P["deltas"].data_ptr(), P["t_mid"].data_ptr(),
+                                                           None, 0, None, N, P["T"], 0, self.opaque, 0.0, P["weights"].data_ptr(),
+                                                           P["g_weights"].data_ptr(), None, None, None, P["g_sigma"].data_ptr(),
+                                                           None, 0, st2)
+                    check(rc, "composite_backward")
                 for li in (1, 0):
                     P = self.lv[li]
                     Tp = P["T"]
                     enc, mlp = m.prop_encoders[li], m.prop_mlp[li]
-                    with span("composite_backward", N=N, T=Tp, C=0):
-                        rc = lib.sanerf_composite_backward(P["sigma"].data_ptr(), P["deltas"].data_ptr(), P["t_mid"].data_ptr(),
-                                                           None, 0, None, N, Tp, 0, self.opaque, 0.0, P["weights"].data_ptr(),
-                                                           P["g_weights"].data_ptr(), None, None, None, P["g_sigma"].data_ptr(),
-                                                           None, 0, st2)
-                    check(rc, "composite_backward")
                     with span("prop_density_backward", B=N * Tp, L=enc.num_levels):
                         rc = lib.sanerf_prop_density_backward(P["x01"].data_ptr(), enc.embeddings.data_ptr(),
                                                               enc.offsets.data_ptr(), mlp.net[0].weight.data_ptr(),
