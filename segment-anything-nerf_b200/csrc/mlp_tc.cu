@@ -742,7 +742,6 @@ __global__ void __launch_bounds__(head::kBwdThreads, 1) head_backward_lockstep_k
 #pragma unroll
         for (uint32_t j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.0f;
         put_tmem16(lane_base, c0, v, split);
-#pragma unroll
         if (!HEAD_DBG(4))
 #pragma unroll
         for (uint32_t j = 0; j < 16; j += 4) put_mn(bufB, bufB + kMn64, row, c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3], split);
@@ -1163,7 +1162,6 @@ __global__ void __launch_bounds__(head::kBwdThreads2, 1) head_backward_kernel(co
 
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < tiles; ++it, tile += gridDim.x) {
-        const uint32_t first = (it == 0) ? 0u : 1u;
         const uint32_t next = tile + gridDim.x;
         HEAD_TRACE(0);
         // ---- G3 -> TMEM A planes; DG2 = G3 W3 starts before anything else of the tile is staged
